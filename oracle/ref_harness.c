@@ -1,0 +1,164 @@
+/*
+ * oracle/ref_harness.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Compiles the UNMODIFIED reference translation unit (/root/reference/main.c,
+ * found through -I at build time; never copied into this repository) together
+ * with the single-rank MPI shim (oracle/shim/mpi.h) and exports a handful of
+ * thin entry points so that tests and bench.py's cpu_baseline leg can drive
+ * the reference's own hot-path functions:
+ *
+ *   stencil_apply  main.c:3648     mg_vcycle   main.c:4831
+ *   pois_op        main.c:4282     pois_solve  main.c:4875
+ *   advdiff        main.c:5027     projection  main.c:5828
+ *
+ * Every symbol of the reference is file-static, hence the #include of the
+ * whole TU.  Nothing of the product (cup3d_b200/) may link or load this.
+ */
+#define main cup3d_reference_main
+#include "main.c"
+#undef main
+
+#include <omp.h>
+#include <time.h>
+#include <unistd.h>
+
+#define API __attribute__((visibility("default")))
+
+static int ref_ready;
+
+/* argv = the reference's own "-key value" command line (without argv[0]);
+ * tabdir = directory holding lab_ss*_t*.bin (the reference opens them in cwd,
+ * main.c:3350-3353). */
+API int ref_init(int argc, char **argv, const char *tabdir) {
+  char cwd[4096];
+  char **av;
+  char *content;
+  int i;
+  if (ref_ready)
+    return 1;
+  av = malloc((argc + 2) * sizeof *av);
+  av[0] = "ref";
+  for (i = 0; i < argc; i++)
+    av[i + 1] = argv[i];
+  av[argc + 1] = NULL;
+  sim.comm = MPI_COMM_WORLD;
+  sim.rank = 0;
+  sim.size = 1;
+  content = param_parse(argc + 1, av);
+  sta_init();
+  if (getcwd(cwd, sizeof cwd) == NULL)
+    return 2;
+  if (chdir(tabdir) != 0)
+    return 3;
+  lab_tables();
+  if (chdir(cwd) != 0)
+    return 4;
+  pois_init();
+  fish_parse(content);
+  mesh_init();
+  free(av);
+  ref_ready = 1;
+  return 0;
+}
+
+API long long ref_nblk(void) { return sta.nblk; }
+API int ref_threads(void) { return omp_get_max_threads(); }
+
+/* out: 5 ints per block (level, ix, iy, iz, 0) and h, origin[3] */
+API void ref_blocks(int *ib, double *rb) {
+  long long i;
+  for (i = 0; i < sta.nblk; i++) {
+    struct Blk *b = &sta.blk[i];
+    ib[4 * i + 0] = b->level;
+    ib[4 * i + 1] = b->ix;
+    ib[4 * i + 2] = b->iy;
+    ib[4 * i + 3] = b->iz;
+    rb[4 * i + 0] = b->h;
+    rb[4 * i + 1] = b->origin[0];
+    rb[4 * i + 2] = b->origin[1];
+    rb[4 * i + 3] = b->origin[2];
+  }
+}
+
+/* raw state: sta.fld is [nblk][F_N][512] (main.c:55-58,131-132) */
+API void ref_state_get(double *out) { memcpy(out, sta.fld, (size_t)sta.nblk * BLK_S * sizeof(Real)); }
+API void ref_state_set(const double *in) { memcpy(sta.fld, in, (size_t)sta.nblk * BLK_S * sizeof(Real)); }
+
+API void ref_set_scalars(double dt, double nu, double uinfx, double uinfy, double uinfz, int step,
+                         int mean_constraint, double ptol, double ptol_rel) {
+  sta.dt = dt;
+  sim.nu = nu;
+  sta.uinf[0] = uinfx;
+  sta.uinf[1] = uinfy;
+  sta.uinf[2] = uinfz;
+  sta.step = step;
+  sim.mean_constraint = mean_constraint;
+  sim.ptol = ptol;
+  sim.ptol_rel = ptol_rel;
+}
+
+API void ref_mg_vcycle(double *in, double *out) { mg_vcycle(in, out); }
+API void ref_pois_op(double *in, double *out) { pois_op(in, out); }
+API void ref_pois_solve(void) { pois_solve(); }
+API void ref_advdiff(void) { advdiff(); }
+API void ref_projection(void) { projection(); }
+
+/* 0 lhs, 1 mg, 2 advdiff, 3 prhs, 4 divp, 5 gradp, 6 vort, 7 q */
+API int ref_stencil(int id) {
+  struct Stencil *tab[] = {&st_lhs, &st_mg, &st_advdiff, &st_prhs, &st_divp, &st_gradp, &st_vort, &st_q};
+  if (id < 0 || id >= (int)(sizeof tab / sizeof *tab))
+    return 1;
+  stencil_apply(tab[id]);
+  return 0;
+}
+
+/* Weighted dot used by the Krylov solver (main.c:4854); builds pois.hw first. */
+API double ref_pois_dot(double *a, double *b) {
+  long long N = sta.nblk * BS3, i;
+  pois_alloc(N);
+  for (i = 0; i < sta.nblk; i++)
+    pois.hw[i] = 1 / (sta.blk[i].h * sta.blk[i].h * sta.blk[i].h);
+  return pois_dot(a, b, N);
+}
+
+/* the block-local FDM inverse (main.c:4368) on one 512-vector */
+API void ref_pre_blk(double *src, double *dst, double invh) {
+  Real a[BS3], b[BS3];
+  pre_blk(src, dst, invh, a, b);
+}
+
+static double now(void) {
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return t.tv_sec + 1e-9 * t.tv_nsec;
+}
+
+/* time n V-cycles (after w warm-ups); returns seconds for the n cycles */
+API double ref_time_vcycle(double *in, double *out, int w, int n) {
+  int k;
+  double t0;
+  for (k = 0; k < w; k++)
+    mg_vcycle(in, out);
+  t0 = now();
+  for (k = 0; k < n; k++)
+    mg_vcycle(in, out);
+  return now() - t0;
+}
+
+API double ref_time_stencil(int id, int w, int n) {
+  int k;
+  double t0;
+  for (k = 0; k < w; k++)
+    ref_stencil(id);
+  t0 = now();
+  for (k = 0; k < n; k++)
+    ref_stencil(id);
+  return now() - t0;
+}
+
+/* one mesh adaptation pass with the reference's own tagging (main.c:4012ff) */
+API void ref_mesh_adapt(double rtol, double ctol) {
+  sim.rtol = rtol;
+  sim.ctol = ctol;
+  mesh_adapt();
+}
