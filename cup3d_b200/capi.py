@@ -1,0 +1,234 @@
+"""ctypes binding of libcup3d_b200.so -- the C ABI of include/cup3d_b200.h.
+
+This is the reference-side binding a maintainer would write (see
+INTEGRATION.md); it contains no numerics.  There is no CPU fallback: if the
+shared library is missing or no CUDA device is present every call raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcup3d_b200.so")
+
+BS3 = 512
+F_CHI, F_PRES, F_VEL, F_TMP, F_LHS, F_N = 0, 1, 2, 5, 8, 9
+ST_LHS, ST_MG, ST_ADVDIFF, ST_PRHS, ST_DIVP, ST_GRADP = range(6)
+
+
+class CupBlk(C.Structure):  # struct Blk, reference main.c:59-63
+    _fields_ = [("level", C.c_int), ("ix", C.c_int), ("iy", C.c_int), ("iz", C.c_int), ("Z", C.c_longlong),
+                ("h", C.c_double), ("origin", C.c_double * 3)]
+
+
+class CupParams(C.Structure):
+    _fields_ = [("dt", C.c_double), ("nu", C.c_double), ("uinf", C.c_double * 3), ("step", C.c_int),
+                ("mean_constraint", C.c_int), ("ptol", C.c_double), ("ptol_rel", C.c_double)]
+
+
+class CupSolveInfo(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("restarts", C.c_int), ("residual", C.c_double),
+                ("rhs_norm", C.c_double), ("vcycles", C.c_int)]
+
+
+# every symbol include/cup3d_b200.h declares: name -> (restype, argtypes)
+_vp, _i, _ll, _dp = C.c_void_p, C.c_int, C.c_longlong, C.POINTER(C.c_double)
+SYMBOLS = {
+    "cup_last_error": (C.c_char_p, []),
+    "cup_version": (_i, []),
+    "cup_create": (_i, [C.POINTER(_vp), _i, _i]),
+    "cup_destroy": (_i, [_vp]),
+    "cup_set_stream": (_i, [_vp, _vp]),
+    "cup_set_params": (_i, [_vp, C.POINTER(CupParams)]),
+    "cup_synchronize": (_i, [_vp]),
+    "cup_mesh_upload": (_i, [_vp, C.POINTER(CupBlk), _ll, C.POINTER(_i), _i]),
+    "cup_nblk": (_ll, [_vp]),
+    "cup_nslot": (_ll, [_vp]),
+    "cup_mg_levels": (_i, [_vp]),
+    "cup_mg_nact": (_ll, [_vp, _i]),
+    "cup_state_h2d": (_i, [_vp, _vp, _i, _i]),
+    "cup_state_d2h": (_i, [_vp, _vp, _i, _i]),
+    "cup_state_dev": (_vp, [_vp, _i]),
+    "cup_stencil_apply": (_i, [_vp, _i]),
+    "cup_stencil_run": (_i, [_vp, _i, C.POINTER(_ll), _ll]),
+    "cup_pois_op": (_i, [_vp, _vp, _vp]),
+    "cup_mg_vcycle": (_i, [_vp, _vp, _vp]),
+    "cup_pois_op_dev": (_i, [_vp, _vp, _vp]),
+    "cup_mg_vcycle_dev": (_i, [_vp, _vp, _vp]),
+    "cup_pois_dot_dev": (_i, [_vp, _vp, _vp, _dp]),
+    "cup_pois_solve": (_i, [_vp, C.POINTER(CupSolveInfo)]),
+    "cup_advdiff": (_i, [_vp]),
+    "cup_projection": (_i, [_vp, C.POINTER(CupSolveInfo)]),
+    "cup_comm_init": (_i, [_vp, _i, _i, _vp, C.c_size_t]),
+    "cup_nccl_unique_id": (_i, [_vp, C.c_size_t]),
+    "cup_kernel_launches": (_ll, [_vp]),
+    "cup_time_smooth": (_i, [_vp, _i, _i, C.POINTER(C.c_float)]),
+    "cup_mg_smooth_dev": (_i, [_vp, _i, _i, _vp, _vp]),
+    "cup_mg_array": (_vp, [_vp, _i]),
+}
+
+_lib = None
+
+
+class CupError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libcup3d_b200.so (built by __graft_entry__.build()).  Fails loudly."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CupError("libcup3d_b200.so not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise CupError("cup3d_b200 error %d: %s" % (rc, lib().cup_last_error().decode()))
+
+
+def blocks_to_struct(ib, rb):
+    """(int [n,4] level,ix,iy,iz ; float [n,4] h,origin) -> ctypes array of CupBlk"""
+    n = len(ib)
+    arr = (CupBlk * n)()
+    a = np.frombuffer(arr, dtype=np.dtype([("level", "i4"), ("ix", "i4"), ("iy", "i4"), ("iz", "i4"), ("Z", "i8"),
+                                           ("h", "f8"), ("origin", "f8", 3)]))
+    a["level"], a["ix"], a["iy"], a["iz"] = ib[:, 0], ib[:, 1], ib[:, 2], ib[:, 3]
+    a["Z"] = np.arange(n)
+    a["h"] = rb[:, 0]
+    a["origin"] = rb[:, 1:4]
+    return arr
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):  # torch tensor (host pinned or device)
+        return a.data_ptr()
+    return a
+
+
+class Context:
+    """One device context == the reference's global `sim`/`sta`/`mg` state for one rank."""
+
+    def __init__(self, device=0, real_bytes=8):
+        self.L = lib()
+        h = _vp()
+        check(self.L.cup_create(C.byref(h), device, real_bytes))
+        self.h = h
+        self.real_bytes = real_bytes
+        self.params = CupParams(dt=0.0, nu=1e-3, uinf=(C.c_double * 3)(0, 0, 0), step=0, mean_constraint=2,
+                                ptol=1e-6, ptol_rel=1e-4)
+
+    def close(self):
+        if self.h:
+            self.L.cup_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, stream_ptr):
+        check(self.L.cup_set_stream(self.h, stream_ptr))
+
+    def set_params(self, **kw):
+        for k, v in kw.items():
+            if k == "uinf":
+                self.params.uinf = (C.c_double * 3)(*v)
+            else:
+                setattr(self.params, k, v)
+        check(self.L.cup_set_params(self.h, C.byref(self.params)))
+
+    def mesh_upload(self, ib, rb, bpd, level_max):
+        arr = blocks_to_struct(np.asarray(ib), np.asarray(rb))
+        b = (C.c_int * 3)(*bpd)
+        check(self.L.cup_mesh_upload(self.h, arr, len(ib), b, level_max))
+
+    @property
+    def nblk(self):
+        return int(self.L.cup_nblk(self.h))
+
+    @property
+    def nslot(self):
+        return int(self.L.cup_nslot(self.h))
+
+    def mg_nact(self, level):
+        return int(self.L.cup_mg_nact(self.h, level))
+
+    def mg_levels(self):
+        return int(self.L.cup_mg_levels(self.h))
+
+    def state_h2d(self, fld, f0=0, nc=F_N):
+        assert fld.dtype == np.float64 and fld.shape == (self.nblk, F_N, BS3) and fld.flags["C_CONTIGUOUS"]
+        check(self.L.cup_state_h2d(self.h, _ptr(fld), f0, nc))
+
+    def state_d2h(self, fld, f0=0, nc=F_N):
+        assert fld.dtype == np.float64 and fld.shape == (self.nblk, F_N, BS3) and fld.flags["C_CONTIGUOUS"]
+        check(self.L.cup_state_d2h(self.h, _ptr(fld), f0, nc))
+
+    def state_dev(self, f):
+        return self.L.cup_state_dev(self.h, f)
+
+    def stencil_apply(self, sid):
+        check(self.L.cup_stencil_apply(self.h, sid))
+
+    def pois_op(self, x, out=None):
+        out = np.empty_like(x) if out is None else out
+        check(self.L.cup_pois_op(self.h, _ptr(x), _ptr(out)))
+        return out
+
+    def mg_vcycle(self, x, out=None):
+        out = np.empty_like(x) if out is None else out
+        check(self.L.cup_mg_vcycle(self.h, _ptr(x), _ptr(out)))
+        return out
+
+    def pois_op_dev(self, d_in, d_out):
+        check(self.L.cup_pois_op_dev(self.h, _ptr(d_in), _ptr(d_out)))
+
+    def mg_vcycle_dev(self, d_in, d_out):
+        check(self.L.cup_mg_vcycle_dev(self.h, _ptr(d_in), _ptr(d_out)))
+
+    def pois_dot_dev(self, a, b):
+        r = C.c_double()
+        check(self.L.cup_pois_dot_dev(self.h, _ptr(a), _ptr(b), C.byref(r)))
+        return r.value
+
+    def pois_solve(self):
+        info = CupSolveInfo()
+        check(self.L.cup_pois_solve(self.h, C.byref(info)))
+        return info
+
+    def advdiff(self):
+        check(self.L.cup_advdiff(self.h))
+
+    def projection(self):
+        info = CupSolveInfo()
+        check(self.L.cup_projection(self.h, C.byref(info)))
+        return info
+
+    def synchronize(self):
+        check(self.L.cup_synchronize(self.h))
+
+    def kernel_launches(self):
+        return int(self.L.cup_kernel_launches(self.h))
+
+    def time_smooth(self, level, reps):
+        ms = C.c_float()
+        check(self.L.cup_time_smooth(self.h, level, reps, C.byref(ms)))
+        return ms.value
+
+    def mg_smooth_dev(self, level, n, d_u, d_f):
+        check(self.L.cup_mg_smooth_dev(self.h, level, n, _ptr(d_u), _ptr(d_f)))

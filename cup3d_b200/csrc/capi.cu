@@ -1,0 +1,280 @@
+// capi.cu -- the extern "C" boundary declared in include/cup3d_b200.h.
+#include <mutex>
+
+#include "blas_kernels.cuh"
+#include "cup_internal.h"
+
+namespace cup {
+
+static thread_local std::string g_err;
+
+void set_error(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+template <typename Real>
+__global__ void k_cvt_in(Real *__restrict__ dst, const double *__restrict__ src, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = (Real)src[i];
+}
+template <typename Real>
+__global__ void k_cvt_out(double *__restrict__ dst, const Real *__restrict__ src, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = (double)src[i];
+}
+
+static int alloc_state(CupCtx *c) {
+  const size_t bytes = (size_t)c->nblk * 512 * (size_t)c->real_bytes;
+  for (int f = 0; f < CUP_F_N; f++) {
+    cudaFree(c->state[f]);
+    c->state[f] = nullptr;
+    CUP_CUDA(cudaMalloc(&c->state[f], bytes));
+    CUP_CUDA(cudaMemset(c->state[f], 0, bytes));
+  }
+  cudaFree(c->tmp_in);
+  cudaFree(c->tmp_out);
+  cudaFree(c->p_old);
+  cudaFree(c->tmp_stage);
+  c->tmp_in = c->tmp_out = c->p_old = c->tmp_stage = nullptr;
+  // staging for host flat vectors: always room for doubles
+  CUP_CUDA(cudaMalloc(&c->tmp_in, (size_t)c->nblk * 512 * 8));
+  CUP_CUDA(cudaMalloc(&c->tmp_out, (size_t)c->nblk * 512 * 8));
+  CUP_CUDA(cudaMalloc(&c->p_old, bytes));
+  if (c->real_bytes == 4)
+    CUP_CUDA(cudaMalloc(&c->tmp_stage, (size_t)c->nblk * 512 * 8));
+  return CUP_OK;
+}
+
+// host flat vector of doubles -> device vector of Real (dst may alias stage for fp64)
+static int vec_h2d(CupCtx *c, void *d_dst, const double *h_src, long long n) {
+  if (c->real_bytes == 8) {
+    CUP_CUDA(cudaMemcpyAsync(d_dst, h_src, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    CUP_CUDA(cudaMemcpyAsync(c->tmp_stage, h_src, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    k_cvt_in<float><<<c->num_sms * 8, 256, 0, c->stream>>>((float *)d_dst, (const double *)c->tmp_stage, n);
+    c->launches++;
+  }
+  return CUP_OK;
+}
+
+}  // namespace cup
+
+using namespace cup;
+
+extern "C" {
+
+const char *cup_last_error(void) { return g_err.c_str(); }
+int cup_version(void) { return 100; }
+
+int cup_create(CupCtx **out, int device, int real_bytes) {
+  if (!out || (real_bytes != 8 && real_bytes != 4)) {
+    set_error("cup_create: real_bytes must be 8 or 4");
+    return CUP_ERR_ARG;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    // no CPU fallback: the product path is CUDA only
+    set_error("cup_create: no CUDA device (%s)", cudaGetErrorString(e));
+    return CUP_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) {
+    set_error("cup_create: device %d of %d", device, ndev);
+    return CUP_ERR_ARG;
+  }
+  CUP_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUP_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    set_error("cup_create: device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major,
+              prop.minor);
+    return CUP_ERR_CUDA;
+  }
+  CupCtx *c = new CupCtx;
+  c->device = device;
+  c->real_bytes = real_bytes;
+  c->num_sms = prop.multiProcessorCount;
+  c->prm.mean_constraint = 2;
+  c->prm.ptol = 1e-6;
+  c->prm.ptol_rel = 1e-4;
+  c->prm.nu = 1e-3;
+  CUP_CUDA(cudaMalloc((void **)&c->d_scal, SCAL_N * sizeof(double)));
+  CUP_CUDA(cudaMemset(c->d_scal, 0, SCAL_N * sizeof(double)));
+  CUP_CUDA(cudaMallocHost((void **)&c->h_scal, SCAL_N * sizeof(double)));
+  *out = c;
+  return CUP_OK;
+}
+
+int cup_destroy(CupCtx *c) {
+  if (!c)
+    return CUP_OK;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  free_krylov(c);
+  free_mesh(c);
+  for (int f = 0; f < CUP_F_N; f++)
+    cudaFree(c->state[f]);
+  cudaFree(c->u1_leaf);
+  cudaFree(c->u0_x);
+  cudaFree(c->u1_x);
+  cudaFree(c->f_x);
+  cudaFree(c->us_x);
+  cudaFree(c->tmp_in);
+  cudaFree(c->tmp_out);
+  cudaFree(c->p_old);
+  cudaFree(c->tmp_stage);
+  cudaFree(c->d_W);
+  cudaFree(c->d_hw);
+  cudaFree(c->d_scal);
+  cudaFreeHost(c->h_scal);
+  delete c;
+  return CUP_OK;
+}
+
+int cup_set_stream(CupCtx *c, void *stream) {
+  c->stream = (cudaStream_t)stream;
+  return CUP_OK;
+}
+
+int cup_set_params(CupCtx *c, const CupParams *p) {
+  if (!p) {
+    set_error("cup_set_params: null");
+    return CUP_ERR_ARG;
+  }
+  c->prm = *p;
+  return CUP_OK;
+}
+
+int cup_synchronize(CupCtx *c) {
+  CUP_CUDA(cudaStreamSynchronize(c->stream));
+  return CUP_OK;
+}
+
+int cup_mesh_upload(CupCtx *c, const CupBlk *blk, long long n, const int bpd[3], int level_max) {
+  CUP_CUDA(cudaSetDevice(c->device));
+  CUP_CUDA(cudaStreamSynchronize(c->stream));
+  free_krylov(c);
+  CUP_TRY(build_mesh(c, blk, n, bpd, level_max));
+  CUP_TRY(alloc_state(c));
+  CUP_TRY(mg_setup(c));
+  return CUP_OK;
+}
+
+long long cup_nblk(const CupCtx *c) { return c->nblk; }
+long long cup_nslot(const CupCtx *c) { return c->nslot; }
+int cup_mg_levels(const CupCtx *c) { return c->top + 1; }
+long long cup_mg_nact(const CupCtx *c, int level) {
+  return (level < 0 || level > c->top) ? -1 : (long long)c->lv[level].act.size();
+}
+
+int cup_state_h2d(CupCtx *c, const double *h_fld, int f0, int nc) {
+  if (f0 < 0 || nc < 1 || f0 + nc > CUP_F_N || c->nblk == 0) {
+    set_error("cup_state_h2d: bad field range %d+%d", f0, nc);
+    return CUP_ERR_ARG;
+  }
+  const size_t spitch = (size_t)CUP_F_N * 512 * 8, row = 512 * 8;
+  for (int f = f0; f < f0 + nc; f++) {
+    void *dst = c->real_bytes == 8 ? c->state[f] : c->tmp_stage;
+    CUP_CUDA(cudaMemcpy2DAsync(dst, row, h_fld + (size_t)f * 512, spitch, row, (size_t)c->nblk,
+                               cudaMemcpyHostToDevice, c->stream));
+    if (c->real_bytes == 4) {
+      k_cvt_in<float><<<c->num_sms * 8, 256, 0, c->stream>>>((float *)c->state[f], (const double *)c->tmp_stage,
+                                                             c->nblk * 512);
+      c->launches++;
+    }
+  }
+  CUP_CUDA(cudaStreamSynchronize(c->stream));
+  return CUP_OK;
+}
+
+int cup_state_d2h(CupCtx *c, double *h_fld, int f0, int nc) {
+  if (f0 < 0 || nc < 1 || f0 + nc > CUP_F_N || c->nblk == 0) {
+    set_error("cup_state_d2h: bad field range %d+%d", f0, nc);
+    return CUP_ERR_ARG;
+  }
+  const size_t dpitch = (size_t)CUP_F_N * 512 * 8, row = 512 * 8;
+  for (int f = f0; f < f0 + nc; f++) {
+    const void *src = c->state[f];
+    if (c->real_bytes == 4) {
+      k_cvt_out<float><<<c->num_sms * 8, 256, 0, c->stream>>>((double *)c->tmp_stage, (const float *)c->state[f],
+                                                              c->nblk * 512);
+      c->launches++;
+      src = c->tmp_stage;
+    }
+    CUP_CUDA(cudaMemcpy2DAsync(h_fld + (size_t)f * 512, dpitch, src, row, row, (size_t)c->nblk,
+                               cudaMemcpyDeviceToHost, c->stream));
+    if (c->real_bytes == 4)
+      CUP_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  CUP_CUDA(cudaStreamSynchronize(c->stream));
+  return CUP_OK;
+}
+
+void *cup_state_dev(CupCtx *c, int f) { return (f < 0 || f >= CUP_F_N) ? nullptr : c->state[f]; }
+
+int cup_pois_op_dev(CupCtx *c, const void *d_in, void *d_out) { return pois_op_dev(c, d_in, d_out); }
+int cup_mg_vcycle_dev(CupCtx *c, const void *d_in, void *d_out) { return mg_vcycle_dev(c, d_in, d_out); }
+
+static int host_op(CupCtx *c, const double *h_in, double *h_out, int which) {
+  if (c->nblk == 0) {
+    set_error("no mesh uploaded");
+    return CUP_ERR_STATE;
+  }
+  const long long N = c->nblk * 512;
+  void *din = c->tmp_in, *dout = c->tmp_out;
+  CUP_TRY(vec_h2d(c, din, h_in, N));
+  CUP_TRY(which == 0 ? pois_op_dev(c, din, dout) : mg_vcycle_dev(c, din, dout));
+  if (c->real_bytes == 4) {
+    k_cvt_out<float><<<c->num_sms * 8, 256, 0, c->stream>>>((double *)c->tmp_stage, (const float *)dout, N);
+    c->launches++;
+    dout = c->tmp_stage;
+  }
+  CUP_CUDA(cudaMemcpyAsync(h_out, dout, (size_t)N * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUP_CUDA(cudaStreamSynchronize(c->stream));
+  return CUP_OK;
+}
+
+int cup_pois_op(CupCtx *c, const double *h_in, double *h_out) { return host_op(c, h_in, h_out, 0); }
+int cup_mg_vcycle(CupCtx *c, const double *h_in, double *h_out) { return host_op(c, h_in, h_out, 1); }
+
+int cup_pois_dot_dev(CupCtx *c, const void *a, const void *b, double *result) {
+  CUP_TRY(wdot(c, a, b, 4));
+  CUP_TRY(fetch_scalars(c, 4, 1));
+  *result = c->h_scal[4];
+  return CUP_OK;
+}
+
+int cup_pois_solve(CupCtx *c, CupSolveInfo *info) { return pois_solve(c, info); }
+int cup_advdiff(CupCtx *c) { return advdiff(c); }
+int cup_projection(CupCtx *c, CupSolveInfo *info) { return projection(c, info); }
+int cup_stencil_apply(CupCtx *c, CupStencilId id) { return stencil_run(c, id, nullptr, c->nblk); }
+int cup_stencil_run(CupCtx *c, CupStencilId id, const long long *list, long long n) {
+  return stencil_run(c, id, list, n);
+}
+
+int cup_comm_init(CupCtx *c, int rank, int nranks, const void *id, size_t id_bytes) {
+  return comm_init(c, rank, nranks, id, id_bytes);
+}
+int cup_nccl_unique_id(void *out, size_t bytes) { return comm_unique_id(out, bytes); }
+
+long long cup_kernel_launches(const CupCtx *c) { return c->launches; }
+int cup_time_smooth(CupCtx *c, int level, int reps, float *ms) { return time_smooth(c, level, reps, ms); }
+int cup_mg_smooth_dev(CupCtx *c, int level, int n, void *d_u, const void *d_f) {
+  return mg_smooth_slots(c, level, n, d_u, d_f);
+}
+void *cup_mg_array(CupCtx *c, int which) {
+  switch (which) {
+  case 0: return c->u0_x;
+  case 1: return c->f_x;
+  case 2: return c->us_x;
+  case 3: return c->u1_x;
+  }
+  return nullptr;
+}
+
+}  // extern "C"

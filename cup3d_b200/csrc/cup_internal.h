@@ -1,0 +1,116 @@
+// cup_internal.h -- shared host-side declarations of the B200 CUP3D hot path.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/cup3d_b200.h"
+
+namespace cup {
+
+void set_error(const char *fmt, ...);
+
+#define CUP_CUDA(call)                                                                              \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess) {                                                                        \
+      cup::set_error("%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));           \
+      return CUP_ERR_CUDA;                                                                          \
+    }                                                                                               \
+  } while (0)
+
+#define CUP_TRY(call)          \
+  do {                         \
+    int rc_ = (call);          \
+    if (rc_ != CUP_OK)         \
+      return rc_;              \
+  } while (0)
+
+enum { NBR_WALL = -1, NBR_COARSE = -2 };
+
+// One multigrid level == one AMR level (reference: struct Lvl, main.c:4443).
+// "active" blocks are those whose level == L in that level's context: leaves
+// of level L plus the synthesised parents of level L+1 blocks (main.c:4540,
+// :4590).  Everything is addressed through SLOTS: slot < nblk is a leaf in
+// block-index order, slot >= nblk is a synthesised parent.
+struct Level {
+  int L = 0;
+  double h = 0;
+  std::vector<int> act;    // [nact] slot of each active block
+  std::vector<int> nbr;    // [nact][6] slot of -x,+x,-y,+y,-z,+z neighbour, NBR_WALL / NBR_COARSE
+  std::vector<int> pslot;  // [nact] slot of the parent (level L-1), L >= 1
+  std::vector<int> oct;    // [nact] octant inside the parent, (ix&1)+2(iy&1)+4(iz&1)
+  std::vector<int> par;    // [npar] indices into act[] of blocks that are synthesised parents
+  int *d_act = nullptr, *d_nbr = nullptr, *d_pslot = nullptr, *d_oct = nullptr, *d_par = nullptr;
+  bool uniform = true;     // no NBR_COARSE entries
+};
+
+struct Krylov;
+
+}  // namespace cup
+
+struct CupCtx {
+  int device = 0;
+  int real_bytes = 8;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  CupParams prm{};
+  long long nblk = 0, nslot = 0;
+  int top = -1;
+  int bpd[3] = {1, 1, 1};
+  int level_max = 1;
+  std::vector<CupBlk> blk;
+  std::vector<cup::Level> lv;   // index = level
+  bool leaf_uniform = true;     // all leaves on one level (fast stencil path)
+  // device state: 9 components, each [nblk][512] Real
+  void *state[CUP_F_N] = {nullptr};
+  // multigrid scratch (Real): pong for leaves, and u/pong/f/us for parent slots
+  void *u1_leaf = nullptr, *u0_x = nullptr, *u1_x = nullptr, *f_x = nullptr, *us_x = nullptr;
+  // leaf-sized temporaries used by the host-pointer entry points and drivers
+  void *tmp_in = nullptr, *tmp_out = nullptr, *tmp_stage = nullptr;
+  void *d_W = nullptr;          // FDM eigenvalue table, lane-major [8][64]
+  void *d_hw = nullptr;         // per-leaf 1/h^3 (pois.hw, main.c:4886)
+  double *d_scal = nullptr;     // device scalars (reductions); always double
+  double *h_scal = nullptr;     // pinned mirror
+  void *pinned = nullptr;       // pinned staging for h2d/d2h
+  size_t pinned_bytes = 0;
+  cup::Krylov *kr = nullptr;
+  long long launches = 0;
+  void *p_old = nullptr;        // projection(): previous pressure
+};
+
+namespace cup {
+
+// mesh.cpp
+int build_mesh(CupCtx *c, const CupBlk *blk, long long n, const int bpd[3], int level_max);
+void free_mesh(CupCtx *c);
+
+// mg_kernels.cu
+int mg_setup(CupCtx *c);  // constants + scratch after build_mesh
+int mg_vcycle_dev(CupCtx *c, const void *d_in, void *d_out);
+int pois_op_dev(CupCtx *c, const void *d_in, void *d_out);
+int mg_smooth_slots(CupCtx *c, int level, int n, void *d_u, const void *d_f);
+int time_smooth(CupCtx *c, int level, int reps, float *ms);
+
+// blas_kernels.cu
+int wdot(CupCtx *c, const void *a, const void *b, int scal_idx);  // -> d_scal[idx] (accumulates from 0)
+int fetch_scalars(CupCtx *c, int first, int n);                   // d_scal -> h_scal, synchronises
+
+// solver.cu
+int pois_solve(CupCtx *c, CupSolveInfo *info);
+int advdiff(CupCtx *c);
+int projection(CupCtx *c, CupSolveInfo *info);
+int stencil_run(CupCtx *c, CupStencilId id, const long long *list, long long n);
+void free_krylov(CupCtx *c);
+
+// comm.cu
+int comm_init(CupCtx *c, int rank, int nranks, const void *id, size_t id_bytes);
+int comm_unique_id(void *out, size_t bytes);
+
+enum { SCAL_N = 256 };
+
+}  // namespace cup

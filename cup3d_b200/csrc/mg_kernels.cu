@@ -1,0 +1,614 @@
+// mg_kernels.cu -- geometric-multigrid V-cycle and Poisson operator, sm_100a.
+//
+// Reference path (main.c): mg_smooth :4689, mg_down :4734, mg_tau :4758,
+// mg_up/mg_up2 :4787-4807, mg_bottom :4808, mg_vcycle :4831, k_lhs/pois_op
+// :4254-4320, pois_init/pre_blk :4321-4380.
+//
+// All kernels are HBM-bandwidth bound by design (no dense contraction on this
+// path, tensor cores unused).  Algorithmic traffic per cell: smooth 3 Reals
+// (read u, f; write u'), down 2.25, tau 4 per coarse cell, up 2.25.
+#include <cmath>
+
+#include "cup_internal.h"
+#include "mg_device.cuh"
+
+namespace cup {
+
+__constant__ double cS64[8][4];
+__constant__ float cS32[8][4];
+
+// ---------------------------------------------------------------------------
+// Smoother: block-Jacobi with the exact FDM block inverse (mg_smooth, :4689).
+//
+// Reference:  t = A u ; r = f - t ; b = S3 W S3 (r/h) ; u += w b, with
+// A u = h (Lint u + G), Lint the 7-point Laplacian with zero ghosts and G the
+// sum of ghost values next to each boundary cell.  S3 W S3 is exactly Lint^-1
+// (pre_w = 1/(lam_i+lam_j+lam_k), :4333), hence
+//      b = Lint^-1 (f/h - G) - u        and      u' = u + w (Lint^-1(f/h - G) - u).
+// The interior stencil cancels analytically; only the ghost faces of the OLD
+// iterate are needed, which is why usrc/udst ping-pong (Jacobi across blocks:
+// the reference applies mg_op to all blocks before any update, :4692).
+//
+// Transform order z,y,x,(scale),x,y,z instead of x,y,z,x,y,z: the operators
+// commute, and starting/ending in z-line ownership makes the global loads and
+// stores of u and f coalesced with no staging.
+//
+// MODE 0: general.  MODE 1: usrc == 0 everywhere (first pre-smooth of the
+// finest level: no u read, no ghosts).
+template <typename Real, int MODE>
+__global__ void __launch_bounds__(TPB) k_smooth(LevelView lv, SlotVec<Real> usrc, SlotVec<Real> udst,
+                                                SlotVec<Real> fvec, const Real *__restrict__ Wl, Real h, Real invh,
+                                                Real omega, const double *__restrict__ fmean) {
+  __shared__ Real ex[512];
+  __shared__ Real halo[6][64];
+  const int t = threadIdx.x, x = t & 7, y = t >> 3;
+  Real w[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    w[k] = Wl[k * 64 + t];
+  const Real q0 = fmean ? (Real)(*fmean) : (Real)0;
+  for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
+    const int slot = lv.act[b];
+    const Real *fb = fvec.at(slot);
+    Real uu[8], v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      v[k] = fb[k * 64 + t];
+    if (MODE == 0) {
+      const Real *ub = usrc.at(slot);
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        uu[k] = ub[k * 64 + t];
+      load_halo<Real>(usrc, ub, lv.nbr + (size_t)b * 6, t, halo);
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        v[k] = invh * ((v[k] - q0) - h * ghost_sum<Real>(halo, x, y, k));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        v[k] = invh * (v[k] - q0);
+    }
+    // forward z
+    dst8<Real>(v);
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      ex[sw(x, y, k)] = v[k];
+    __syncthreads();
+    // forward y : thread owns (x2, *, z2)
+    {
+      const int x2 = t & 7, z2 = t >> 3;
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        v[k] = ex[sw(x2, k, z2)];
+      dst8<Real>(v);
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        ex[sw(x2, k, z2)] = v[k];
+    }
+    __syncthreads();
+    // forward x, scale by 1/(lam_i+lam_j+lam_k), inverse x : thread owns (*, y3, z3)
+    {
+      const int y3 = t & 7, z3 = t >> 3;
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        v[k] = ex[sw(k, y3, z3)];
+      dst8<Real>(v);
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        v[k] *= w[k];
+      dst8<Real>(v);
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        ex[sw(k, y3, z3)] = v[k];
+    }
+    __syncthreads();
+    // inverse y
+    {
+      const int x2 = t & 7, z2 = t >> 3;
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        v[k] = ex[sw(x2, k, z2)];
+      dst8<Real>(v);
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        ex[sw(x2, k, z2)] = v[k];
+    }
+    __syncthreads();
+    // inverse z and update
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      v[k] = ex[sw(x, y, k)];
+    dst8<Real>(v);
+    Real *ob = udst.at(slot);
+    if (MODE == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        ob[k * 64 + t] = uu[k] + omega * (v[k] - uu[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        ob[k * 64 + t] = omega * v[k];
+    }
+    // the next iteration's first write to ex/halo is ordered behind its own
+    // __syncthreads() after the halo fill (MODE 0); MODE 1 needs one here
+    if (MODE == 1)
+      __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Residual + restriction (mg_down, :4734): r = f - A u; the parent's octant
+// receives sum_8 r (scale 1) into f and mean_8 u into u (mg_sum/mg_put).
+template <typename Real>
+__global__ void __launch_bounds__(TPB) k_down(LevelView lv, const int *__restrict__ pslot,
+                                              const int *__restrict__ oct, SlotVec<Real> u, SlotVec<Real> f, Real h) {
+  __shared__ Real tu[512];
+  __shared__ Real tr[512];
+  __shared__ Real halo[6][64];
+  const int t = threadIdx.x, x = t & 7, y = t >> 3;
+  for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
+    const int slot = lv.act[b];
+    const Real *ub = u.at(slot);
+    const Real *fb = f.at(slot);
+    Real uu[8], ff[8], tt[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      uu[k] = ub[k * 64 + t];
+      ff[k] = fb[k * 64 + t];
+      tu[k * 64 + t] = uu[k];
+    }
+    load_halo<Real>(u, ub, lv.nbr + (size_t)b * 6, t, halo);
+    __syncthreads();
+    lap_line<Real>(tu, halo, uu, x, y, t, h, tt);
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      tr[k * 64 + t] = ff[k] - tt[k];
+    __syncthreads();
+    // thread t -> coarse cell (cx, cy, cz) of the 4^3 octant; summation order
+    // of mg_sum (:4716-4720): x fastest, then y, then z.
+    {
+      const int cx = t & 3, cy = (t >> 2) & 3, cz = t >> 4;
+      const int base = ((2 * cz) << 6) + ((2 * cy) << 3) + 2 * cx;
+      const Real sr = ((((((tr[base] + tr[base + 1]) + tr[base + 8]) + tr[base + 9]) + tr[base + 64]) +
+                         tr[base + 65]) + tr[base + 72]) + tr[base + 73];
+      const Real su = ((((((tu[base] + tu[base + 1]) + tu[base + 8]) + tu[base + 9]) + tu[base + 64]) +
+                         tu[base + 65]) + tu[base + 72]) + tu[base + 73];
+      const int o = oct[b], ps = pslot[b];
+      const int pidx = ((4 * (o >> 2) + cz) << 6) + ((4 * ((o >> 1) & 1) + cy) << 3) + 4 * (o & 1) + cx;
+      f.at(ps)[pidx] = sr;
+      u.at(ps)[pidx] = (Real)0.125 * su;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// out = A u on a list of blocks.  TAU: FAS coarse right-hand side (mg_tau,
+// :4758): f += A u, us = u on the synthesised parents.  Otherwise plain
+// operator apply (k_lhs/k_mg + pois_op's mean term, :4254-4316):
+// out = A u + shift*h^3 with shift read from a device scalar.
+template <typename Real, bool TAU>
+__global__ void __launch_bounds__(TPB) k_apply(LevelView lv, const int *__restrict__ sub, int nsub, SlotVec<Real> u,
+                                               SlotVec<Real> out, SlotVec<Real> us, Real h,
+                                               const double *__restrict__ shift, Real h3) {
+  __shared__ Real tu[512];
+  __shared__ Real halo[6][64];
+  const int t = threadIdx.x, x = t & 7, y = t >> 3;
+  const Real add = shift ? (Real)(*shift) * h3 : (Real)0;
+  for (int i = blockIdx.x; i < nsub; i += gridDim.x) {
+    const int b = sub ? sub[i] : i;
+    const int slot = lv.act[b];
+    const Real *ub = u.at(slot);
+    Real uu[8], tt[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      uu[k] = ub[k * 64 + t];
+      tu[k * 64 + t] = uu[k];
+    }
+    load_halo<Real>(u, ub, lv.nbr + (size_t)b * 6, t, halo);
+    __syncthreads();
+    lap_line<Real>(tu, halo, uu, x, y, t, h, tt);
+    Real *ob = out.at(slot);
+    if (TAU) {
+      Real *sb = us.at(slot);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        ob[k * 64 + t] += tt[k];
+        sb[k * 64 + t] = uu[k];
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        ob[k * 64 + t] = tt[k] + add;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Prolongation (mg_up/mg_get/mg_add, :4771-4807): u_f += (u_c - us) of the
+// parent cell, piecewise-constant injection.
+template <typename Real>
+__global__ void __launch_bounds__(TPB) k_up(LevelView lv, const int *__restrict__ pslot, const int *__restrict__ oct,
+                                            SlotVec<Real> u, SlotVec<Real> us) {
+  const int t = threadIdx.x, x = t & 7, y = t >> 3;
+  for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
+    const int slot = lv.act[b], ps = pslot[b], o = oct[b];
+    const Real *pu = u.at(ps);
+    const Real *pus = us.at(ps);
+    Real *ub = u.at(slot);
+    const int pbase = ((4 * (o >> 2)) << 6) + ((4 * ((o >> 1) & 1) + (y >> 1)) << 3) + 4 * (o & 1) + (x >> 1);
+    Real d[4];
+#pragma unroll
+    for (int kz = 0; kz < 4; kz++)
+      d[kz] = pu[pbase + (kz << 6)] - pus[pbase + (kz << 6)];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      ub[k * 64 + t] += d[k >> 1];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// sum over active blocks of f  (mg_bottom's mean, :4811-4821).  All active
+// blocks of a level share h, so the h^3 weights cancel: q0 = sum(f)/(512*nact).
+template <typename Real>
+__global__ void __launch_bounds__(256) k_level_sum(LevelView lv, SlotVec<Real> f, double *out, double scale) {
+  __shared__ double red[8];
+  double s = 0;
+  for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
+    const Real *fb = f.at(lv.act[b]);
+    for (int j = threadIdx.x; j < 512; j += blockDim.x)
+      s += (double)fb[j];
+  }
+  for (int o = 16; o > 0; o >>= 1)
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0)
+    red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); i++)
+      tot += red[i];
+    atomicAdd(out, tot * scale);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+namespace {
+
+template <typename Real>
+struct Arr {
+  // the four slot-space vectors of the V-cycle
+  SlotVec<Real> u0, u1, f, us;
+};
+
+inline LevelView view(const Level &v) { return LevelView{v.d_act, v.d_nbr, (int)v.act.size()}; }
+
+inline int grid_for(const CupCtx *c, long long nwork, int per_sm) {
+  long long g = (long long)c->num_sms * per_sm;
+  if (g > nwork)
+    g = nwork;
+  if (g < 1)
+    g = 1;
+  return (int)g;
+}
+
+template <typename Real>
+int smooth_level(CupCtx *c, const Level &v, int n, Arr<Real> &a, bool first_is_zero, const double *fmean) {
+  if (v.act.empty() || n == 0)
+    return CUP_OK;
+  if (!v.uniform) {
+    set_error("multigrid level %d has coarse-fine interfaces: AMR smoother not available in this build", v.L);
+    return CUP_ERR_UNSUPPORTED;
+  }
+  const int grid = grid_for(c, (long long)v.act.size(), 16);
+  const Real h = (Real)v.h, invh = (Real)(1.0 / v.h), om = (Real)0.8;  // mg_omega, main.c:4434
+  for (int it = 0; it < n; it++) {
+    SlotVec<Real> &src = (it & 1) ? a.u1 : a.u0;
+    SlotVec<Real> &dst = (it & 1) ? a.u0 : a.u1;
+    if (it == 0 && first_is_zero)
+      k_smooth<Real, 1><<<grid, TPB, 0, c->stream>>>(view(v), src, dst, a.f, (const Real *)c->d_W, h, invh, om,
+                                                      fmean);
+    else
+      k_smooth<Real, 0><<<grid, TPB, 0, c->stream>>>(view(v), src, dst, a.f, (const Real *)c->d_W, h, invh, om,
+                                                      fmean);
+    c->launches++;
+  }
+  if (n & 1) {
+    set_error("odd smoothing count %d not supported (ping-pong)", n);
+    return CUP_ERR_UNSUPPORTED;
+  }
+  return CUP_OK;
+}
+
+template <typename Real>
+int vcycle_t(CupCtx *c, const Real *d_in, Real *d_out) {
+  const int nleaf = (int)c->nblk;
+  Arr<Real> a;
+  a.u0 = SlotVec<Real>{d_out, (Real *)c->u0_x, nleaf};
+  a.u1 = SlotVec<Real>{(Real *)c->u1_leaf, (Real *)c->u1_x, nleaf};
+  a.f = SlotVec<Real>{const_cast<Real *>(d_in), (Real *)c->f_x, nleaf};
+  a.us = SlotVec<Real>{nullptr, (Real *)c->us_x, nleaf};
+  enum { MG_PRE = 2, MG_POST = 2, MG_BOT = 50 };  // main.c:4433
+  // finest level holding blocks
+  int top = c->top;
+  while (top > 0 && c->lv[top].act.empty())
+    top--;
+  if (!c->leaf_uniform) {
+    set_error("mg_vcycle on a multi-level mesh is not available in this build");
+    return CUP_ERR_UNSUPPORTED;
+  }
+  for (int L = top; L >= 1; L--) {
+    const Level &v = c->lv[L];
+    // u == 0 on entry only at the finest level (vec_zero, :4834); coarser
+    // levels start from the restricted u (FAS).
+    CUP_TRY(smooth_level<Real>(c, v, MG_PRE, a, L == top, nullptr));
+    const int grid = grid_for(c, (long long)v.act.size(), 12);
+    k_down<Real><<<grid, TPB, 0, c->stream>>>(view(v), v.d_pslot, v.d_oct, a.u0, a.f, (Real)v.h);
+    c->launches++;
+    const Level &w = c->lv[L - 1];
+    const int gridw = grid_for(c, (long long)w.par.size(), 12);
+    k_apply<Real, true><<<gridw, TPB, 0, c->stream>>>(view(w), w.d_par, (int)w.par.size(), a.u0, a.f, a.us,
+                                                       (Real)w.h, nullptr, (Real)0);
+    c->launches++;
+  }
+  {
+    const Level &v = c->lv[0];
+    double *q = c->d_scal + 0;
+    const double *fmean = nullptr;
+    if (top == 0) {
+      // single-level mesh: f is the caller's vector, u starts from zero
+    }
+    CUP_CUDA(cudaMemsetAsync(q, 0, sizeof(double), c->stream));
+    k_level_sum<Real><<<grid_for(c, (long long)v.act.size(), 4), 256, 0, c->stream>>>(
+        view(v), a.f, q, 1.0 / (512.0 * (double)v.act.size()));
+    c->launches++;
+    fmean = q;
+    CUP_TRY(smooth_level<Real>(c, v, MG_BOT, a, top == 0, fmean));
+  }
+  for (int L = 1; L <= top; L++) {
+    const Level &v = c->lv[L];
+    const int grid = grid_for(c, (long long)v.act.size(), 16);
+    k_up<Real><<<grid, TPB, 0, c->stream>>>(view(v), v.d_pslot, v.d_oct, a.u0, a.us);
+    c->launches++;
+    CUP_TRY(smooth_level<Real>(c, v, MG_POST, a, false, nullptr));
+  }
+  CUP_CUDA(cudaGetLastError());
+  return CUP_OK;
+}
+
+template <typename Real>
+__global__ void k_wsum(const Real *__restrict__ a, const Real *__restrict__ hw3, long long nblk, double *out) {
+  // sum_i a_i * h_i^3   (pois_op's avg_p, main.c:4286-4294); hw3 = per-block h^3
+  __shared__ double red[8];
+  double s = 0;
+  for (long long b = blockIdx.x; b < nblk; b += gridDim.x) {
+    const Real *p = a + b * 512;
+    double sb = 0;
+    for (int j = threadIdx.x; j < 512; j += blockDim.x)
+      sb += (double)p[j];
+    s += sb * (double)hw3[b];
+  }
+  for (int o = 16; o > 0; o >>= 1)
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0)
+    red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); i++)
+      tot += red[i];
+    atomicAdd(out, tot);
+  }
+}
+
+template <typename Real>
+__global__ void k_pin(const Real *in, Real *out, long long off, const double *avg, int mode) {
+  // bMeanConstraint 1: out[pin] = avg_p ; > 2: out[pin] = in[pin]  (main.c:4305, :4318)
+  out[off] = mode == 1 ? (Real)(*avg) : in[off];
+}
+
+template <typename Real>
+int pois_op_t(CupCtx *c, const Real *d_in, Real *d_out) {
+  if (!c->leaf_uniform) {
+    set_error("pois_op on a multi-level mesh is not available in this build");
+    return CUP_ERR_UNSUPPORTED;
+  }
+  int top = c->top;
+  while (top > 0 && c->lv[top].act.empty())
+    top--;
+  const Level &v = c->lv[top];
+  const int mc = c->prm.mean_constraint;
+  const double *shift = nullptr;
+  double *q = c->d_scal + 1;
+  if (mc == 1 || mc == 2) {
+    CUP_CUDA(cudaMemsetAsync(q, 0, sizeof(double), c->stream));
+    k_wsum<Real><<<grid_for(c, c->nblk, 8), 256, 0, c->stream>>>(d_in, (const Real *)c->d_hw, c->nblk, q);
+    c->launches++;
+    if (mc == 2)
+      shift = q;
+  }
+  const int nleaf = (int)c->nblk;
+  SlotVec<Real> u{const_cast<Real *>(d_in), nullptr, nleaf}, o{d_out, nullptr, nleaf}, us{nullptr, nullptr, nleaf};
+  const Real h = (Real)v.h;
+  k_apply<Real, false><<<grid_for(c, c->nblk, 16), TPB, 0, c->stream>>>(view(v), nullptr, (int)v.act.size(), u, o,
+                                                                         us, h, shift, h * h * h);
+  c->launches++;
+  if (mc == 1 || mc > 2) {
+    long long pin = -1;  // pois_pin: block (0,0,0), main.c:4888
+    for (long long i = 0; i < c->nblk; i++)
+      if (c->blk[i].ix == 0 && c->blk[i].iy == 0 && c->blk[i].iz == 0)
+        pin = i;
+    if (pin >= 0) {
+      k_pin<Real><<<1, 1, 0, c->stream>>>(d_in, d_out, pin * 512, q, mc);
+      c->launches++;
+    }
+  }
+  CUP_CUDA(cudaGetLastError());
+  return CUP_OK;
+}
+
+}  // namespace
+
+int mg_setup(CupCtx *c) {
+  // FDM constants exactly as pois_init computes them (main.c:4322-4334)
+  const int BS = 8;
+  double lam[8], S[8][8];
+  for (int j = 0; j < BS; j++) {
+    lam[j] = 2 * cos(M_PI * (j + 1) / (BS + 1)) - 2;
+    for (int k = 0; k < BS; k++)
+      S[j][k] = sqrt(2.0 / (BS + 1)) * sin(M_PI * (j + 1) * (k + 1) / (BS + 1));
+  }
+  double s64[8][4];
+  float s32[8][4];
+  for (int j = 0; j < 8; j++)
+    for (int k = 0; k < 4; k++) {
+      s64[j][k] = S[j][k];
+      s32[j][k] = (float)S[j][k];
+    }
+  CUP_CUDA(cudaMemcpyToSymbol(cS64, s64, sizeof s64));
+  CUP_CUDA(cudaMemcpyToSymbol(cS32, s32, sizeof s32));
+  // lane-major eigenvalue table for the x pass: thread (y3, z3) = (t&7, t>>3)
+  // scales mode (k, y3, z3):  Wl[k][t] = pre_w[IDX(k, t&7, t>>3)]
+  std::vector<double> W(512);
+  for (int k = 0; k < 8; k++)
+    for (int t = 0; t < 64; t++)
+      W[k * 64 + t] = 1 / (lam[k] + lam[t & 7] + lam[t >> 3]);
+  cudaFree(c->d_W);
+  const size_t rb = (size_t)c->real_bytes;
+  CUP_CUDA(cudaMalloc(&c->d_W, 512 * rb));
+  if (c->real_bytes == 8) {
+    CUP_CUDA(cudaMemcpy(c->d_W, W.data(), 512 * 8, cudaMemcpyHostToDevice));
+  } else {
+    std::vector<float> Wf(W.begin(), W.end());
+    CUP_CUDA(cudaMemcpy(c->d_W, Wf.data(), 512 * 4, cudaMemcpyHostToDevice));
+  }
+  // scratch in slot space
+  cudaFree(c->u1_leaf);
+  cudaFree(c->u0_x);
+  cudaFree(c->u1_x);
+  cudaFree(c->f_x);
+  cudaFree(c->us_x);
+  cudaFree(c->d_hw);
+  c->u1_leaf = c->u0_x = c->u1_x = c->f_x = c->us_x = c->d_hw = nullptr;
+  const size_t nx = (size_t)(c->nslot - c->nblk) + 1;
+  CUP_CUDA(cudaMalloc(&c->u1_leaf, (size_t)c->nblk * 512 * rb));
+  CUP_CUDA(cudaMalloc(&c->u0_x, nx * 512 * rb));
+  CUP_CUDA(cudaMalloc(&c->u1_x, nx * 512 * rb));
+  CUP_CUDA(cudaMalloc(&c->f_x, nx * 512 * rb));
+  CUP_CUDA(cudaMalloc(&c->us_x, nx * 512 * rb));
+  CUP_CUDA(cudaMemset(c->u0_x, 0, nx * 512 * rb));
+  CUP_CUDA(cudaMemset(c->u1_x, 0, nx * 512 * rb));
+  CUP_CUDA(cudaMemset(c->f_x, 0, nx * 512 * rb));
+  CUP_CUDA(cudaMemset(c->us_x, 0, nx * 512 * rb));
+  CUP_CUDA(cudaMemset(c->u1_leaf, 0, (size_t)c->nblk * 512 * rb));
+  // per-leaf h^3 (weights of avg_p / pois_dot use 1/h^3: stored as h^3 here)
+  CUP_CUDA(cudaMalloc(&c->d_hw, (size_t)c->nblk * rb));
+  if (c->real_bytes == 8) {
+    std::vector<double> hw((size_t)c->nblk);
+    for (long long i = 0; i < c->nblk; i++)
+      hw[i] = c->blk[i].h * c->blk[i].h * c->blk[i].h;
+    CUP_CUDA(cudaMemcpy(c->d_hw, hw.data(), hw.size() * 8, cudaMemcpyHostToDevice));
+  } else {
+    std::vector<float> hw((size_t)c->nblk);
+    for (long long i = 0; i < c->nblk; i++)
+      hw[i] = (float)(c->blk[i].h * c->blk[i].h * c->blk[i].h);
+    CUP_CUDA(cudaMemcpy(c->d_hw, hw.data(), hw.size() * 4, cudaMemcpyHostToDevice));
+  }
+  return CUP_OK;
+}
+
+int mg_vcycle_dev(CupCtx *c, const void *d_in, void *d_out) {
+  if (c->nblk == 0) {
+    set_error("mg_vcycle: no mesh uploaded");
+    return CUP_ERR_STATE;
+  }
+  return c->real_bytes == 8 ? vcycle_t<double>(c, (const double *)d_in, (double *)d_out)
+                            : vcycle_t<float>(c, (const float *)d_in, (float *)d_out);
+}
+
+int pois_op_dev(CupCtx *c, const void *d_in, void *d_out) {
+  if (c->nblk == 0) {
+    set_error("pois_op: no mesh uploaded");
+    return CUP_ERR_STATE;
+  }
+  return c->real_bytes == 8 ? pois_op_t<double>(c, (const double *)d_in, (double *)d_out)
+                            : pois_op_t<float>(c, (const float *)d_in, (float *)d_out);
+}
+
+int mg_smooth_slots(CupCtx *c, int level, int n, void *d_u, const void *d_f) {
+  // unit-test hook: n smoothing sweeps of one level on caller vectors in slot
+  // space (nslot*512 Reals)
+  if (level < 0 || level > c->top) {
+    set_error("mg_smooth: bad level %d", level);
+    return CUP_ERR_ARG;
+  }
+  const int nleaf = (int)c->nblk;
+  const size_t rb = (size_t)c->real_bytes;
+  if (c->real_bytes == 8) {
+    Arr<double> a;
+    double *u = (double *)d_u;
+    const double *f = (const double *)d_f;
+    a.u0 = SlotVec<double>{u, u + (size_t)nleaf * 512, nleaf};
+    a.u1 = SlotVec<double>{(double *)c->u1_leaf, (double *)c->u1_x, nleaf};
+    a.f = SlotVec<double>{const_cast<double *>(f), const_cast<double *>(f) + (size_t)nleaf * 512, nleaf};
+    a.us = SlotVec<double>{nullptr, (double *)c->us_x, nleaf};
+    return smooth_level<double>(c, c->lv[level], n, a, false, nullptr);
+  }
+  (void)rb;
+  Arr<float> a;
+  float *u = (float *)d_u;
+  const float *f = (const float *)d_f;
+  a.u0 = SlotVec<float>{u, u + (size_t)nleaf * 512, nleaf};
+  a.u1 = SlotVec<float>{(float *)c->u1_leaf, (float *)c->u1_x, nleaf};
+  a.f = SlotVec<float>{const_cast<float *>(f), const_cast<float *>(f) + (size_t)nleaf * 512, nleaf};
+  a.us = SlotVec<float>{nullptr, (float *)c->us_x, nleaf};
+  return smooth_level<float>(c, c->lv[level], n, a, false, nullptr);
+}
+
+int time_smooth(CupCtx *c, int level, int reps, float *ms) {
+  if (level < 0 || level > c->top || reps < 1 || c->lv[level].act.empty()) {
+    set_error("time_smooth: bad level %d", level);
+    return CUP_ERR_ARG;
+  }
+  const Level &v = c->lv[level];
+  const int nleaf = (int)c->nblk;
+  cudaEvent_t e0, e1;
+  CUP_CUDA(cudaEventCreate(&e0));
+  CUP_CUDA(cudaEventCreate(&e1));
+  const int grid = grid_for(c, (long long)v.act.size(), 16);
+  // state[] vectors double as inputs: F_PRES as u, F_LHS as f, F_TMP as u'
+  if (c->real_bytes == 8) {
+    SlotVec<double> s{(double *)c->state[CUP_F_PRES], (double *)c->u0_x, nleaf};
+    SlotVec<double> d{(double *)c->u1_leaf, (double *)c->u1_x, nleaf};
+    SlotVec<double> f{(double *)c->state[CUP_F_LHS], (double *)c->f_x, nleaf};
+    CUP_CUDA(cudaEventRecord(e0, c->stream));
+    for (int r = 0; r < reps; r++)
+      k_smooth<double, 0><<<grid, TPB, 0, c->stream>>>(view(v), (r & 1) ? d : s, (r & 1) ? s : d, f,
+                                                        (const double *)c->d_W, v.h, 1.0 / v.h, 0.8, nullptr);
+    CUP_CUDA(cudaEventRecord(e1, c->stream));
+  } else {
+    SlotVec<float> s{(float *)c->state[CUP_F_PRES], (float *)c->u0_x, nleaf};
+    SlotVec<float> d{(float *)c->u1_leaf, (float *)c->u1_x, nleaf};
+    SlotVec<float> f{(float *)c->state[CUP_F_LHS], (float *)c->f_x, nleaf};
+    CUP_CUDA(cudaEventRecord(e0, c->stream));
+    for (int r = 0; r < reps; r++)
+      k_smooth<float, 0><<<grid, TPB, 0, c->stream>>>(view(v), (r & 1) ? d : s, (r & 1) ? s : d, f,
+                                                       (const float *)c->d_W, (float)v.h, (float)(1.0 / v.h), 0.8f,
+                                                       nullptr);
+    CUP_CUDA(cudaEventRecord(e1, c->stream));
+  }
+  c->launches += reps;
+  CUP_CUDA(cudaEventSynchronize(e1));
+  float t = 0;
+  CUP_CUDA(cudaEventElapsedTime(&t, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms = t / reps;
+  return CUP_OK;
+}
+
+}  // namespace cup

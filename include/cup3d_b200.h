@@ -1,0 +1,152 @@
+/*
+ * cup3d_b200.h -- C ABI of the B200-native CUP3D hot path.
+ *
+ * The reference (slitvinov/CUP3D, main.c) has no plugin interface: every
+ * symbol is file-static in one translation unit.  The boundary reproduced
+ * here is therefore the CALL SURFACE its time loop uses:
+ *
+ *   reference (main.c)                     this library
+ *   ------------------------------------   ---------------------------------
+ *   struct Blk                  :59-63     CupBlk (same members, same order)
+ *   sta.fld [nblk][F_N][512]    :55-58     cup_state_h2d / cup_state_d2h
+ *   tree_sync+halo_build+fc_prepare+
+ *     mg_build (rebuild hook)   :3325-3328 cup_mesh_upload
+ *   struct Stencil st_*         :3627-3630 CupStencilId
+ *   stencil_apply / stencil_run :3631-3648 cup_stencil_apply / cup_stencil_run
+ *   pois_op(in,out)             :4282      cup_pois_op
+ *   mg_vcycle(in,out)           :4831      cup_mg_vcycle
+ *   pois_solve()                :4875      cup_pois_solve
+ *   advdiff()                   :5027      cup_advdiff
+ *   projection()                :5828      cup_projection
+ *   halo_sync / xch_exec (MPI)  :2899,:3101 cup_comm_init (NCCL, one rank/GPU)
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  Every function
+ * returns 0 on success and a negative CupStatus otherwise (the reference
+ * aborts through fatal(), main.c:134); cup_last_error() gives the text.
+ * There is NO CPU fallback: without a CUDA device every call fails.
+ * Vectors named h_* are host pointers, d_* are device pointers.  All flat
+ * vectors are in block-index order, 512 cells per block, x fastest
+ * (IDX(x,y,z) = (z*8+y)*8+x, main.c:58).
+ */
+#ifndef CUP3D_B200_H
+#define CUP3D_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { CUP_BS = 8, CUP_BS3 = 512 };
+/* field offsets inside one block of sta.fld (main.c:55) */
+enum { CUP_F_CHI = 0, CUP_F_PRES = 1, CUP_F_VEL = 2, CUP_F_TMP = 5, CUP_F_LHS = 8, CUP_F_N = 9 };
+
+typedef enum {
+  CUP_OK = 0,
+  CUP_ERR_ARG = -1,     /* bad argument / unsupported configuration */
+  CUP_ERR_CUDA = -2,    /* CUDA runtime error */
+  CUP_ERR_MESH = -3,    /* inconsistent mesh (missing neighbour / sibling) */
+  CUP_ERR_STATE = -4,   /* call order (mesh not uploaded, ...) */
+  CUP_ERR_NCCL = -5,
+  CUP_ERR_UNSUPPORTED = -6
+} CupStatus;
+
+/* struct Blk, main.c:59-63 (Real = double in the reference build) */
+typedef struct CupBlk {
+  int level, ix, iy, iz;
+  long long Z;
+  double h, origin[3];
+} CupBlk;
+
+/* the reference's Stencil instances (main.c:4267,4280,5026,5699,5714,5735) */
+typedef enum {
+  CUP_ST_LHS = 0,     /* st_lhs     F_PRES -> F_LHS   */
+  CUP_ST_MG = 1,      /* st_mg      F_PRES -> F_LHS (no flux faces) */
+  CUP_ST_ADVDIFF = 2, /* st_advdiff F_VEL  -> F_TMP += */
+  CUP_ST_PRHS = 3,    /* st_prhs    F_VEL,F_TMP,F_CHI -> F_LHS */
+  CUP_ST_DIVP = 4,    /* st_divp    F_PRES -> F_TMP[0] */
+  CUP_ST_GRADP = 5    /* st_gradp   F_PRES -> F_TMP[0..2] */
+} CupStencilId;
+
+/* run-time scalars the kernels read from the reference's sim/sta globals */
+typedef struct CupParams {
+  double dt;             /* sta.dt */
+  double nu;             /* sim.nu */
+  double uinf[3];        /* sta.uinf */
+  int step;              /* sta.step (incremental pressure after STEP_2ND) */
+  int mean_constraint;   /* sim.mean_constraint (bMeanConstraint) */
+  double ptol, ptol_rel; /* sim.ptol, sim.ptol_rel */
+} CupParams;
+
+typedef struct CupSolveInfo {
+  int iterations;   /* Krylov iterations (it, main.c:4954) */
+  int restarts;
+  double residual;  /* final ||r||/sqrt(vol) */
+  double rhs_norm;  /* ||b||/sqrt(vol) */
+  int vcycles;      /* V-cycles applied */
+} CupSolveInfo;
+
+typedef struct CupCtx CupCtx;
+
+const char *cup_last_error(void);
+int cup_version(void);
+
+/* real_bytes: 8 (the reference build, typedef double Real) or 4 */
+int cup_create(CupCtx **ctx, int device, int real_bytes);
+int cup_destroy(CupCtx *ctx);
+/* run all later work on this CUDA stream (cudaStream_t as void*); 0 = default */
+int cup_set_stream(CupCtx *ctx, void *stream);
+int cup_set_params(CupCtx *ctx, const CupParams *p);
+int cup_synchronize(CupCtx *ctx);
+
+/* Rebuild hook.  blk = this rank's sta.blk[0..n), bpd = sim.bpdx/y/z,
+ * level_max = sim.level_max.  Builds neighbour tables, flux-face plans and
+ * the multigrid hierarchy on the device (replaces main.c:3325-3328). */
+int cup_mesh_upload(CupCtx *ctx, const CupBlk *blk, long long n, const int bpd[3], int level_max);
+long long cup_nblk(const CupCtx *ctx);
+long long cup_nslot(const CupCtx *ctx); /* leaves + synthesised MG parents */
+int cup_mg_levels(const CupCtx *ctx);
+long long cup_mg_nact(const CupCtx *ctx, int level);
+
+/* sta.fld <-> device.  h_fld is the reference's layout [nblk][9][512] doubles;
+ * f0/nc select a field range (e.g. CUP_F_VEL,3). */
+int cup_state_h2d(CupCtx *ctx, const double *h_fld, int f0, int nc);
+int cup_state_d2h(CupCtx *ctx, double *h_fld, int f0, int nc);
+/* device pointer of one state component: flat [nblk][512] Reals */
+void *cup_state_dev(CupCtx *ctx, int f);
+
+/* the per-block compute loop */
+int cup_stencil_apply(CupCtx *ctx, CupStencilId id);
+int cup_stencil_run(CupCtx *ctx, CupStencilId id, const long long *list, long long n);
+
+/* flat-vector operators, host buffers (H2D + compute + D2H, synchronous) */
+int cup_pois_op(CupCtx *ctx, const double *h_in, double *h_out);
+int cup_mg_vcycle(CupCtx *ctx, const double *h_in, double *h_out);
+/* same on device-resident vectors of Real (asynchronous on the ctx stream) */
+int cup_pois_op_dev(CupCtx *ctx, const void *d_in, void *d_out);
+int cup_mg_vcycle_dev(CupCtx *ctx, const void *d_in, void *d_out);
+/* sum_i a_i b_i / h_i^3 (pois_dot, main.c:4854); synchronous */
+int cup_pois_dot_dev(CupCtx *ctx, const void *d_a, const void *d_b, double *result);
+
+/* F_LHS (rhs), F_PRES (guess) -> F_PRES; uses params ptol/ptol_rel/mean_constraint */
+int cup_pois_solve(CupCtx *ctx, CupSolveInfo *info);
+int cup_advdiff(CupCtx *ctx);
+int cup_projection(CupCtx *ctx, CupSolveInfo *info);
+
+/* One rank per GPU.  nccl_id = the 128 bytes of an ncclUniqueId created on
+ * rank 0 and distributed by the caller (torch.distributed / MPI_Bcast). */
+int cup_comm_init(CupCtx *ctx, int rank, int nranks, const void *nccl_id, size_t id_bytes);
+int cup_nccl_unique_id(void *out, size_t bytes);
+
+/* instrumentation: number of kernels launched by this context so far */
+long long cup_kernel_launches(const CupCtx *ctx);
+/* timing of an internal kernel class with CUDA events on the ctx stream:
+ * runs `reps` launches of the level-`level` smoother; returns ms per launch */
+int cup_time_smooth(CupCtx *ctx, int level, int reps, float *ms_per_launch);
+
+/* unit-test hooks on device vectors in MG slot space (nslot*512 Reals) */
+int cup_mg_smooth_dev(CupCtx *ctx, int level, int n, void *d_u, const void *d_f);
+void *cup_mg_array(CupCtx *ctx, int which); /* 0 u, 1 f, 2 us, 3 u-pong */
+
+#ifdef __cplusplus
+}
+#endif
+#endif
