@@ -1,0 +1,273 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the CUP3D hot path on B200.
+
+Metric (BASELINE.json): cell-updates/s of the geometric-multigrid Poisson
+V-cycle on a 512^3 uniform grid (bpd 1, levelStart 6, levelMax 7; 262 144
+blocks of 8^3), fp64, zero right-hand side + a +1/-1 point-source pair.  One
+"step" = one complete mg_vcycle over the whole grid; one cell-update = one
+finest-level cell processed by one V-cycle.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+ours      : the CUDA library through its C ABI.  `value` is measured with the
+            vectors resident in HBM (CUDA events on the library's stream);
+            `e2e` calls the host-pointer entry cup_mg_vcycle() with pinned
+            host buffers, H2D + V-cycle + D2H inside the timed region.
+reference : the reference's own CPU implementation (oracle/_ref, the
+            unmodified main.c + single-rank MPI shim, OpenMP over all host
+            cores) timed on a bounded sample of the same workload.
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_CELL_VCYCLE = 171.0  # algorithmic bytes per cell-update, fp64 (SURVEY.md 8d / DESIGN.md)
+B_PER_CELL_SMOOTH = 24.0   # smoother: read u, f, write u' (3 Reals)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """per-launch DRAM bytes of the dominant kernel from the committed ncu capture, if any"""
+    p = os.path.join(ROOT, "profiles", "smooth_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([s.strip() for s in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def point_sources(ib, rb):
+    """b = +1 at cell 0 of the block containing (.25,.25,.25), -1 at (.75,.75,.75)"""
+    import numpy as np
+    out = []
+    for p in (0.25, 0.75):
+        lo = rb[:, 1:4]
+        hi = lo + 8 * rb[:, 0:1]
+        hit = np.all((lo <= p) & (p < hi), axis=1)
+        out.append(int(np.nonzero(hit)[0][0]))
+    return out
+
+
+def cpu_reference_run(level, warmup, steps, timeout=900):
+    """time the reference's CPU V-cycle in a subprocess (its state is process-global)"""
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "cpu_baseline.py"), "--level", str(level), "--warmup",
+           str(warmup), "--steps", str(steps)]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    for line in r.stdout.splitlines()[::-1]:
+        if line.startswith("{"):
+            return json.loads(line)
+    raise RuntimeError("cpu baseline failed: " + r.stderr[-2000:])
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    lvl = args.cpu_level
+    res = cpu_reference_run(lvl, args.warmup, args.steps)
+    cells = (8 << lvl) ** 3
+    line = {
+        "impl": "reference", "metric": "poisson_vcycle_cell_updates_per_s", "value": res["cell_updates_per_s"],
+        "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": res["ms_per_cycle"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "512^3 uniform Poisson V-cycle (bpd 1, levelStart 6, levelMax 7), fp64, point-source "
+                               "pair; CPU arm timed on a bounded %d^3 sample of the same workload" % (8 << lvl)},
+        "cpu_baseline": {"value": res["cell_updates_per_s"], "unit": "cell-updates/s", "cores": res["threads"],
+                         "kind": res["kind"], "sample": "%d V-cycles of the %d^3 grid (%d cells), %s" %
+                         (args.steps, 8 << lvl, cells, res["what"])},
+        "e2e": {"value": res["cell_updates_per_s"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import cup3d_b200
+    from cup3d_b200 import mesh
+
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    L = args.level
+    ib, rb = mesh.uniform_blocks(L)
+    if world > 1:
+        raise SystemExit("bench.py: multi-GPU domain decomposition is not built yet in this round")
+    ctx = cup3d_b200.Context(local_rank, 8)
+    ctx.mesh_upload(ib, rb, (1, 1, 1), L + 1)
+    ctx.set_params(mean_constraint=2)
+    n = len(ib)
+    N = n * 512
+    src = point_sources(ib, rb)
+    b = torch.zeros(N, dtype=torch.float64, device="cuda")
+    b[src[0] * 512] = 1.0
+    b[src[1] * 512] = -1.0
+    z = torch.empty_like(b)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    for _ in range(args.warmup):
+        ctx.mg_vcycle_dev(b, z)
+    torch.cuda.synchronize()
+    clk = ClockSampler(local_rank)
+    clk.start()
+    l0 = ctx.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        ctx.mg_vcycle_dev(b, z)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.kernel_launches() - l0
+    # dominant kernel: finest-level smoother, timed live with CUDA events on the same stream
+    sm_ms = ctx.time_smooth(L, 40)
+    clocks = clk.stop()
+    checksum = float(z.abs().sum().item())
+
+    # end to end through the host-pointer C ABI: pinned host in/out, H2D + V-cycle + D2H per step
+    hb = torch.zeros(N, dtype=torch.float64).pin_memory()
+    hb[src[0] * 512] = 1.0
+    hb[src[1] * 512] = -1.0
+    hz = torch.empty(N, dtype=torch.float64).pin_memory()
+    e2e_steps = max(3, min(args.steps, 5))
+    ctx.mg_vcycle(hb, hz)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.mg_vcycle(hb, hz)  # synchronous: returns after the D2H
+    t_e2e = (time.perf_counter() - t0) / e2e_steps
+    assert abs(float(hz.abs().sum().item()) - checksum) <= 1e-9 * checksum
+
+    cells = N
+    value = cells * args.steps / (ms * 1e-3)
+    peak, peak_src = measured_peak()
+    smooth_gbs = cells * B_PER_CELL_SMOOTH / (sm_ms * 1e-3) / 1e9
+    traffic = ncu_traffic()
+    cpu = None
+    if not args.no_cpu:
+        try:
+            r = cpu_reference_run(args.cpu_level, 1, 3)
+            cpu = {"value": r["cell_updates_per_s"], "unit": "cell-updates/s", "cores": r["threads"],
+                   "kind": r["kind"],
+                   "sample": "3 V-cycles of a %d^3 grid (same block-structured workload, bounded), %s" %
+                             (8 << args.cpu_level, r["what"])}
+        except Exception as ex:  # the oracle always exists; report why it did not run
+            cpu = {"value": None, "unit": "cell-updates/s", "cores": 0, "kind": "reference",
+                   "sample": "failed: %s" % str(ex)[:200]}
+    line = {
+        "metric": "poisson_vcycle_cell_updates_per_s", "value": value, "unit": "cell-updates/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%d^3 uniform Poisson V-cycle (bpd 1, levelStart %d, levelMax %d), fp64, zero RHS + "
+                               "point-source pair" % (8 << L, L, L + 1),
+                   "blocks": n, "mg_levels": L + 1, "l2_policy": "inputs larger than L2 (%.2f GB per vector)" %
+                   (N * 8 / 1e9), "parallelism": "1 rank per GPU, %d rank(s)" % world},
+        "hbm_gbs_vcycle": cells * B_PER_CELL_VCYCLE * args.steps / (ms * 1e-3) / 1e9,
+        "roofline": {"bound": "hbm", "kernel": "k_smooth<double,0> (finest level)", "achieved": smooth_gbs,
+                     "peak": peak, "unit": "GB/s", "frac": smooth_gbs / peak,
+                     "traffic": traffic["bytes_per_launch"] if traffic else None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": cells * B_PER_CELL_SMOOTH, "ms_per_launch": sm_ms,
+                     "vcycle_frac_at_171B_per_cell": cells * B_PER_CELL_VCYCLE * args.steps / (ms * 1e-3) / 1e9 / peak},
+        "cpu_baseline": cpu,
+        "e2e": {"value": cells / t_e2e, "unit": "cell-updates/s", "h2d_bytes_per_step": N * 8,
+                "d2h_bytes_per_step": N * 8, "ms_per_step": t_e2e * 1e3},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--level", type=int, default=6, help="uniform level: grid = (8<<level)^3; 6 = 512^3")
+    ap.add_argument("--cpu-level", type=int, default=5, help="grid of the bounded CPU sample (5 = 256^3)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -60,6 +60,7 @@ SYMBOLS = {
     "cup_pois_solve": (_i, [_vp, C.POINTER(CupSolveInfo)]),
     "cup_advdiff": (_i, [_vp]),
     "cup_projection": (_i, [_vp, C.POINTER(CupSolveInfo)]),
+    "cup_projection_udef_ready": (_i, [_vp, _i]),
     "cup_comm_init": (_i, [_vp, _i, _i, _vp, C.c_size_t]),
     "cup_nccl_unique_id": (_i, [_vp, C.c_size_t]),
     "cup_kernel_launches": (_ll, [_vp]),

@@ -252,6 +252,10 @@ int cup_pois_dot_dev(CupCtx *c, const void *a, const void *b, double *result) {
 int cup_pois_solve(CupCtx *c, CupSolveInfo *info) { return pois_solve(c, info); }
 int cup_advdiff(CupCtx *c) { return advdiff(c); }
 int cup_projection(CupCtx *c, CupSolveInfo *info) { return projection(c, info); }
+int cup_projection_udef_ready(CupCtx *c, int flag) {
+  c->keep_tmp_udef = flag != 0;
+  return CUP_OK;
+}
 int cup_stencil_apply(CupCtx *c, CupStencilId id) { return stencil_run(c, id, nullptr, c->nblk); }
 int cup_stencil_run(CupCtx *c, CupStencilId id, const long long *list, long long n) {
   return stencil_run(c, id, list, n);

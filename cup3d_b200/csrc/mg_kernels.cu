@@ -8,6 +8,7 @@
 // path, tensor cores unused).  Algorithmic traffic per cell: smooth 3 Reals
 // (read u, f; write u'), down 2.25, tau 4 per coarse cell, up 2.25.
 #include <cmath>
+#include <cstdlib>
 
 #include "cup_internal.h"
 #include "mg_device.cuh"
@@ -35,8 +36,8 @@ __constant__ float cS32[8][4];
 //
 // MODE 0: general.  MODE 1: usrc == 0 everywhere (first pre-smooth of the
 // finest level: no u read, no ghosts).
-template <typename Real, int MODE>
-__global__ void __launch_bounds__(TPB) k_smooth(LevelView lv, SlotVec<Real> usrc, SlotVec<Real> udst,
+template <typename Real, int MODE, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) k_smooth(LevelView lv, SlotVec<Real> usrc, SlotVec<Real> udst,
                                                 SlotVec<Real> fvec, const Real *__restrict__ Wl, Real h, Real invh,
                                                 Real omega, const double *__restrict__ fmean) {
   __shared__ Real ex[512];
@@ -296,6 +297,27 @@ inline int grid_for(const CupCtx *c, long long nwork, int per_sm) {
   return (int)g;
 }
 
+static int smooth_minb() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("CUP_SMOOTH_MINB");
+    v = e ? atoi(e) : 8;
+  }
+  return v;
+}
+
+template <typename Real>
+void launch_smooth0(CupCtx *c, int grid, LevelView lv, SlotVec<Real> src, SlotVec<Real> dst, SlotVec<Real> f, Real h,
+                    Real invh, Real om, const double *fmean) {
+  const Real *W = (const Real *)c->d_W;
+  switch (smooth_minb()) {
+  case 10: k_smooth<Real, 0, 10><<<grid, TPB, 0, c->stream>>>(lv, src, dst, f, W, h, invh, om, fmean); break;
+  case 12: k_smooth<Real, 0, 12><<<grid, TPB, 0, c->stream>>>(lv, src, dst, f, W, h, invh, om, fmean); break;
+  case 16: k_smooth<Real, 0, 16><<<grid, TPB, 0, c->stream>>>(lv, src, dst, f, W, h, invh, om, fmean); break;
+  default: k_smooth<Real, 0, 8><<<grid, TPB, 0, c->stream>>>(lv, src, dst, f, W, h, invh, om, fmean); break;
+  }
+}
+
 template <typename Real>
 int smooth_level(CupCtx *c, const Level &v, int n, Arr<Real> &a, bool first_is_zero, const double *fmean) {
   if (v.act.empty() || n == 0)
@@ -310,11 +332,10 @@ int smooth_level(CupCtx *c, const Level &v, int n, Arr<Real> &a, bool first_is_z
     SlotVec<Real> &src = (it & 1) ? a.u1 : a.u0;
     SlotVec<Real> &dst = (it & 1) ? a.u0 : a.u1;
     if (it == 0 && first_is_zero)
-      k_smooth<Real, 1><<<grid, TPB, 0, c->stream>>>(view(v), src, dst, a.f, (const Real *)c->d_W, h, invh, om,
-                                                      fmean);
+      k_smooth<Real, 1, 8><<<grid, TPB, 0, c->stream>>>(view(v), src, dst, a.f, (const Real *)c->d_W, h, invh, om,
+                                                         fmean);
     else
-      k_smooth<Real, 0><<<grid, TPB, 0, c->stream>>>(view(v), src, dst, a.f, (const Real *)c->d_W, h, invh, om,
-                                                      fmean);
+      launch_smooth0<Real>(c, grid, view(v), src, dst, a.f, h, invh, om, fmean);
     c->launches++;
   }
   if (n & 1) {
@@ -587,8 +608,7 @@ int time_smooth(CupCtx *c, int level, int reps, float *ms) {
     SlotVec<double> f{(double *)c->state[CUP_F_LHS], (double *)c->f_x, nleaf};
     CUP_CUDA(cudaEventRecord(e0, c->stream));
     for (int r = 0; r < reps; r++)
-      k_smooth<double, 0><<<grid, TPB, 0, c->stream>>>(view(v), (r & 1) ? d : s, (r & 1) ? s : d, f,
-                                                        (const double *)c->d_W, v.h, 1.0 / v.h, 0.8, nullptr);
+      launch_smooth0<double>(c, grid, view(v), (r & 1) ? d : s, (r & 1) ? s : d, f, v.h, 1.0 / v.h, 0.8, nullptr);
     CUP_CUDA(cudaEventRecord(e1, c->stream));
   } else {
     SlotVec<float> s{(float *)c->state[CUP_F_PRES], (float *)c->u0_x, nleaf};
@@ -596,9 +616,8 @@ int time_smooth(CupCtx *c, int level, int reps, float *ms) {
     SlotVec<float> f{(float *)c->state[CUP_F_LHS], (float *)c->f_x, nleaf};
     CUP_CUDA(cudaEventRecord(e0, c->stream));
     for (int r = 0; r < reps; r++)
-      k_smooth<float, 0><<<grid, TPB, 0, c->stream>>>(view(v), (r & 1) ? d : s, (r & 1) ? s : d, f,
-                                                       (const float *)c->d_W, (float)v.h, (float)(1.0 / v.h), 0.8f,
-                                                       nullptr);
+      launch_smooth0<float>(c, grid, view(v), (r & 1) ? d : s, (r & 1) ? s : d, f, (float)v.h, (float)(1.0 / v.h),
+                            0.8f, nullptr);
     CUP_CUDA(cudaEventRecord(e1, c->stream));
   }
   c->launches += reps;

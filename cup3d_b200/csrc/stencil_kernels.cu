@@ -1,8 +1,486 @@
-// stencil_kernels.cu -- per-block stencil sweeps (placeholder until the
-// kernels land; every entry fails loudly rather than falling back).
+// stencil_kernels.cu -- the per-block stencil sweeps and the time-step drivers
+// built on them (uniform-level meshes: every face neighbour is a same-level
+// block or a domain wall).
+//
+// Reference (main.c): k_advdiff :4986 / advdiff :5027, k_prhs :5663, k_divp
+// :5700, k_gradp :5715, k_lhs :4254, projection :5828, wall BC OP_BC :3524.
+//
+// Decomposition as in mg_device.cuh: one 8^3 block per 64 threads, thread
+// (x, y) owns a z-line in registers, x/y neighbours through shared memory.
+// Wall ghosts copy the nearest interior cell, with the wall-normal component of
+// vector fields negated (free slip; gen_table.py:195-231).
+#include <cmath>
+
+#include "blas_kernels.cuh"
 #include "cup_internal.h"
+#include "mg_device.cuh"
+
 namespace cup {
-int advdiff(CupCtx *) { set_error("advdiff: not built yet"); return CUP_ERR_UNSUPPORTED; }
-int projection(CupCtx *, CupSolveInfo *) { set_error("projection: not built yet"); return CUP_ERR_UNSUPPORTED; }
-int stencil_run(CupCtx *, CupStencilId, const long long *, long long) { set_error("stencil_run: not built yet"); return CUP_ERR_UNSUPPORTED; }
+
+struct Vec3P {
+  const void *c[3];
+};
+struct Vec3W {
+  void *c[3];
+};
+
+// ---------------------------------------------------------------------------
+// k_advdiff: TMP_c += fac_a * (u . grad) u_c + fac_d * lap u_c
+// ---------------------------------------------------------------------------
+template <typename Real>
+__device__ __forceinline__ Real upwind(Real U, Real um3, Real um2, Real um1, Real u, Real up1, Real up2, Real up3) {
+  // derivative(), main.c:4980-4985: 5th-order upwind-biased, /60
+  if (U > 0)
+    return (((((Real)-2 * um3 + (Real)15 * um2) - (Real)60 * um1) + (Real)20 * u) + (Real)30 * up1 - (Real)3 * up2) /
+           (Real)60.;
+  return ((((((Real)2 * up3 - (Real)15 * up2) + (Real)60 * up1) - (Real)20 * u) - (Real)30 * um1) + (Real)3 * um2) /
+         (Real)60.;
 }
+
+enum { AD_ROW = 16, AD_SLAB = 14 * 16 };  // padded tile: [8 z][14 y][16 x], halo offset 3
+
+template <typename Real>
+__global__ void __launch_bounds__(TPB) k_advdiff(LevelView lv, const Real *__restrict__ v0, const Real *__restrict__ v1,
+                                                 const Real *__restrict__ v2, Real *__restrict__ t0,
+                                                 Real *__restrict__ t1, Real *__restrict__ t2, Real fac_a, Real fac_d,
+                                                 Real ux, Real uy, Real uz) {
+  __shared__ Real tile[8 * AD_SLAB];
+  const int t = threadIdx.x, x = t & 7, y = t >> 3;
+  const int a = t & 7, c2 = t >> 3;  // halo element coordinates
+  const Real *vel[3] = {v0, v1, v2};
+  Real *tmp[3] = {t0, t1, t2};
+  const Real uinf[3] = {ux, uy, uz};
+  for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
+    const size_t own = (size_t)lv.act[b] * 512;
+    const int *nbr6 = lv.nbr + (size_t)b * 6;
+    int nb[6];
+#pragma unroll
+    for (int f = 0; f < 6; f++)
+      nb[f] = nbr6[f];
+    Real vv[3][8];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        vv[c][k] = vel[c][own + k * 64 + t];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const Real *vc = vel[c];
+      // z-extended line: ghost layers -3..-1 and 8..10
+      Real line[14];
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        line[3 + k] = vv[c][k];
+      {
+        const Real sg = (c == 2) ? (Real)-1 : (Real)1;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          line[i] = nb[4] >= 0 ? vc[(size_t)nb[4] * 512 + (5 + i) * 64 + t] : sg * vv[c][0];
+          line[11 + i] = nb[5] >= 0 ? vc[(size_t)nb[5] * 512 + i * 64 + t] : sg * vv[c][7];
+        }
+      }
+      __syncthreads();  // previous component's tile fully consumed
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        tile[k * AD_SLAB + (y + 3) * AD_ROW + (x + 3)] = vv[c][k];
+      {
+        const Real sx = (c == 0) ? (Real)-1 : (Real)1, sy = (c == 1) ? (Real)-1 : (Real)1;
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+          // -x / +x: element (y = a, z = c2)
+          const Real xm = nb[0] >= 0 ? vc[(size_t)nb[0] * 512 + c2 * 64 + a * 8 + (5 + p)] : sx * vc[own + c2 * 64 + a * 8];
+          const Real xp = nb[1] >= 0 ? vc[(size_t)nb[1] * 512 + c2 * 64 + a * 8 + p] : sx * vc[own + c2 * 64 + a * 8 + 7];
+          tile[c2 * AD_SLAB + (a + 3) * AD_ROW + p] = xm;
+          tile[c2 * AD_SLAB + (a + 3) * AD_ROW + 11 + p] = xp;
+          // -y / +y: element (x = a, z = c2)
+          const Real ym = nb[2] >= 0 ? vc[(size_t)nb[2] * 512 + c2 * 64 + (5 + p) * 8 + a] : sy * vc[own + c2 * 64 + a];
+          const Real yp = nb[3] >= 0 ? vc[(size_t)nb[3] * 512 + c2 * 64 + p * 8 + a] : sy * vc[own + c2 * 64 + 56 + a];
+          tile[c2 * AD_SLAB + p * AD_ROW + (a + 3)] = ym;
+          tile[c2 * AD_SLAB + (11 + p) * AD_ROW + (a + 3)] = yp;
+        }
+      }
+      __syncthreads();
+      Real *oc = tmp[c];
+      const int a1 = (c + 1) % 3, a2 = (c + 2) % 3;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const Real *row = tile + k * AD_SLAB + (y + 3) * AD_ROW + (x + 3);
+        const Real u = line[3 + k];
+        Real dd[3], pr[3];
+        const Real U0 = vv[0][k] + uinf[0], U1 = vv[1][k] + uinf[1], U2 = vv[2][k] + uinf[2];
+        dd[0] = upwind<Real>(U0, row[-3], row[-2], row[-1], u, row[1], row[2], row[3]);
+        pr[0] = row[1] + row[-1];
+        dd[1] = upwind<Real>(U1, row[-3 * AD_ROW], row[-2 * AD_ROW], row[-AD_ROW], u, row[AD_ROW], row[2 * AD_ROW],
+                             row[3 * AD_ROW]);
+        pr[1] = row[AD_ROW] + row[-AD_ROW];
+        dd[2] = upwind<Real>(U2, line[k], line[k + 1], line[k + 2], u, line[k + 4], line[k + 5], line[k + 6]);
+        pr[2] = line[k + 4] + line[k + 2];
+        const Real Uabs[3] = {U0, U1, U2};
+        const Real adv = Uabs[c] * dd[c] + (Uabs[a1] * dd[a1] + Uabs[a2] * dd[a2]);
+        const Real lap = (pr[c] + (pr[a1] + pr[a2])) - (Real)6 * u;
+        oc[own + k * 64 + t] += fac_a * adv + fac_d * lap;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// RK3 stage update (advdiff, main.c:5039-5054): V += TMP*alpha/h^3 ; TMP *= beta
+template <typename Real>
+__global__ void __launch_bounds__(256) k_rk_update(Real *__restrict__ v, Real *__restrict__ tm, long long n, Real ih3,
+                                                   Real beta) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const Real tv = tm[i];
+    v[i] += tv * ih3;
+    tm[i] = tv * beta;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// k_prhs: LHS = fac*div(u) - chi*fac*div(udef), fac = h^2/(2 dt)   (main.c:5663)
+// Only the face-normal component is needed on each face: u on x faces, v on y
+// faces, w on z faces (and the same of udef), so the halo is 6 components x 2
+// faces instead of 6 x 6.
+// ---------------------------------------------------------------------------
+template <typename Real>
+__global__ void __launch_bounds__(TPB) k_prhs(LevelView lv, const Real *__restrict__ v0, const Real *__restrict__ v1,
+                                              const Real *__restrict__ v2, const Real *__restrict__ d0,
+                                              const Real *__restrict__ d1, const Real *__restrict__ d2,
+                                              const Real *__restrict__ chi, Real *__restrict__ lhs, Real fac) {
+  __shared__ Real tl[4][512];      // u, v, udef_x, udef_y cores
+  __shared__ Real hl[4][2][64];    // their -/+ faces (x faces for u/udef_x, y faces for v/udef_y)
+  const int t = threadIdx.x, x = t & 7, y = t >> 3;
+  const int a = t & 7, c2 = t >> 3;
+  for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
+    const size_t own = (size_t)lv.act[b] * 512;
+    const int *nbr6 = lv.nbr + (size_t)b * 6;
+    const int n0 = nbr6[0], n1 = nbr6[1], n2 = nbr6[2], n3 = nbr6[3], n4 = nbr6[4], n5 = nbr6[5];
+    Real w[8], dz[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      tl[0][k * 64 + t] = v0[own + k * 64 + t];
+      tl[1][k * 64 + t] = v1[own + k * 64 + t];
+      tl[2][k * 64 + t] = d0[own + k * 64 + t];
+      tl[3][k * 64 + t] = d1[own + k * 64 + t];
+      w[k] = v2[own + k * 64 + t];
+      dz[k] = d2[own + k * 64 + t];
+    }
+    // x faces of u and udef_x: element (y = a, z = c2); wall: -own (normal component flips)
+    hl[0][0][t] = n0 >= 0 ? v0[(size_t)n0 * 512 + c2 * 64 + a * 8 + 7] : -v0[own + c2 * 64 + a * 8];
+    hl[0][1][t] = n1 >= 0 ? v0[(size_t)n1 * 512 + c2 * 64 + a * 8] : -v0[own + c2 * 64 + a * 8 + 7];
+    hl[2][0][t] = n0 >= 0 ? d0[(size_t)n0 * 512 + c2 * 64 + a * 8 + 7] : -d0[own + c2 * 64 + a * 8];
+    hl[2][1][t] = n1 >= 0 ? d0[(size_t)n1 * 512 + c2 * 64 + a * 8] : -d0[own + c2 * 64 + a * 8 + 7];
+    // y faces of v and udef_y: element (x = a, z = c2)
+    hl[1][0][t] = n2 >= 0 ? v1[(size_t)n2 * 512 + c2 * 64 + 56 + a] : -v1[own + c2 * 64 + a];
+    hl[1][1][t] = n3 >= 0 ? v1[(size_t)n3 * 512 + c2 * 64 + a] : -v1[own + c2 * 64 + 56 + a];
+    hl[3][0][t] = n2 >= 0 ? d1[(size_t)n2 * 512 + c2 * 64 + 56 + a] : -d1[own + c2 * 64 + a];
+    hl[3][1][t] = n3 >= 0 ? d1[(size_t)n3 * 512 + c2 * 64 + a] : -d1[own + c2 * 64 + 56 + a];
+    // z faces of w and udef_z straight into registers
+    const Real wzm = n4 >= 0 ? v2[(size_t)n4 * 512 + 448 + t] : -w[0];
+    const Real wzp = n5 >= 0 ? v2[(size_t)n5 * 512 + t] : -w[7];
+    const Real dzm = n4 >= 0 ? d2[(size_t)n4 * 512 + 448 + t] : -dz[0];
+    const Real dzp = n5 >= 0 ? d2[(size_t)n5 * 512 + t] : -dz[7];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int i = k * 64 + t;
+      const Real uxp = x < 7 ? tl[0][i + 1] : hl[0][1][y + 8 * k];
+      const Real uxm = x > 0 ? tl[0][i - 1] : hl[0][0][y + 8 * k];
+      const Real vyp = y < 7 ? tl[1][i + 8] : hl[1][1][x + 8 * k];
+      const Real vym = y > 0 ? tl[1][i - 8] : hl[1][0][x + 8 * k];
+      const Real wzp_ = k < 7 ? w[k < 7 ? k + 1 : 7] : wzp;
+      const Real wzm_ = k > 0 ? w[k > 0 ? k - 1 : 0] : wzm;
+      const Real dxp = x < 7 ? tl[2][i + 1] : hl[2][1][y + 8 * k];
+      const Real dxm = x > 0 ? tl[2][i - 1] : hl[2][0][y + 8 * k];
+      const Real dyp = y < 7 ? tl[3][i + 8] : hl[3][1][x + 8 * k];
+      const Real dym = y > 0 ? tl[3][i - 8] : hl[3][0][x + 8 * k];
+      const Real dzp_ = k < 7 ? dz[k < 7 ? k + 1 : 7] : dzp;
+      const Real dzm_ = k > 0 ? dz[k > 0 ? k - 1 : 0] : dzm;
+      Real p = fac * (((((uxp - uxm) + vyp) - vym) + wzp_) - wzm_);
+      const Real div_us = ((((dxp - dxm) + dyp) - dym) + dzp_) - dzm_;
+      p += -chi[own + i] * fac * div_us;
+      lhs[own + i] = p;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// k_divp (main.c:5700): TMP0 = h * (sum of 6 neighbours - 6 p); note the
+// summation order differs from k_lhs.   k_gradp (:5715): TMP_a = fac*(p+ - p-).
+// ---------------------------------------------------------------------------
+template <typename Real, int WHAT>  // 0 divp, 1 gradp
+__global__ void __launch_bounds__(TPB) k_pres(LevelView lv, const Real *__restrict__ p, Real *__restrict__ o0,
+                                              Real *__restrict__ o1, Real *__restrict__ o2, Real fac) {
+  __shared__ Real tu[512];
+  __shared__ Real halo[6][64];
+  const int t = threadIdx.x, x = t & 7, y = t >> 3;
+  SlotVec<Real> pv{const_cast<Real *>(p), nullptr, 0x7fffffff};
+  for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
+    const size_t own = (size_t)lv.act[b] * 512;
+    Real uu[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      uu[k] = p[own + k * 64 + t];
+      tu[k * 64 + t] = uu[k];
+    }
+    load_halo<Real>(pv, p + own, lv.nbr + (size_t)b * 6, t, halo);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int i = k * 64 + t;
+      const Real xm = x > 0 ? tu[i - 1] : halo[0][y + 8 * k];
+      const Real xp = x < 7 ? tu[i + 1] : halo[1][y + 8 * k];
+      const Real ym = y > 0 ? tu[i - 8] : halo[2][x + 8 * k];
+      const Real yp = y < 7 ? tu[i + 8] : halo[3][x + 8 * k];
+      const Real zm = k > 0 ? uu[k > 0 ? k - 1 : 0] : halo[4][t];
+      const Real zp = k < 7 ? uu[k < 7 ? k + 1 : 7] : halo[5][t];
+      if (WHAT == 0) {
+        o0[own + i] = fac * ((((((xp + xm) + yp) + ym) + zp) + zm) - (Real)6.0 * uu[k]);
+      } else {
+        o0[own + i] = fac * (xp - xm);
+        o1[own + i] = fac * (yp - ym);
+        o2[own + i] = fac * (zp - zm);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// pointwise pieces of projection() (main.c:5841-5916)
+// ---------------------------------------------------------------------------
+template <typename Real>
+__global__ void __launch_bounds__(256) k_lhs_minus(Real *__restrict__ lhs, const Real *__restrict__ b,
+                                                   Real *__restrict__ p, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    lhs[i] -= b[i];
+    p[i] = 0;
+  }
+}
+
+// p -= avg ; p += p_old (optional), avg = scal[0]/scal[1]
+template <typename Real>
+__global__ void __launch_bounds__(256) k_pres_fix(Real *__restrict__ p, const Real *__restrict__ pold, long long n,
+                                                  const double *__restrict__ scal, double vol) {
+  const Real avg = (Real)(scal[0] / vol);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    Real v = p[i] - avg;
+    if (pold)
+      v += pold[i];
+    p[i] = v;
+  }
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256) k_vel_add(Real *__restrict__ v, const Real *__restrict__ g, long long n,
+                                                 Real fac) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    v[i] += fac * g[i];
+}
+
+// sum_i p_i * h_i^3 over leaves -> out (projection's avg, :5873-5882)
+template <typename Real>
+__global__ void __launch_bounds__(256) k_wsum_blk(const Real *__restrict__ a, const Real *__restrict__ h3,
+                                                  long long nblk, double *out) {
+  __shared__ double red[8];
+  double s = 0;
+  for (long long b = blockIdx.x; b < nblk; b += gridDim.x) {
+    const Real *p = a + b * 512;
+    s += ((double)p[threadIdx.x] + (double)p[threadIdx.x + 256]) * (double)h3[b];
+  }
+  for (int o = 16; o > 0; o >>= 1)
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0)
+    red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0;
+    for (int i = 0; i < 8; i++)
+      tot += red[i];
+    atomicAdd(out, tot);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+namespace {
+
+inline int sgrid(const CupCtx *c, long long n) {
+  long long g = (n + 255) / 256, cap = (long long)c->num_sms * 8;
+  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+inline int bgrid(const CupCtx *c, long long nb, int per_sm) {
+  long long g = (long long)c->num_sms * per_sm;
+  return (int)(g < nb ? g : (nb < 1 ? 1 : nb));
+}
+
+const Level *leaf_level(CupCtx *c) {
+  int top = c->top;
+  while (top > 0 && c->lv[top].act.empty())
+    top--;
+  return &c->lv[top];
+}
+
+int need_uniform(CupCtx *c, const char *what) {
+  if (c->nblk == 0) {
+    set_error("%s: no mesh uploaded", what);
+    return CUP_ERR_STATE;
+  }
+  if (!c->leaf_uniform) {
+    set_error("%s: multi-level (AMR) meshes are not available in this build", what);
+    return CUP_ERR_UNSUPPORTED;
+  }
+  return CUP_OK;
+}
+
+template <typename Real>
+int stencil_t(CupCtx *c, CupStencilId id, const int *d_sub, long long nsub) {
+  const Level &v = *leaf_level(c);
+  LevelView lv{v.d_act, v.d_nbr, (int)v.act.size()};
+  if (d_sub) {
+    set_error("stencil_run: block sub-lists are only supported for CUP_ST_MG/CUP_ST_LHS");
+    return CUP_ERR_UNSUPPORTED;
+  }
+  (void)nsub;
+  Real **S = (Real **)c->state;
+  const Real h = (Real)v.h;
+  const double dt = c->prm.dt, hd = v.h;
+  switch (id) {
+  case CUP_ST_ADVDIFF: {
+    // fac_a = -dt/h*h^3 ; fac_d = (nu/h)*(dt/h)*h^3   (main.c:4993-4995, coef = 1)
+    const double h3 = hd * hd * hd;
+    const double fa = -dt / hd * h3 * 1.0, fd = (c->prm.nu / hd) * (dt / hd) * h3 * 1.0;
+    k_advdiff<Real><<<bgrid(c, c->nblk, 8), TPB, 0, c->stream>>>(
+        lv, S[CUP_F_VEL], S[CUP_F_VEL + 1], S[CUP_F_VEL + 2], S[CUP_F_TMP], S[CUP_F_TMP + 1], S[CUP_F_TMP + 2],
+        (Real)fa, (Real)fd, (Real)c->prm.uinf[0], (Real)c->prm.uinf[1], (Real)c->prm.uinf[2]);
+    break;
+  }
+  case CUP_ST_PRHS: {
+    const double fac = 0.5 * hd * hd / dt;
+    k_prhs<Real><<<bgrid(c, c->nblk, 8), TPB, 0, c->stream>>>(lv, S[CUP_F_VEL], S[CUP_F_VEL + 1], S[CUP_F_VEL + 2],
+                                                              S[CUP_F_TMP], S[CUP_F_TMP + 1], S[CUP_F_TMP + 2],
+                                                              S[CUP_F_CHI], S[CUP_F_LHS], (Real)fac);
+    break;
+  }
+  case CUP_ST_DIVP:
+    k_pres<Real, 0><<<bgrid(c, c->nblk, 12), TPB, 0, c->stream>>>(lv, S[CUP_F_PRES], S[CUP_F_TMP], nullptr, nullptr,
+                                                                  h);
+    break;
+  case CUP_ST_GRADP: {
+    const double fac = -0.5 * dt * hd * hd;
+    k_pres<Real, 1><<<bgrid(c, c->nblk, 12), TPB, 0, c->stream>>>(lv, S[CUP_F_PRES], S[CUP_F_TMP], S[CUP_F_TMP + 1],
+                                                                  S[CUP_F_TMP + 2], (Real)fac);
+    break;
+  }
+  case CUP_ST_LHS:
+  case CUP_ST_MG: {
+    // k_lhs / k_mg on the state: F_PRES -> F_LHS, no mean term (that is pois_op's)
+    const int mc = c->prm.mean_constraint;
+    c->prm.mean_constraint = 0;
+    int rc = pois_op_dev(c, S[CUP_F_PRES], S[CUP_F_LHS]);
+    c->prm.mean_constraint = mc;
+    return rc;
+  }
+  default:
+    set_error("stencil_run: unknown stencil id %d", (int)id);
+    return CUP_ERR_ARG;
+  }
+  c->launches++;
+  CUP_CUDA(cudaGetLastError());
+  return CUP_OK;
+}
+
+template <typename Real>
+int advdiff_t(CupCtx *c) {
+  // 3-stage low-storage RK (Williamson), main.c:5027-5056
+  const double alpha[3] = {1.0 / 3.0, 15.0 / 16.0, 8.0 / 15.0};
+  const double beta[3] = {-5.0 / 9.0, -153.0 / 128.0, 0.0};
+  const Level &v = *leaf_level(c);
+  const long long N = c->nblk * 512;
+  const size_t rb = sizeof(Real);
+  Real **S = (Real **)c->state;
+  for (int q = 0; q < 3; q++)
+    CUP_CUDA(cudaMemsetAsync(S[CUP_F_TMP + q], 0, N * rb, c->stream));
+  for (int s = 0; s < 3; s++) {
+    CUP_TRY(stencil_t<Real>(c, CUP_ST_ADVDIFF, nullptr, 0));
+    const double ih3 = alpha[s] / (v.h * v.h * v.h);
+    for (int q = 0; q < 3; q++) {
+      k_rk_update<Real><<<sgrid(c, N), 256, 0, c->stream>>>(S[CUP_F_VEL + q], S[CUP_F_TMP + q], N, (Real)ih3,
+                                                             (Real)beta[s]);
+      c->launches++;
+    }
+  }
+  CUP_CUDA(cudaGetLastError());
+  return CUP_OK;
+}
+
+template <typename Real>
+int projection_t(CupCtx *c, CupSolveInfo *info) {
+  const Level &v = *leaf_level(c);
+  const long long N = c->nblk * 512;
+  const size_t rb = sizeof(Real);
+  Real **S = (Real **)c->state;
+  enum { STEP_2ND = 2 };  // main.c:130
+  // p_old = p ; TMP = 0   (fish_tmpv would add udef into TMP here: the caller uploads F_TMP
+  // already containing it when fish are present -- see INTEGRATION.md)
+  CUP_CUDA(cudaMemcpyAsync(c->p_old, S[CUP_F_PRES], N * rb, cudaMemcpyDeviceToDevice, c->stream));
+  if (!c->keep_tmp_udef)
+    for (int q = 0; q < 3; q++)
+      CUP_CUDA(cudaMemsetAsync(S[CUP_F_TMP + q], 0, N * rb, c->stream));
+  CUP_TRY(stencil_t<Real>(c, CUP_ST_PRHS, nullptr, 0));
+  if (c->prm.step > STEP_2ND) {
+    CUP_TRY(stencil_t<Real>(c, CUP_ST_DIVP, nullptr, 0));
+    k_lhs_minus<Real><<<sgrid(c, N), 256, 0, c->stream>>>(S[CUP_F_LHS], S[CUP_F_TMP], S[CUP_F_PRES], N);
+    c->launches++;
+  } else {
+    CUP_CUDA(cudaMemsetAsync(S[CUP_F_PRES], 0, N * rb, c->stream));
+  }
+  CUP_TRY(pois_solve(c, info));
+  // subtract the volume-weighted mean (main.c:5871-5895)
+  double vol = 0;
+  for (long long i = 0; i < c->nblk; i++)
+    vol += 512 * (c->blk[i].h * c->blk[i].h * c->blk[i].h);
+  double *q = c->d_scal + 5;
+  CUP_CUDA(cudaMemsetAsync(q, 0, sizeof(double), c->stream));
+  k_wsum_blk<Real><<<bgrid(c, c->nblk, 8), 256, 0, c->stream>>>(S[CUP_F_PRES], (const Real *)c->d_hw, c->nblk, q);
+  c->launches++;
+  k_pres_fix<Real><<<sgrid(c, N), 256, 0, c->stream>>>(S[CUP_F_PRES],
+                                                        c->prm.step > STEP_2ND ? (const Real *)c->p_old : nullptr, N, q,
+                                                        vol);
+  c->launches++;
+  CUP_TRY(stencil_t<Real>(c, CUP_ST_GRADP, nullptr, 0));
+  const double fac = 1.0 / (v.h * v.h * v.h);
+  for (int a = 0; a < 3; a++) {
+    k_vel_add<Real><<<sgrid(c, N), 256, 0, c->stream>>>(S[CUP_F_VEL + a], S[CUP_F_TMP + a], N, (Real)fac);
+    c->launches++;
+  }
+  CUP_CUDA(cudaGetLastError());
+  CUP_CUDA(cudaStreamSynchronize(c->stream));
+  return CUP_OK;
+}
+
+}  // namespace
+
+int stencil_run(CupCtx *c, CupStencilId id, const long long *list, long long n) {
+  CUP_TRY(need_uniform(c, "stencil_run"));
+  if (list != nullptr && n != c->nblk) {
+    set_error("stencil_run: block sub-lists are not supported yet (n=%lld of %lld)", n, c->nblk);
+    return CUP_ERR_UNSUPPORTED;
+  }
+  return c->real_bytes == 8 ? stencil_t<double>(c, id, nullptr, n) : stencil_t<float>(c, id, nullptr, n);
+}
+
+int advdiff(CupCtx *c) {
+  CUP_TRY(need_uniform(c, "advdiff"));
+  return c->real_bytes == 8 ? advdiff_t<double>(c) : advdiff_t<float>(c);
+}
+
+int projection(CupCtx *c, CupSolveInfo *info) {
+  CUP_TRY(need_uniform(c, "projection"));
+  return c->real_bytes == 8 ? projection_t<double>(c, info) : projection_t<float>(c, info);
+}
+
+}  // namespace cup

@@ -130,6 +130,10 @@ int cup_pois_dot_dev(CupCtx *ctx, const void *d_a, const void *d_b, double *resu
 int cup_pois_solve(CupCtx *ctx, CupSolveInfo *info);
 int cup_advdiff(CupCtx *ctx);
 int cup_projection(CupCtx *ctx, CupSolveInfo *info);
+/* projection() zeroes F_TMP and lets fish_tmpv() (host, main.c:5799) add the
+ * deformation velocity before the divergence sweep.  With flag != 0 the caller
+ * has uploaded F_TMP = fish_tmpv() result already and the zeroing is skipped. */
+int cup_projection_udef_ready(CupCtx *ctx, int flag);
 
 /* One rank per GPU.  nccl_id = the 128 bytes of an ncclUniqueId created on
  * rank 0 and distributed by the caller (torch.distributed / MPI_Bcast). */

@@ -1,0 +1,53 @@
+#!/usr/bin/env python3
+"""oracle/cpu_baseline.py -- TEST/BENCH INFRASTRUCTURE ONLY.
+
+Times the reference's own CPU V-cycle (mg_vcycle, main.c:4831) on the host
+cores: oracle/_ref (the unmodified reference, OpenMP over all cores) when it
+was built, else the C restatement oracle/libcup_oracle.so.  Run as a
+subprocess by bench.py because the reference keeps its mesh in file-statics.
+Prints one JSON line.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--level", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    a = ap.parse_args()
+    L = a.level
+    from oracle import refbind as R
+    if R.available():
+        R.init(levelStart=L, levelMax=L + 1)
+        n = R.nblk()
+        ib, rb = R.blocks()
+        b = np.zeros((n, 512))
+        lo = rb[:, 1:4]
+        hi = lo + 8 * rb[:, 0:1]
+        for p, v in ((0.25, 1.0), (0.75, -1.0)):
+            i = int(np.nonzero(np.all((lo <= p) & (p < hi), axis=1))[0][0])
+            b[i, 0] = v
+        sec = R.time_vcycle(b, a.warmup, a.steps)
+        kind, threads = "reference", R.threads()
+        what = "unmodified reference main.c (oracle/_ref), gcc -O3 -fopenmp, %d OpenMP threads, 1 rank" % threads
+    else:
+        from oracle import portbind as P
+        sec, n, threads = P.time_vcycle_uniform(L, a.warmup, a.steps)
+        kind = "port"
+        what = "C restatement oracle/cup_oracle.c, %d OpenMP threads" % threads
+    cells = n * 512
+    print(json.dumps({"cell_updates_per_s": cells * a.steps / sec, "ms_per_cycle": 1e3 * sec / a.steps,
+                      "threads": threads, "kind": kind, "what": what, "cells": cells}))
+
+
+if __name__ == "__main__":
+    main()
