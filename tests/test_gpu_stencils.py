@@ -70,7 +70,8 @@ def test_projection(built, name, step):
     out = np.zeros_like(s0)
     ctx.state_d2h(out)
     ref = c.g["proj_step%d" % step]  # PRES, VEL(3)
-    assert info.residual < 1e-10
+    # pois_solve stops on ptol OR ptol_rel*|rhs| (main.c:4915)
+    assert info.residual < max(1e-10, 1e-12 * info.rhs_norm)
     ep = relerr(out[:, 1], ref[:, 0])
     ev = relerr(out[:, 2:5], ref[:, 1:4])
     assert ep < 1e-7 and ev < 1e-9, (ep, ev, info.iterations)
