@@ -3,6 +3,7 @@
 
 #include "blas_kernels.cuh"
 #include "cup_internal.h"
+#include "smooth_tma.cuh"
 
 namespace cup {
 
@@ -117,6 +118,7 @@ int cup_destroy(CupCtx *c) {
   cudaDeviceSynchronize();
   free_krylov(c);
   free_mesh(c);
+  free_tma_cache(c);
   for (int f = 0; f < CUP_F_N; f++)
     cudaFree(c->state[f]);
   cudaFree(c->u1_leaf);

@@ -81,6 +81,7 @@ struct CupCtx {
   cup::Krylov *kr = nullptr;
   long long launches = 0;
   void *p_old = nullptr;        // projection(): previous pressure
+  void *tma_cache = nullptr;    // tensor-map cache (smooth_tma.cu)
   bool keep_tmp_udef = false;   // projection(): F_TMP already holds fish_tmpv()'s udef
 };
 

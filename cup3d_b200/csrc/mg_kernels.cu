@@ -12,6 +12,7 @@
 
 #include "cup_internal.h"
 #include "mg_device.cuh"
+#include "smooth_tma.cuh"
 
 namespace cup {
 
@@ -297,6 +298,16 @@ inline int grid_for(const CupCtx *c, long long nwork, int per_sm) {
   return (int)g;
 }
 
+// CUP_SMOOTH_IMPL=ldg selects the plain-load smoother (k_smooth) instead of the TMA one
+static bool smooth_use_tma() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("CUP_SMOOTH_IMPL");
+    v = (e && strcmp(e, "ldg") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static int smooth_minb() {
   static int v = -1;
   if (v < 0) {
@@ -307,15 +318,18 @@ static int smooth_minb() {
 }
 
 template <typename Real>
-void launch_smooth0(CupCtx *c, int grid, LevelView lv, SlotVec<Real> src, SlotVec<Real> dst, SlotVec<Real> f, Real h,
-                    Real invh, Real om, const double *fmean) {
+int launch_smooth0(CupCtx *c, int grid, LevelView lv, SlotVec<Real> src, SlotVec<Real> dst, SlotVec<Real> f, Real h,
+                   Real invh, Real om, const double *fmean) {
   const Real *W = (const Real *)c->d_W;
+  if (smooth_use_tma())
+    return smooth_tma_launch<Real>(c, grid, lv, src, dst, f, h, invh, om, fmean);
   switch (smooth_minb()) {
   case 10: k_smooth<Real, 0, 10><<<grid, TPB, 0, c->stream>>>(lv, src, dst, f, W, h, invh, om, fmean); break;
   case 12: k_smooth<Real, 0, 12><<<grid, TPB, 0, c->stream>>>(lv, src, dst, f, W, h, invh, om, fmean); break;
   case 16: k_smooth<Real, 0, 16><<<grid, TPB, 0, c->stream>>>(lv, src, dst, f, W, h, invh, om, fmean); break;
   default: k_smooth<Real, 0, 8><<<grid, TPB, 0, c->stream>>>(lv, src, dst, f, W, h, invh, om, fmean); break;
   }
+  return CUP_OK;
 }
 
 template <typename Real>
@@ -326,7 +340,7 @@ int smooth_level(CupCtx *c, const Level &v, int n, Arr<Real> &a, bool first_is_z
     set_error("multigrid level %d has coarse-fine interfaces: AMR smoother not available in this build", v.L);
     return CUP_ERR_UNSUPPORTED;
   }
-  const int grid = grid_for(c, (long long)v.act.size(), 16);
+  const int grid = grid_for(c, (long long)v.act.size(), smooth_use_tma() ? 12 : 16);
   const Real h = (Real)v.h, invh = (Real)(1.0 / v.h), om = (Real)0.8;  // mg_omega, main.c:4434
   for (int it = 0; it < n; it++) {
     SlotVec<Real> &src = (it & 1) ? a.u1 : a.u0;
@@ -335,7 +349,7 @@ int smooth_level(CupCtx *c, const Level &v, int n, Arr<Real> &a, bool first_is_z
       k_smooth<Real, 1, 8><<<grid, TPB, 0, c->stream>>>(view(v), src, dst, a.f, (const Real *)c->d_W, h, invh, om,
                                                          fmean);
     else
-      launch_smooth0<Real>(c, grid, view(v), src, dst, a.f, h, invh, om, fmean);
+      CUP_TRY(launch_smooth0<Real>(c, grid, view(v), src, dst, a.f, h, invh, om, fmean));
     c->launches++;
   }
   if (n & 1) {
@@ -600,7 +614,7 @@ int time_smooth(CupCtx *c, int level, int reps, float *ms) {
   cudaEvent_t e0, e1;
   CUP_CUDA(cudaEventCreate(&e0));
   CUP_CUDA(cudaEventCreate(&e1));
-  const int grid = grid_for(c, (long long)v.act.size(), 16);
+  const int grid = grid_for(c, (long long)v.act.size(), smooth_use_tma() ? 12 : 16);
   // state[] vectors double as inputs: F_PRES as u, F_LHS as f, F_TMP as u'
   if (c->real_bytes == 8) {
     SlotVec<double> s{(double *)c->state[CUP_F_PRES], (double *)c->u0_x, nleaf};
@@ -608,7 +622,8 @@ int time_smooth(CupCtx *c, int level, int reps, float *ms) {
     SlotVec<double> f{(double *)c->state[CUP_F_LHS], (double *)c->f_x, nleaf};
     CUP_CUDA(cudaEventRecord(e0, c->stream));
     for (int r = 0; r < reps; r++)
-      launch_smooth0<double>(c, grid, view(v), (r & 1) ? d : s, (r & 1) ? s : d, f, v.h, 1.0 / v.h, 0.8, nullptr);
+      CUP_TRY(launch_smooth0<double>(c, grid, view(v), (r & 1) ? d : s, (r & 1) ? s : d, f, v.h, 1.0 / v.h, 0.8,
+                                     nullptr));
     CUP_CUDA(cudaEventRecord(e1, c->stream));
   } else {
     SlotVec<float> s{(float *)c->state[CUP_F_PRES], (float *)c->u0_x, nleaf};
@@ -616,8 +631,8 @@ int time_smooth(CupCtx *c, int level, int reps, float *ms) {
     SlotVec<float> f{(float *)c->state[CUP_F_LHS], (float *)c->f_x, nleaf};
     CUP_CUDA(cudaEventRecord(e0, c->stream));
     for (int r = 0; r < reps; r++)
-      launch_smooth0<float>(c, grid, view(v), (r & 1) ? d : s, (r & 1) ? s : d, f, (float)v.h, (float)(1.0 / v.h),
-                            0.8f, nullptr);
+      CUP_TRY(launch_smooth0<float>(c, grid, view(v), (r & 1) ? d : s, (r & 1) ? s : d, f, (float)v.h,
+                                    (float)(1.0 / v.h), 0.8f, nullptr));
     CUP_CUDA(cudaEventRecord(e1, c->stream));
   }
   c->launches += reps;

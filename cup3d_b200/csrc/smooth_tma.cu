@@ -1,0 +1,290 @@
+// smooth_tma.cu -- the production smoother: block-Jacobi sweep with TMA staging.
+//
+// Same arithmetic as k_smooth<Real,0> (mg_kernels.cu; reference mg_smooth,
+// main.c:4689) but every global read goes through the TMA engine:
+//
+//   u block, f block      1-D bulk copies (4 KB each in fp64)
+//   z faces               1-D bulk copies (one 8x8 plane is contiguous)
+//   y faces               3-D tensor-map boxes {8 x, 1 y, 8 z}
+//   x faces               3-D tensor-map boxes {16 bytes of x, 8 y, 8 z}
+//
+// all completing on one mbarrier.  The stage is consumed into registers at the
+// top of an iteration, so the loads of the NEXT block are issued before the
+// transforms of the current one start: HBM latency overlaps the FDM work
+// without holding registers, and the strided x-face gather costs no LSU
+// wavefronts.  One 8^3 block per 64-thread CTA iteration, persistent grid.
+#include <cuda.h>
+
+#include <map>
+#include <tuple>
+
+#include "cup_internal.h"
+#include "mg_device.cuh"
+#include "tma.cuh"
+
+namespace cup {
+
+template <typename Real>
+struct TmaCfg {
+  static constexpr int NCOL = 16 / (int)sizeof(Real);  // x columns per 16-byte TMA row
+  static constexpr uint32_t BYTES = (512 * 2 + 64 * 2 + 64 * 2 + 64 * NCOL * 2) * (uint32_t)sizeof(Real);
+};
+
+template <typename Real>
+__global__ void __launch_bounds__(TPB, 12)
+    k_smooth_tma(LevelView lv, SlotVec<Real> usrc, SlotVec<Real> udst, SlotVec<Real> fvec, const Real *__restrict__ Wl,
+                 Real h, Real invh, Real omega, const double *__restrict__ fmean,
+                 const __grid_constant__ CUtensorMap mx_leaf, const __grid_constant__ CUtensorMap my_leaf,
+                 const __grid_constant__ CUtensorMap mx_extra, const __grid_constant__ CUtensorMap my_extra) {
+  constexpr int NCOL = TmaCfg<Real>::NCOL;
+  __shared__ __align__(128) Real s_u[512];
+  __shared__ __align__(128) Real s_f[512];
+  __shared__ __align__(128) Real s_z[2][64];
+  __shared__ __align__(128) Real s_y[2][64];
+  __shared__ __align__(128) Real s_x[2][64 * NCOL];
+  __shared__ __align__(128) Real ex[512];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ int s_wall;  // bit f set: face f is a domain wall (ghost = own boundary plane)
+
+  const int t = threadIdx.x, x = t & 7, y = t >> 3;
+  const int G = gridDim.x;
+  Real w[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    w[k] = Wl[k * 64 + t];
+  const Real q0 = fmean ? (Real)(*fmean) : (Real)0;
+
+  // thread 0 is the TMA producer: stage one block (its u, f and six ghost faces)
+  auto issue = [&](int slot, const int (&nb)[6]) {
+    int wall = 0;
+#pragma unroll
+    for (int f = 0; f < 6; f++)
+      wall |= (nb[f] < 0) << f;
+    s_wall = wall;
+    mbar_arrive_expect_tx(&mbar, TmaCfg<Real>::BYTES);
+    const Real *own = usrc.at(slot);
+    tma_load_1d(s_u, own, 512 * sizeof(Real), &mbar);
+    tma_load_1d(s_f, fvec.at(slot), 512 * sizeof(Real), &mbar);
+    // z faces: neighbour's opposite plane, or own plane at a wall
+    tma_load_1d(s_z[0], nb[4] >= 0 ? usrc.at(nb[4]) + 7 * 64 : own, 64 * sizeof(Real), &mbar);
+    tma_load_1d(s_z[1], nb[5] >= 0 ? usrc.at(nb[5]) : own + 7 * 64, 64 * sizeof(Real), &mbar);
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+      const int ts = nb[f] >= 0 ? nb[f] : slot;
+      const bool leaf = ts < usrc.nleaf;
+      const int row0 = (leaf ? ts : ts - usrc.nleaf) * 8;
+      // plane inside the source block: opposite side for a neighbour, same side at a wall
+      const bool high = (nb[f] >= 0) ? !(f & 1) : (f & 1);
+      if (f < 2)
+        tma_load_3d(s_x[f], leaf ? &mx_leaf : &mx_extra, high ? 8 - NCOL : 0, 0, row0, &mbar);
+      else
+        tma_load_3d(s_y[f - 2], leaf ? &my_leaf : &my_extra, 0, high ? 7 : 0, row0, &mbar);
+    }
+  };
+
+  if (t == 0) {
+    mbar_init(&mbar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  int b = blockIdx.x;
+  if (t == 0 && b < lv.nact) {
+    int nb[6];
+#pragma unroll
+    for (int f = 0; f < 6; f++)
+      nb[f] = lv.nbr[(size_t)b * 6 + f];
+    issue(lv.act[b], nb);
+  }
+  uint32_t phase = 0;
+  for (; b < lv.nact; b += G) {
+    const int slot = lv.act[b];
+    // producer: fetch the NEXT block's indices now so they are in registers when needed
+    int nslot = 0, nnb[6] = {0, 0, 0, 0, 0, 0};
+    const bool more = (b + G) < lv.nact;
+    if (t == 0 && more) {
+      nslot = lv.act[b + G];
+#pragma unroll
+      for (int f = 0; f < 6; f++)
+        nnb[f] = lv.nbr[(size_t)(b + G) * 6 + f];
+    }
+    mbar_wait(&mbar, phase);
+    phase ^= 1;
+    const int wall = s_wall;
+    Real uu[8], v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      uu[k] = s_u[k * 64 + t];
+      v[k] = s_f[k * 64 + t];
+    }
+    {
+      // ghost sums (see ghost_sum in mg_device.cuh); x-face column depends on wall-ness
+      const int cxm = (wall & 1) ? 0 : NCOL - 1, cxp = (wall & 2) ? NCOL - 1 : 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        Real g = 0;
+        if (x == 0)
+          g += s_x[0][(k * 8 + y) * NCOL + cxm];
+        if (x == 7)
+          g += s_x[1][(k * 8 + y) * NCOL + cxp];
+        if (y == 0)
+          g += s_y[0][k * 8 + x];
+        if (y == 7)
+          g += s_y[1][k * 8 + x];
+        if (k == 0)
+          g += s_z[0][t];
+        if (k == 7)
+          g += s_z[1][t];
+        v[k] = invh * ((v[k] - q0) - h * g);
+      }
+    }
+    __syncthreads();  // stage fully consumed
+    if (t == 0 && more)
+      issue(nslot, nnb);
+    // forward z
+    dst8<Real>(v);
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      ex[sw(x, y, k)] = v[k];
+    __syncthreads();
+    {
+      const int x2 = t & 7, z2 = t >> 3;
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        v[k] = ex[sw(x2, k, z2)];
+      dst8<Real>(v);
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        ex[sw(x2, k, z2)] = v[k];
+    }
+    __syncthreads();
+    {
+      const int y3 = t & 7, z3 = t >> 3;
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        v[k] = ex[sw(k, y3, z3)];
+      dst8<Real>(v);
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        v[k] *= w[k];
+      dst8<Real>(v);
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        ex[sw(k, y3, z3)] = v[k];
+    }
+    __syncthreads();
+    {
+      const int x2 = t & 7, z2 = t >> 3;
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        v[k] = ex[sw(x2, k, z2)];
+      dst8<Real>(v);
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        ex[sw(x2, k, z2)] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      v[k] = ex[sw(x, y, k)];
+    dst8<Real>(v);
+    Real *ob = udst.at(slot);
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      ob[k * 64 + t] = uu[k] + omega * (v[k] - uu[k]);
+    // next iteration's first ex write happens after its own __syncthreads: no extra barrier
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host: tensor maps
+// ---------------------------------------------------------------------------
+namespace {
+
+typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                             const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                             CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeFn)p;
+  }
+  return fn;
+}
+
+struct MapCache {
+  std::map<std::tuple<const void *, long long, int, int>, CUtensorMap> m;
+};
+
+// kind 0: x faces, box {16 B, 8, 8}; kind 1: y faces, box {8, 1, 8}
+int get_map(CupCtx *c, const void *base, long long nblocks, int kind, CUtensorMap *out) {
+  if (!c->tma_cache)
+    c->tma_cache = new MapCache;
+  MapCache *mc = (MapCache *)c->tma_cache;
+  auto key = std::make_tuple(base, nblocks, kind, c->real_bytes);
+  auto it = mc->m.find(key);
+  if (it != mc->m.end()) {
+    *out = it->second;
+    return CUP_OK;
+  }
+  EncodeFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return CUP_ERR_CUDA;
+  }
+  const cuuint64_t rb = (cuuint64_t)c->real_bytes;
+  cuuint64_t dims[3] = {8, 8, (cuuint64_t)nblocks * 8};
+  cuuint64_t strides[2] = {8 * rb, 64 * rb};
+  cuuint32_t box[3] = {kind == 0 ? (cuuint32_t)(16 / rb) : 8u, kind == 0 ? 8u : 1u, 8u};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, c->real_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                   const_cast<void *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: %d (base %p, blocks %lld, kind %d)", (int)r, base, nblocks, kind);
+    return CUP_ERR_CUDA;
+  }
+  if (mc->m.size() > 4096)
+    mc->m.clear();
+  mc->m[key] = m;
+  *out = m;
+  return CUP_OK;
+}
+
+}  // namespace
+
+void free_tma_cache(CupCtx *c) {
+  delete (MapCache *)c->tma_cache;
+  c->tma_cache = nullptr;
+}
+
+template <typename Real>
+int smooth_tma_launch(CupCtx *c, int grid, LevelView lv, SlotVec<Real> src, SlotVec<Real> dst, SlotVec<Real> f, Real h,
+                      Real invh, Real om, const double *fmean) {
+  CUtensorMap mxl, myl, mxe, mye;
+  const long long nleaf = c->nblk, nx = c->nslot - c->nblk + 1;
+  // a part that holds no blocks of this vector still needs a valid (unused) descriptor
+  const void *lb = src.leaf ? (const void *)src.leaf : (const void *)src.extra;
+  const void *eb = src.extra ? (const void *)src.extra : (const void *)src.leaf;
+  CUP_TRY(get_map(c, lb, src.leaf ? nleaf : 1, 0, &mxl));
+  CUP_TRY(get_map(c, lb, src.leaf ? nleaf : 1, 1, &myl));
+  CUP_TRY(get_map(c, eb, src.extra ? nx : 1, 0, &mxe));
+  CUP_TRY(get_map(c, eb, src.extra ? nx : 1, 1, &mye));
+  k_smooth_tma<Real><<<grid, TPB, 0, c->stream>>>(lv, src, dst, f, (const Real *)c->d_W, h, invh, om, fmean, mxl, myl,
+                                                   mxe, mye);
+  return CUP_OK;
+}
+
+template int smooth_tma_launch<double>(CupCtx *, int, LevelView, SlotVec<double>, SlotVec<double>, SlotVec<double>,
+                                       double, double, double, const double *);
+template int smooth_tma_launch<float>(CupCtx *, int, LevelView, SlotVec<float>, SlotVec<float>, SlotVec<float>, float,
+                                      float, float, const double *);
+
+}  // namespace cup

@@ -1,0 +1,10 @@
+// smooth_tma.cuh -- launcher of the TMA-staged smoother (smooth_tma.cu)
+#pragma once
+#include "mg_device.cuh"
+struct CupCtx;
+namespace cup {
+template <typename Real>
+int smooth_tma_launch(CupCtx *c, int grid, LevelView lv, SlotVec<Real> src, SlotVec<Real> dst, SlotVec<Real> f, Real h,
+                      Real invh, Real om, const double *fmean);
+void free_tma_cache(CupCtx *c);
+}  // namespace cup
