@@ -156,67 +156,101 @@ def run_ours(args, rank, world, local_rank):
     import cup3d_b200
     from cup3d_b200 import mesh
 
+    from cup3d_b200 import capi
+    torch.cuda.set_device(local_rank)
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    torch.cuda.set_device(local_rank)
     L = args.level
-    ib, rb = mesh.uniform_blocks(L)
-    if world > 1:
-        raise SystemExit("bench.py: multi-GPU domain decomposition is not built yet in this round")
+    gib, grb = mesh.uniform_blocks(L)
+    # strong scaling: the SAME 512^3 grid, contiguous ranges of the Hilbert-ordered block list
+    # per rank (the reference's mesh_init split, main.c:3306-3322)
+    owner = capi.split_owner(len(gib), world)
+    mine = np.nonzero(owner == rank)[0]
+    ib, rb = gib[mine], grb[mine]
     ctx = cup3d_b200.Context(local_rank, 8)
+    if world > 1:
+        box = [capi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(rank, world, box[0])
     ctx.mesh_upload(ib, rb, (1, 1, 1), L + 1)
     ctx.set_params(mean_constraint=2)
     n = len(ib)
     N = n * 512
-    src = point_sources(ib, rb)
+    gcells = len(gib) * 512
+    gsrc = point_sources(gib, grb)
     b = torch.zeros(N, dtype=torch.float64, device="cuda")
-    b[src[0] * 512] = 1.0
-    b[src[1] * 512] = -1.0
+    src = []
+    for g, val in zip(gsrc, (1.0, -1.0)):
+        if owner[g] == rank:
+            src.append((int(g - mine[0]), val))
+            b[int(g - mine[0]) * 512] = val
     z = torch.empty_like(b)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
 
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for _ in range(args.warmup):
         ctx.mg_vcycle_dev(b, z)
-    torch.cuda.synchronize()
+    barrier()
     clk = ClockSampler(local_rank)
     clk.start()
     l0 = ctx.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
+    barrier()
     e0.record(stream)
     for _ in range(args.steps):
         ctx.mg_vcycle_dev(b, z)
     e1.record(stream)
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))  # device time, max over ranks
     launches = ctx.kernel_launches() - l0
     # dominant kernel: finest-level smoother, timed live with CUDA events on the same stream
+    # (single-rank kernel time; ghost faces of other ranks are whatever the last exchange left)
     sm_ms = ctx.time_smooth(L, 40)
     clocks = clk.stop()
     checksum = float(z.abs().sum().item())
 
     # end to end through the host-pointer C ABI: pinned host in/out, H2D + V-cycle + D2H per step
     hb = torch.zeros(N, dtype=torch.float64).pin_memory()
-    hb[src[0] * 512] = 1.0
-    hb[src[1] * 512] = -1.0
+    for i, val in src:
+        hb[i * 512] = val
     hz = torch.empty(N, dtype=torch.float64).pin_memory()
     e2e_steps = max(3, min(args.steps, 5))
     ctx.mg_vcycle(hb, hz)
+    barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         ctx.mg_vcycle(hb, hz)  # synchronous: returns after the D2H
-    t_e2e = (time.perf_counter() - t0) / e2e_steps
-    assert abs(float(hz.abs().sum().item()) - checksum) <= 1e-9 * checksum
+    barrier()
+    t_e2e = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    assert abs(float(hz.abs().sum().item()) - checksum) <= 1e-9 * max(checksum, 1e-300)
+    if rank != 0:
+        ctx.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
-    cells = N
+    cells = gcells
     value = cells * args.steps / (ms * 1e-3)
     peak, peak_src = measured_peak()
-    smooth_gbs = cells * B_PER_CELL_SMOOTH / (sm_ms * 1e-3) / 1e9
+    smooth_gbs = N * B_PER_CELL_SMOOTH / (sm_ms * 1e-3) / 1e9
     traffic = ncu_traffic()
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         try:
             r = cpu_reference_run(args.cpu_level, 1, 3)
             cpu = {"value": r["cell_updates_per_s"], "unit": "cell-updates/s", "cores": r["threads"],
@@ -232,22 +266,26 @@ def run_ours(args, rank, world, local_rank):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%d^3 uniform Poisson V-cycle (bpd 1, levelStart %d, levelMax %d), fp64, zero RHS + "
                                "point-source pair" % (8 << L, L, L + 1),
-                   "blocks": n, "mg_levels": L + 1, "l2_policy": "inputs larger than L2 (%.2f GB per vector)" %
-                   (N * 8 / 1e9), "parallelism": "1 rank per GPU, %d rank(s)" % world},
+                   "blocks": len(gib), "mg_levels": L + 1,
+                   "l2_policy": "inputs larger than L2 (%.2f GB per vector per rank)" % (N * 8 / 1e9),
+                   "parallelism": "%d rank(s), one per GPU, contiguous Hilbert ranges of the block list; "
+                                  "face halos + restrict/prolong by NCCL send/recv, scalars by NCCL allreduce" % world},
         "hbm_gbs_vcycle": cells * B_PER_CELL_VCYCLE * args.steps / (ms * 1e-3) / 1e9,
         "roofline": {"bound": "hbm", "kernel": "k_smooth<double,0> (finest level)", "achieved": smooth_gbs,
                      "peak": peak, "unit": "GB/s", "frac": smooth_gbs / peak,
                      "traffic": traffic["bytes_per_launch"] if traffic else None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": cells * B_PER_CELL_SMOOTH, "ms_per_launch": sm_ms,
+                     "algorithmic_bytes_per_launch": N * B_PER_CELL_SMOOTH, "ms_per_launch": sm_ms,
                      "vcycle_frac_at_171B_per_cell": cells * B_PER_CELL_VCYCLE * args.steps / (ms * 1e-3) / 1e9 / peak},
         "cpu_baseline": cpu,
-        "e2e": {"value": cells / t_e2e, "unit": "cell-updates/s", "h2d_bytes_per_step": N * 8,
-                "d2h_bytes_per_step": N * 8, "ms_per_step": t_e2e * 1e3},
+        "e2e": {"value": cells / t_e2e, "unit": "cell-updates/s", "h2d_bytes_per_step": gcells * 8,
+                "d2h_bytes_per_step": gcells * 8, "ms_per_step": t_e2e * 1e3},
         "gpu_launches": launches,
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
     ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def main():

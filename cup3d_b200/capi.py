@@ -32,6 +32,14 @@ class CupSolveInfo(C.Structure):
                 ("rhs_norm", C.c_double), ("vcycles", C.c_int)]
 
 
+class CupPlan(C.Structure):
+    _ip = C.POINTER(C.c_int)
+    _fields_ = [("nblk", C.c_longlong), ("nslot", C.c_longlong), ("nact", C.c_int), ("nsend", C.c_int),
+                ("nrecv", C.c_int), ("act", _ip), ("ijk", _ip), ("nbr", _ip), ("send_slot", _ip), ("send_plane", _ip),
+                ("send_cnt", _ip), ("recv_cnt", _ip), ("pslot", _ip), ("oct", _ip), ("res_send_cnt", _ip),
+                ("res_recv_cnt", _ip), ("nres_recv", C.c_int), ("res_recv_slot", _ip), ("res_recv_oct", _ip)]
+
+
 # every symbol include/cup3d_b200.h declares: name -> (restype, argtypes)
 _vp, _i, _ll, _dp = C.c_void_p, C.c_int, C.c_longlong, C.POINTER(C.c_double)
 SYMBOLS = {
@@ -63,6 +71,9 @@ SYMBOLS = {
     "cup_projection_udef_ready": (_i, [_vp, _i]),
     "cup_comm_init": (_i, [_vp, _i, _i, _vp, C.c_size_t]),
     "cup_nccl_unique_id": (_i, [_vp, C.c_size_t]),
+    "cup_plan_build": (_i, [C.POINTER(CupBlk), _ll, C.POINTER(_i), _i, _i, C.POINTER(_i), _i, _i,
+                       C.POINTER(CupPlan)]),
+    "cup_plan_free": (None, [C.POINTER(CupPlan)]),
     "cup_kernel_launches": (_ll, [_vp]),
     "cup_time_smooth": (_i, [_vp, _i, _i, C.POINTER(C.c_float)]),
     "cup_mg_smooth_dev": (_i, [_vp, _i, _i, _vp, _vp]),
@@ -109,6 +120,36 @@ def blocks_to_struct(ib, rb):
     return arr
 
 
+def plan_build(ib, rb, owner, nranks, rank, bpd, level_max, level):
+    """host-only exchange plan of `rank` for one multigrid level -> dict of numpy arrays"""
+    arr = blocks_to_struct(np.asarray(ib), np.asarray(rb))
+    own = np.ascontiguousarray(owner, np.int32)
+    b = (C.c_int * 3)(*bpd)
+    p = CupPlan()
+    check(lib().cup_plan_build(arr, len(ib), own.ctypes.data_as(C.POINTER(C.c_int)), nranks, rank, b, level_max,
+                               level, C.byref(p)))
+
+    def arr_of(ptr, n):
+        return np.ctypeslib.as_array(ptr, shape=(n,)).copy() if n > 0 else np.zeros(0, np.int32)
+
+    out = dict(nblk=p.nblk, nslot=p.nslot, nact=p.nact, nsend=p.nsend, nrecv=p.nrecv,
+               act=arr_of(p.act, p.nact), ijk=arr_of(p.ijk, 3 * p.nact).reshape(-1, 3), nbr=arr_of(p.nbr, 6 * p.nact).reshape(-1, 6),
+               send_slot=arr_of(p.send_slot, p.nsend), send_plane=arr_of(p.send_plane, p.nsend),
+               send_cnt=arr_of(p.send_cnt, nranks), recv_cnt=arr_of(p.recv_cnt, nranks),
+               pslot=arr_of(p.pslot, p.nact if level > 0 else 0), oct=arr_of(p.oct, p.nact if level > 0 else 0),
+               res_send_cnt=arr_of(p.res_send_cnt, nranks), res_recv_cnt=arr_of(p.res_recv_cnt, nranks),
+               res_recv_slot=arr_of(p.res_recv_slot, p.nres_recv), res_recv_oct=arr_of(p.res_recv_oct, p.nres_recv))
+    lib().cup_plan_free(C.byref(p))
+    return out
+
+
+def split_owner(n, nranks):
+    """owner rank of each of n Hilbert-ordered blocks: the reference's contiguous split (mesh_init, main.c:3306-3322)"""
+    base, rem = divmod(n, nranks)
+    cnt = [base + (1 if r < rem else 0) for r in range(nranks)]
+    return np.repeat(np.arange(nranks, dtype=np.int32), cnt)
+
+
 def _ptr(a):
     if a is None:
         return None
@@ -117,6 +158,12 @@ def _ptr(a):
     if hasattr(a, "data_ptr"):  # torch tensor (host pinned or device)
         return a.data_ptr()
     return a
+
+
+def nccl_unique_id():
+    buf = (C.c_char * 128)()
+    check(lib().cup_nccl_unique_id(buf, 128))
+    return bytes(buf)
 
 
 class Context:
@@ -152,6 +199,11 @@ class Context:
             else:
                 setattr(self.params, k, v)
         check(self.L.cup_set_params(self.h, C.byref(self.params)))
+
+    def comm_init(self, rank, nranks, id_bytes=None):
+        """one rank per GPU; id_bytes = the ncclUniqueId made by nccl_unique_id() on rank 0"""
+        buf = (C.c_char * 128).from_buffer_copy(id_bytes) if id_bytes is not None else None
+        check(self.L.cup_comm_init(self.h, rank, nranks, buf, 128 if id_bytes is not None else 0))
 
     def mesh_upload(self, ib, rb, bpd, level_max):
         arr = blocks_to_struct(np.asarray(ib), np.asarray(rb))

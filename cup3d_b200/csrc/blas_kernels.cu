@@ -8,6 +8,7 @@
 // host never waits for intermediate results.
 #include "blas_kernels.cuh"
 #include "cup_internal.h"
+#include "comm.cuh"
 
 namespace cup {
 
@@ -79,7 +80,7 @@ int wdot(CupCtx *c, const void *a, const void *b, int idx) {
                                                   c->nblk, out);
   c->launches++;
   CUP_CUDA(cudaGetLastError());
-  return CUP_OK;
+  return comm_allreduce(c, idx, 1);  // MPI_Allreduce of pois_dot, main.c:4860
 }
 
 int fetch_scalars(CupCtx *c, int first, int n) {

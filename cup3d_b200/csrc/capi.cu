@@ -4,6 +4,7 @@
 #include "blas_kernels.cuh"
 #include "cup_internal.h"
 #include "smooth_tma.cuh"
+#include "comm.cuh"
 
 namespace cup {
 
@@ -117,8 +118,10 @@ int cup_destroy(CupCtx *c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   free_krylov(c);
+  comm_free_level_buffers(c);
   free_mesh(c);
   free_tma_cache(c);
+  comm_free(c);
   for (int f = 0; f < CUP_F_N; f++)
     cudaFree(c->state[f]);
   cudaFree(c->u1_leaf);
@@ -161,9 +164,15 @@ int cup_mesh_upload(CupCtx *c, const CupBlk *blk, long long n, const int bpd[3],
   CUP_CUDA(cudaSetDevice(c->device));
   CUP_CUDA(cudaStreamSynchronize(c->stream));
   free_krylov(c);
-  CUP_TRY(build_mesh(c, blk, n, bpd, level_max));
+  comm_free_level_buffers(c);
+  // tree_sync (main.c:2928): all ranks learn all blocks; owner = contributing rank
+  std::vector<CupBlk> gblk;
+  std::vector<int> owner;
+  CUP_TRY(comm_gather_blocks(c, blk, n, gblk, owner));
+  CUP_TRY(build_mesh(c, gblk.data(), (long long)gblk.size(), owner.data(), bpd, level_max));
   CUP_TRY(alloc_state(c));
   CUP_TRY(mg_setup(c));
+  CUP_TRY(comm_alloc_level_buffers(c));
   return CUP_OK;
 }
 
@@ -267,6 +276,64 @@ int cup_comm_init(CupCtx *c, int rank, int nranks, const void *id, size_t id_byt
   return comm_init(c, rank, nranks, id, id_bytes);
 }
 int cup_nccl_unique_id(void *out, size_t bytes) { return comm_unique_id(out, bytes); }
+
+static int *dup_ints(const std::vector<int> &v) {
+  int *p = (int *)malloc((v.size() + 1) * sizeof(int));
+  if (!v.empty())
+    memcpy(p, v.data(), v.size() * sizeof(int));
+  return p;
+}
+
+int cup_plan_build(const CupBlk *gblk, long long G, const int *owner, int nranks, int rank, const int bpd[3],
+                   int level_max, int level, CupPlan *out) {
+  HostMesh m;
+  CUP_TRY(build_tables(&m, gblk, G, owner, nranks, rank, bpd, level_max));
+  if (level < 0 || level > m.top || !out) {
+    set_error("cup_plan_build: level %d of %d", level, m.top + 1);
+    return CUP_ERR_ARG;
+  }
+  const Level &v = m.lv[level];
+  memset(out, 0, sizeof *out);
+  out->nblk = m.nblk;
+  out->nslot = m.nslot;
+  out->nact = (int)v.act.size();
+  out->nsend = (int)v.face_sslot.size();
+  out->nrecv = v.nface_recv;
+  out->act = dup_ints(v.act);
+  out->ijk = dup_ints(v.ijk);
+  out->nbr = dup_ints(v.nbr);
+  out->send_slot = dup_ints(v.face_sslot);
+  out->send_plane = dup_ints(v.face_splane);
+  out->send_cnt = dup_ints(v.face_scnt);
+  out->recv_cnt = dup_ints(v.face_rcnt);
+  out->pslot = dup_ints(v.pslot);
+  out->oct = dup_ints(v.oct);
+  out->res_send_cnt = dup_ints(v.res_scnt);
+  out->res_recv_cnt = dup_ints(v.res_rcnt);
+  out->nres_recv = (int)v.res_rslot.size();
+  out->res_recv_slot = dup_ints(v.res_rslot);
+  out->res_recv_oct = dup_ints(v.res_roct);
+  return CUP_OK;
+}
+
+void cup_plan_free(CupPlan *p) {
+  if (!p)
+    return;
+  free(p->act);
+  free(p->ijk);
+  free(p->nbr);
+  free(p->send_slot);
+  free(p->send_plane);
+  free(p->send_cnt);
+  free(p->recv_cnt);
+  free(p->pslot);
+  free(p->oct);
+  free(p->res_send_cnt);
+  free(p->res_recv_cnt);
+  free(p->res_recv_slot);
+  free(p->res_recv_oct);
+  memset(p, 0, sizeof *p);
+}
 
 long long cup_kernel_launches(const CupCtx *c) { return c->launches; }
 int cup_time_smooth(CupCtx *c, int level, int reps, float *ms) { return time_smooth(c, level, reps, ms); }

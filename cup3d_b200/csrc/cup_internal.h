@@ -30,7 +30,9 @@ void set_error(const char *fmt, ...);
       return rc_;              \
   } while (0)
 
-enum { NBR_WALL = -1, NBR_COARSE = -2 };
+// neighbour codes: >= 0 local slot; NBR_WALL; NBR_COARSE (AMR); <= NBR_REMOTE0: face
+// number (NBR_REMOTE0 - code) of the level's received-face buffer (owned by another rank)
+enum { NBR_WALL = -1, NBR_COARSE = -2, NBR_REMOTE0 = -3 };
 
 // One multigrid level == one AMR level (reference: struct Lvl, main.c:4443).
 // "active" blocks are those whose level == L in that level's context: leaves
@@ -41,12 +43,38 @@ struct Level {
   int L = 0;
   double h = 0;
   std::vector<int> act;    // [nact] slot of each active block
+  std::vector<int> ijk;    // [nact][3] block index at this level (host only)
   std::vector<int> nbr;    // [nact][6] slot of -x,+x,-y,+y,-z,+z neighbour, NBR_WALL / NBR_COARSE
   std::vector<int> pslot;  // [nact] slot of the parent (level L-1), L >= 1
   std::vector<int> oct;    // [nact] octant inside the parent, (ix&1)+2(iy&1)+4(iz&1)
   std::vector<int> par;    // [npar] indices into act[] of blocks that are synthesised parents
   int *d_act = nullptr, *d_nbr = nullptr, *d_pslot = nullptr, *d_oct = nullptr, *d_par = nullptr;
   bool uniform = true;     // no NBR_COARSE entries
+  long long gnact = 0;     // active blocks of this level over all ranks
+  // ---- multi-rank plans (empty on one rank) ----
+  std::vector<int> inner, bnd;             // act[] indices without / with a remote neighbour
+  int *d_inner = nullptr, *d_bnd = nullptr;
+  int nface_recv = 0;                      // faces received per exchange (64 Reals each)
+  std::vector<int> face_rcnt, face_scnt;   // [nranks] faces received from / sent to each peer
+  std::vector<int> face_sslot, face_splane;  // send list: local slot + plane (0..5), peer-major
+  int *d_face_sslot = nullptr, *d_face_splane = nullptr;
+  // restriction to remote parents: pslot[k] <= NBR_REMOTE0 -> entry of the send buffer
+  std::vector<int> res_scnt, res_rcnt;     // [nranks] children sent to / received from each peer
+  std::vector<int> res_rslot, res_roct;    // received children: local parent slot, octant
+  int *d_res_rslot = nullptr, *d_res_roct = nullptr;
+  // device scratch (comm.cu): faces out/in [n][64], restriction out/in [n][128]
+  void *d_fsend = nullptr, *d_frecv = nullptr, *d_rsend = nullptr, *d_rrecv = nullptr;
+};
+
+// pure-host result of the topology build (mesh.cpp); also what the CPU tests inspect
+struct HostMesh {
+  int nranks = 1, rank = 0, top = -1, level_max = 1;
+  int bpd[3] = {1, 1, 1};
+  long long nblk = 0, nslot = 0, gblocks = 0, gnslot = 0, pin_local = -1;
+  double gvol = 0;
+  bool leaf_uniform = true;
+  std::vector<CupBlk> blk;
+  std::vector<Level> lv;
 };
 
 struct Krylov;
@@ -59,7 +87,12 @@ struct CupCtx {
   int num_sms = 148;
   cudaStream_t stream = nullptr;
   CupParams prm{};
-  long long nblk = 0, nslot = 0;
+  long long nblk = 0, nslot = 0;   // LOCAL leaves / local slots
+  long long gblocks = 0;           // leaves over all ranks
+  double gvol = 0;                 // volume over all ranks (pois_solve's vol)
+  long long pin_local = -1;        // local index of block (0,0,0) or -1 (pois_pin)
+  int rank = 0, nranks = 1;
+  void *comm = nullptr;            // cup::Comm (comm.cu)
   int top = -1;
   int bpd[3] = {1, 1, 1};
   int level_max = 1;
@@ -88,7 +121,9 @@ struct CupCtx {
 namespace cup {
 
 // mesh.cpp
-int build_mesh(CupCtx *c, const CupBlk *blk, long long n, const int bpd[3], int level_max);
+int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner, int nranks, int rank,
+                 const int bpd[3], int level_max);
+int build_mesh(CupCtx *c, const CupBlk *gblk, long long G, const int *owner, const int bpd[3], int level_max);
 void free_mesh(CupCtx *c);
 
 // mg_kernels.cu

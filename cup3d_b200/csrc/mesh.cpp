@@ -7,15 +7,24 @@
 //
 //   per multigrid level L (== AMR level L, reference mg_build main.c:4522):
 //     act[k]      slot of the k-th active block            (v->act,  :4538)
-//     nbr[k][6]   slot of each face neighbour / wall code  (znei+node_get)
+//     nbr[k][6]   face neighbour: slot / wall / remote face (znei+node_get)
 //     pslot[k]    slot of the parent at level L-1          (v->pslot,:4628)
 //     oct[k]      octant inside the parent                 (v->oct,  :4559)
-//     par[]       which level-(L) blocks are synthesised parents (w->par, :4616)
+//     par[]       which level-L blocks are synthesised parents (w->par, :4616)
 //
-// Slots follow the reference: leaves keep their block index, synthesised
-// parents are appended (mg.nslot++, main.c:4592).  Block ORDER is whatever the
-// caller's sta.blk[] has (the reference sorts by a Hilbert key; nothing here
-// depends on it, the tables are built from (level, ix, iy, iz) alone).
+// Multi-rank (one rank per GPU): every rank holds the GLOBAL leaf list (the
+// reference all-gathers it in tree_sync, main.c:2928) with an owner per block,
+// builds the same global hierarchy deterministically, and then localises it:
+// owned blocks get local slots, neighbours owned by another rank become
+// entries of a face-exchange plan (the analogue of halo_build, main.c:3030,
+// but exchanging 8x8 FACES instead of whole blocks), remote parents become
+// entries of restrict/prolong plans (v->x / v->xr, main.c:4621-4664; parent
+// owner = smallest rank among the 8 children, :4561-4569).  Both sides of
+// every exchange order their entries by (peer, position of the SENDER's block
+// in the level's global order, plane), so no plan negotiation is needed.
+//
+// Block ORDER is whatever the caller's sta.blk[] has (the reference sorts by
+// a Hilbert key; nothing here depends on it).
 #include <algorithm>
 #include <cstdint>
 #include <unordered_map>
@@ -27,60 +36,57 @@ namespace cup {
 namespace {
 
 struct Ent {
-  int level, ix, iy, iz, slot;
+  int level, ix, iy, iz, gslot;
 };
 
 inline uint64_t key_of(int level, int ix, int iy, int iz) {
   return ((uint64_t)level << 57) | ((uint64_t)iz << 38) | ((uint64_t)iy << 19) | (uint64_t)ix;
 }
 
-template <typename T>
-int upload(T **d, const std::vector<T> &h) {
-  *d = nullptr;
-  if (h.empty())
-    return CUP_OK;
-  CUP_CUDA(cudaMalloc((void **)d, h.size() * sizeof(T)));
-  CUP_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
-  return CUP_OK;
+struct Xent {  // one exchange entry before sorting
+  int peer, pos, plane, ref;
+  bool operator<(const Xent &o) const {
+    if (peer != o.peer) return peer < o.peer;
+    if (pos != o.pos) return pos < o.pos;
+    return plane < o.plane;
+  }
+};
+
+void count_by_peer(const std::vector<Xent> &v, int nranks, std::vector<int> &cnt) {
+  cnt.assign(nranks, 0);
+  for (const Xent &e : v)
+    cnt[e.peer]++;
 }
 
 }  // namespace
 
-void free_mesh(CupCtx *c) {
-  for (auto &v : c->lv) {
-    cudaFree(v.d_act);
-    cudaFree(v.d_nbr);
-    cudaFree(v.d_pslot);
-    cudaFree(v.d_oct);
-    cudaFree(v.d_par);
-  }
-  c->lv.clear();
-  c->blk.clear();
-  c->nblk = c->nslot = 0;
-  c->top = -1;
-}
-
-int build_mesh(CupCtx *c, const CupBlk *blk, long long n, const int bpd[3], int level_max) {
-  if (n <= 0 || n > (1LL << 30) || level_max < 1 || level_max > 20 || bpd[0] < 1 || bpd[1] < 1 || bpd[2] < 1) {
-    set_error("cup_mesh_upload: bad arguments (n=%lld level_max=%d)", n, level_max);
+int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner_in, int nranks, int rank,
+                 const int bpd[3], int level_max) {
+  if (G <= 0 || G > (1LL << 30) || level_max < 1 || level_max > 20 || bpd[0] < 1 || bpd[1] < 1 || bpd[2] < 1 ||
+      nranks < 1 || rank < 0 || rank >= nranks) {
+    set_error("mesh: bad arguments (blocks=%lld level_max=%d ranks=%d)", G, level_max, nranks);
     return CUP_ERR_ARG;
   }
-  free_mesh(c);
-  c->blk.assign(blk, blk + n);
-  c->nblk = n;
-  c->level_max = level_max;
+  m->lv.clear();
+  m->nranks = nranks;
+  m->rank = rank;
+  m->level_max = level_max;
   for (int d = 0; d < 3; d++)
-    c->bpd[d] = bpd[d];
+    m->bpd[d] = bpd[d];
   // mg.top = sim.level_max - 1 (main.c:4526): levels above the finest leaf are
   // simply empty, exactly as in the reference.
-  c->top = level_max - 1;
-  c->lv.resize(c->top + 1);
+  m->top = level_max - 1;
+  m->lv.resize(m->top + 1);
+  m->gblocks = G;
 
+  std::vector<int> owner((size_t)G);  // per GLOBAL slot, grows with parents
   int lmin = 1 << 30, lmax = -1;
-  std::vector<Ent> cur((size_t)n);
-  for (long long i = 0; i < n; i++) {
-    const CupBlk &b = blk[i];
-    if (b.level < 0 || b.level > c->top) {
+  std::vector<Ent> cur((size_t)G);
+  m->gvol = 0;
+  m->pin_local = -1;
+  for (long long i = 0; i < G; i++) {
+    const CupBlk &b = gblk[i];
+    if (b.level < 0 || b.level > m->top) {
       set_error("block %lld: level %d outside [0,%d)", i, b.level, level_max);
       return CUP_ERR_MESH;
     }
@@ -89,38 +95,58 @@ int build_mesh(CupCtx *c, const CupBlk *blk, long long n, const int bpd[3], int 
       set_error("block %lld: index (%d,%d,%d) outside level %d", i, b.ix, b.iy, b.iz, b.level);
       return CUP_ERR_MESH;
     }
+    owner[i] = owner_in ? owner_in[i] : 0;
+    if (owner[i] < 0 || owner[i] >= nranks) {
+      set_error("block %lld: owner %d outside [0,%d)", i, owner[i], nranks);
+      return CUP_ERR_ARG;
+    }
     cur[i] = {b.level, b.ix, b.iy, b.iz, (int)i};
     lmin = std::min(lmin, b.level);
     lmax = std::max(lmax, b.level);
+    m->gvol += 512.0 * (b.h * b.h * b.h);
   }
-  c->leaf_uniform = (lmin == lmax);
+  m->leaf_uniform = (lmin == lmax);
   // h of level L: the reference stores h per block = h0 / 2^L (main.c:1400)
-  double h0 = blk[0].h * (double)(1 << blk[0].level);
-  long long nslot = n;
+  const double h0 = gblk[0].h * (double)(1 << gblk[0].level);
+  long long gnslot = G;
 
-  for (int L = c->top; L >= 0; L--) {
-    Level &v = c->lv[L];
-    v.L = L;
-    v.h = h0 / (double)(1 << L);
+  // local slots: owned leaves in global order, then owned parents in creation order
+  std::vector<int> g2l((size_t)G, -1);
+  m->blk.clear();
+  for (long long i = 0; i < G; i++)
+    if (owner[i] == rank) {
+      g2l[i] = (int)m->blk.size();
+      if (gblk[i].ix == 0 && gblk[i].iy == 0 && gblk[i].iz == 0)
+        m->pin_local = (long long)m->blk.size();  // pois_pin, main.c:4888
+      m->blk.push_back(gblk[i]);
+    }
+  m->nblk = (long long)m->blk.size();
+  long long lnslot = m->nblk;
+
+  // ---- global hierarchy, finest to coarsest ------------------------------
+  struct GLevel {
+    std::vector<Ent> act;          // global active list (global order)
+    std::vector<int> nbr;          // [n][6] global slot / NBR_WALL / NBR_COARSE
+    std::vector<int> pg;           // parent global slot
+  };
+  std::vector<GLevel> gl(m->top + 1);
+  for (int L = m->top; L >= 0; L--) {
+    GLevel &g = gl[L];
     std::unordered_map<uint64_t, int> map;
     map.reserve(cur.size() * 2);
-    for (const Ent &e : cur) {
-      if (!map.emplace(key_of(e.level, e.ix, e.iy, e.iz), e.slot).second) {
+    for (const Ent &e : cur)
+      if (!map.emplace(key_of(e.level, e.ix, e.iy, e.iz), e.gslot).second) {
         set_error("duplicate block level %d (%d,%d,%d)", e.level, e.ix, e.iy, e.iz);
         return CUP_ERR_MESH;
       }
-    }
-    std::vector<const Ent *> active;
     for (const Ent &e : cur)
       if (e.level == L)
-        active.push_back(&e);
-    size_t na = active.size();
-    v.act.resize(na);
-    v.nbr.assign(na * 6, NBR_WALL);
+        g.act.push_back(e);
+    const size_t na = g.act.size();
+    g.nbr.assign(na * 6, NBR_WALL);
     const int dim[3] = {bpd[0] << L, bpd[1] << L, bpd[2] << L};
     for (size_t k = 0; k < na; k++) {
-      const Ent &e = *active[k];
-      v.act[k] = e.slot;
+      const Ent &e = g.act[k];
       const int idx[3] = {e.ix, e.iy, e.iz};
       for (int f = 0; f < 6; f++) {
         int d = f / 2, s = (f & 1) ? 1 : -1;
@@ -130,47 +156,47 @@ int build_mesh(CupCtx *c, const CupBlk *blk, long long n, const int bpd[3], int 
           continue;  // domain wall (nei_outside, main.c:2837)
         auto it = map.find(key_of(L, q[0], q[1], q[2]));
         if (it != map.end()) {
-          v.nbr[k * 6 + f] = it->second;
+          g.nbr[k * 6 + f] = it->second;
         } else {
           // must be covered by a coarser leaf (2:1 balance): check its presence
           if (L == 0 || map.find(key_of(L - 1, q[0] / 2, q[1] / 2, q[2] / 2)) == map.end()) {
             set_error("level %d block (%d,%d,%d): face %d neighbour missing", L, e.ix, e.iy, e.iz, f);
             return CUP_ERR_MESH;
           }
-          v.nbr[k * 6 + f] = NBR_COARSE;
-          v.uniform = false;
+          g.nbr[k * 6 + f] = NBR_COARSE;
         }
       }
     }
     if (L == 0)
       break;
-    // parents: one new slot per distinct parent, first-appearance order
+    // parents: one new global slot per distinct parent, first-appearance order;
+    // owner = smallest rank among the children (mg_build, main.c:4561-4569)
     std::unordered_map<uint64_t, int> pmap;
     std::vector<Ent> next;
     next.reserve(cur.size() - na + na / 8 + 1);
     for (const Ent &e : cur)
       if (e.level < L)
         next.push_back(e);
-    size_t first_parent = next.size();
-    v.pslot.resize(na);
-    v.oct.resize(na);
+    g.pg.resize(na);
     std::vector<int> nchild;
+    const long long first = gnslot;
     for (size_t k = 0; k < na; k++) {
-      const Ent &e = *active[k];
-      uint64_t pk = key_of(L - 1, e.ix / 2, e.iy / 2, e.iz / 2);
+      const Ent &e = g.act[k];
+      const uint64_t pk = key_of(L - 1, e.ix / 2, e.iy / 2, e.iz / 2);
       auto it = pmap.find(pk);
       int ps;
       if (it == pmap.end()) {
-        ps = (int)nslot++;
+        ps = (int)gnslot++;
         pmap.emplace(pk, ps);
         next.push_back({L - 1, e.ix / 2, e.iy / 2, e.iz / 2, ps});
         nchild.push_back(0);
+        owner.push_back(owner[e.gslot]);
       } else {
         ps = it->second;
+        owner[ps] = std::min(owner[ps], owner[e.gslot]);
       }
-      nchild[(size_t)(ps - (nslot - (long long)nchild.size()))]++;
-      v.pslot[k] = ps;
-      v.oct[k] = (e.ix & 1) + 2 * (e.iy & 1) + 4 * (e.iz & 1);
+      nchild[(size_t)(ps - first)]++;
+      g.pg[k] = ps;
     }
     for (size_t p = 0; p < nchild.size(); p++)
       if (nchild[p] != 8) {
@@ -178,25 +204,186 @@ int build_mesh(CupCtx *c, const CupBlk *blk, long long n, const int bpd[3], int 
         set_error("level %d: a parent has %d of 8 children (siblings missing)", L, nchild[p]);
         return CUP_ERR_MESH;
       }
-    // which active blocks of level L-1 are those parents is resolved below,
-    // once level L-1's active list exists
     cur.swap(next);
-    (void)first_parent;
   }
-  // par[]: indices (into act[]) of synthesised parents, i.e. slot >= nblk
-  for (int L = 0; L <= c->top; L++) {
-    Level &v = c->lv[L];
+  // local slots of owned parents, in global-slot order
+  g2l.resize((size_t)gnslot, -1);
+  for (long long s = G; s < gnslot; s++)
+    if (owner[s] == rank)
+      g2l[s] = (int)lnslot++;
+  m->nslot = lnslot;
+  m->gnslot = gnslot;
+
+  // ---- localise ----------------------------------------------------------
+  for (int L = 0; L <= m->top; L++) {
+    Level &v = m->lv[L];
+    const GLevel &g = gl[L];
+    v = Level();
+    v.L = L;
+    v.h = h0 / (double)(1 << L);
+    v.gnact = (long long)g.act.size();
+    std::vector<Xent> rx, sx;  // face recv / send
+    for (size_t k = 0; k < g.act.size(); k++) {
+      const int gs = g.act[k].gslot;
+      if (owner[gs] != rank)
+        continue;
+      const int lk = (int)v.act.size();
+      v.act.push_back(g2l[gs]);
+      v.ijk.push_back(g.act[k].ix);
+      v.ijk.push_back(g.act[k].iy);
+      v.ijk.push_back(g.act[k].iz);
+      for (int f = 0; f < 6; f++) {
+        const int gn = g.nbr[k * 6 + f];
+        int code;
+        if (gn == NBR_WALL || gn == NBR_COARSE) {
+          code = gn;
+          if (gn == NBR_COARSE)
+            v.uniform = false;
+        } else if (owner[gn] == rank) {
+          code = g2l[gn];
+        } else {
+          code = 0;  // patched after sorting
+          rx.push_back({owner[gn], -1, f ^ 1, lk * 6 + f});
+          rx.back().pos = gn;  // provisional: global slot; replaced by level position below
+          sx.push_back({owner[gn], (int)k, f, g2l[gs]});
+        }
+        v.nbr.push_back(code);
+      }
+    }
+    // position of a global slot inside this level's global order
+    if (!rx.empty()) {
+      std::unordered_map<int, int> pos;
+      pos.reserve(g.act.size() * 2);
+      for (size_t k = 0; k < g.act.size(); k++)
+        pos[g.act[k].gslot] = (int)k;
+      for (Xent &e : rx)
+        e.pos = pos[e.pos];
+    }
+    std::sort(rx.begin(), rx.end());
+    std::sort(sx.begin(), sx.end());
+    count_by_peer(rx, nranks, v.face_rcnt);
+    count_by_peer(sx, nranks, v.face_scnt);
+    for (size_t i = 0; i < rx.size(); i++)
+      v.nbr[(size_t)rx[i].ref] = NBR_REMOTE0 - (int)i;
+    for (const Xent &e : sx) {
+      v.face_sslot.push_back(e.ref);
+      v.face_splane.push_back(e.plane);
+    }
+    v.nface_recv = (int)rx.size();
+    // restrict / prolong plans (L >= 1)
+    if (L >= 1) {
+      std::vector<Xent> rs, rr;
+      int lk = 0;
+      for (size_t k = 0; k < g.act.size(); k++) {
+        const int gs = g.act[k].gslot, gp = g.pg[k];
+        const Ent &e = g.act[k];
+        const int oct = (e.ix & 1) + 2 * (e.iy & 1) + 4 * (e.iz & 1);
+        if (owner[gs] == rank) {
+          v.oct.push_back(oct);
+          if (owner[gp] == rank) {
+            v.pslot.push_back(g2l[gp]);
+          } else {
+            v.pslot.push_back(0);
+            rs.push_back({owner[gp], (int)k, 0, lk});
+          }
+          lk++;
+        } else if (owner[gp] == rank) {
+          rr.push_back({owner[gs], (int)k, oct, g2l[gp]});
+        }
+      }
+      std::sort(rs.begin(), rs.end());
+      std::sort(rr.begin(), rr.end());
+      count_by_peer(rs, nranks, v.res_scnt);
+      count_by_peer(rr, nranks, v.res_rcnt);
+      for (size_t i = 0; i < rs.size(); i++)
+        v.pslot[(size_t)rs[i].ref] = NBR_REMOTE0 - (int)i;
+      for (const Xent &e : rr) {
+        v.res_rslot.push_back(e.ref);
+        v.res_roct.push_back(e.plane);
+      }
+    } else {
+      v.res_scnt.assign(nranks, 0);
+      v.res_rcnt.assign(nranks, 0);
+    }
+    // par[]: indices (into act[]) of synthesised parents, i.e. local slot >= nblk
     for (size_t k = 0; k < v.act.size(); k++)
-      if (v.act[k] >= n)
+      if (v.act[k] >= m->nblk)
         v.par.push_back((int)k);
+    // interior / boundary split for comm-compute overlap
+    for (size_t k = 0; k < v.act.size(); k++) {
+      bool rem = false;
+      for (int f = 0; f < 6; f++)
+        rem |= v.nbr[k * 6 + f] <= NBR_REMOTE0;
+      (rem ? v.bnd : v.inner).push_back((int)k);
+    }
   }
-  c->nslot = nslot;
+  return CUP_OK;
+}
+
+namespace {
+template <typename T>
+int upload(T **d, const std::vector<T> &h) {
+  *d = nullptr;
+  if (h.empty())
+    return CUP_OK;
+  CUP_CUDA(cudaMalloc((void **)d, h.size() * sizeof(T)));
+  CUP_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return CUP_OK;
+}
+}  // namespace
+
+void free_mesh(CupCtx *c) {
+  for (auto &v : c->lv) {
+    cudaFree(v.d_act);
+    cudaFree(v.d_nbr);
+    cudaFree(v.d_pslot);
+    cudaFree(v.d_oct);
+    cudaFree(v.d_par);
+    cudaFree(v.d_inner);
+    cudaFree(v.d_bnd);
+    cudaFree(v.d_face_sslot);
+    cudaFree(v.d_face_splane);
+    cudaFree(v.d_res_rslot);
+    cudaFree(v.d_res_roct);
+  }
+  c->lv.clear();
+  c->blk.clear();
+  c->nblk = c->nslot = 0;
+  c->top = -1;
+}
+
+int build_mesh(CupCtx *c, const CupBlk *gblk, long long G, const int *owner, const int bpd[3], int level_max) {
+  free_mesh(c);
+  HostMesh m;
+  CUP_TRY(build_tables(&m, gblk, G, owner, c->nranks, c->rank, bpd, level_max));
+  if (m.nblk == 0) {
+    set_error("rank %d owns no blocks", c->rank);
+    return CUP_ERR_ARG;
+  }
+  c->blk.swap(m.blk);
+  c->lv.swap(m.lv);
+  c->nblk = m.nblk;
+  c->nslot = m.nslot;
+  c->gblocks = m.gblocks;
+  c->gvol = m.gvol;
+  c->pin_local = m.pin_local;
+  c->top = m.top;
+  c->level_max = level_max;
+  c->leaf_uniform = m.leaf_uniform;
+  for (int d = 0; d < 3; d++)
+    c->bpd[d] = bpd[d];
   for (auto &v : c->lv) {
     CUP_TRY(upload(&v.d_act, v.act));
     CUP_TRY(upload(&v.d_nbr, v.nbr));
     CUP_TRY(upload(&v.d_pslot, v.pslot));
     CUP_TRY(upload(&v.d_oct, v.oct));
     CUP_TRY(upload(&v.d_par, v.par));
+    CUP_TRY(upload(&v.d_inner, v.inner));
+    CUP_TRY(upload(&v.d_bnd, v.bnd));
+    CUP_TRY(upload(&v.d_face_sslot, v.face_sslot));
+    CUP_TRY(upload(&v.d_face_splane, v.face_splane));
+    CUP_TRY(upload(&v.d_res_rslot, v.res_rslot));
+    CUP_TRY(upload(&v.d_res_roct, v.res_roct));
   }
   return CUP_OK;
 }

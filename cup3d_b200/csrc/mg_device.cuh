@@ -14,6 +14,8 @@
 namespace cup {
 
 enum { TPB = 64 };  // threads per 8^3 block
+// neighbour codes (cup_internal.h): >= 0 local slot, -1 wall, <= kRemote0 received face number
+enum { kWall = -1, kCoarse = -2, kRemote0 = -3 };
 
 // slot -> pointer.  Slots below nleaf are leaves and live in the caller's flat
 // vector (block-index order); the rest are synthesised multigrid parents and
@@ -34,6 +36,7 @@ struct LevelView {
   const int *act;  // [nact]
   const int *nbr;  // [nact][6]
   int nact;
+  const void *rface;  // faces received from other ranks: [nface][64] Reals, plane order (a, c)
 };
 
 // 8-point DST-I matrix S[j][k] = sqrt(2/9) sin(pi (j+1)(k+1)/9), k < 4 only:
@@ -83,11 +86,15 @@ __device__ __forceinline__ int sw(int x, int y, int z) { return (z << 6) + (((y 
 //   x faces: a = y, c = z;   y faces: a = x, c = z;   z faces: a = x, c = y.
 template <typename Real>
 __device__ __forceinline__ void load_halo(const SlotVec<Real> &u, const Real *own, const int *nbr6, int t,
-                                          Real (*halo)[64]) {
+                                          Real (*halo)[64], const Real *rface = nullptr) {
   const int a = t & 7, c = t >> 3;
 #pragma unroll
   for (int f = 0; f < 6; f++) {
     const int nb = nbr6[f];
+    if (nb <= kRemote0) {  // packed by the owner in exactly this (a, c) order
+      halo[f][t] = rface[(size_t)(kRemote0 - nb) * 64 + t];
+      continue;
+    }
     const Real *src = nb >= 0 ? u.at(nb) : own;
     // plane coordinate inside the source block
     const int p = (nb >= 0) ? ((f & 1) ? 0 : 7) : ((f & 1) ? 7 : 0);

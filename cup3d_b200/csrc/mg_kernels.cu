@@ -13,6 +13,7 @@
 #include "cup_internal.h"
 #include "mg_device.cuh"
 #include "smooth_tma.cuh"
+#include "comm.cuh"
 
 namespace cup {
 
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_smooth(LevelView lv, SlotVec<Real
 #pragma unroll
       for (int k = 0; k < 8; k++)
         uu[k] = ub[k * 64 + t];
-      load_halo<Real>(usrc, ub, lv.nbr + (size_t)b * 6, t, halo);
+      load_halo<Real>(usrc, ub, lv.nbr + (size_t)b * 6, t, halo, (const Real *)lv.rface);
       __syncthreads();
 #pragma unroll
       for (int k = 0; k < 8; k++)
@@ -144,7 +145,8 @@ __global__ void __launch_bounds__(TPB, MINB) k_smooth(LevelView lv, SlotVec<Real
 // receives sum_8 r (scale 1) into f and mean_8 u into u (mg_sum/mg_put).
 template <typename Real>
 __global__ void __launch_bounds__(TPB) k_down(LevelView lv, const int *__restrict__ pslot,
-                                              const int *__restrict__ oct, SlotVec<Real> u, SlotVec<Real> f, Real h) {
+                                              const int *__restrict__ oct, SlotVec<Real> u, SlotVec<Real> f, Real h,
+                                              Real *__restrict__ rsend) {
   __shared__ Real tu[512];
   __shared__ Real tr[512];
   __shared__ Real halo[6][64];
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(TPB) k_down(LevelView lv, const int *__restric
       ff[k] = fb[k * 64 + t];
       tu[k * 64 + t] = uu[k];
     }
-    load_halo<Real>(u, ub, lv.nbr + (size_t)b * 6, t, halo);
+    load_halo<Real>(u, ub, lv.nbr + (size_t)b * 6, t, halo, (const Real *)lv.rface);
     __syncthreads();
     lap_line<Real>(tu, halo, uu, x, y, t, h, tt);
 #pragma unroll
@@ -177,9 +179,15 @@ __global__ void __launch_bounds__(TPB) k_down(LevelView lv, const int *__restric
       const Real su = ((((((tu[base] + tu[base + 1]) + tu[base + 8]) + tu[base + 9]) + tu[base + 64]) +
                          tu[base + 65]) + tu[base + 72]) + tu[base + 73];
       const int o = oct[b], ps = pslot[b];
-      const int pidx = ((4 * (o >> 2) + cz) << 6) + ((4 * ((o >> 1) & 1) + cy) << 3) + 4 * (o & 1) + cx;
-      f.at(ps)[pidx] = sr;
-      u.at(ps)[pidx] = (Real)0.125 * su;
+      if (ps >= 0) {
+        const int pidx = ((4 * (o >> 2) + cz) << 6) + ((4 * ((o >> 1) & 1) + cy) << 3) + 4 * (o & 1) + cx;
+        f.at(ps)[pidx] = sr;
+        u.at(ps)[pidx] = (Real)0.125 * su;
+      } else {  // parent lives on another rank: 64 r + 64 u (MG_M layout, main.c:4750)
+        Real *q = rsend + (size_t)(kRemote0 - ps) * 128;
+        q[t] = sr;
+        q[64 + t] = (Real)0.125 * su;
+      }
     }
     __syncthreads();
   }
@@ -208,7 +216,7 @@ __global__ void __launch_bounds__(TPB) k_apply(LevelView lv, const int *__restri
       uu[k] = ub[k * 64 + t];
       tu[k * 64 + t] = uu[k];
     }
-    load_halo<Real>(u, ub, lv.nbr + (size_t)b * 6, t, halo);
+    load_halo<Real>(u, ub, lv.nbr + (size_t)b * 6, t, halo, (const Real *)lv.rface);
     __syncthreads();
     lap_line<Real>(tu, halo, uu, x, y, t, h, tt);
     Real *ob = out.at(slot);
@@ -233,18 +241,25 @@ __global__ void __launch_bounds__(TPB) k_apply(LevelView lv, const int *__restri
 // parent cell, piecewise-constant injection.
 template <typename Real>
 __global__ void __launch_bounds__(TPB) k_up(LevelView lv, const int *__restrict__ pslot, const int *__restrict__ oct,
-                                            SlotVec<Real> u, SlotVec<Real> us) {
+                                            SlotVec<Real> u, SlotVec<Real> us, const Real *__restrict__ precv) {
   const int t = threadIdx.x, x = t & 7, y = t >> 3;
   for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
     const int slot = lv.act[b], ps = pslot[b], o = oct[b];
-    const Real *pu = u.at(ps);
-    const Real *pus = us.at(ps);
     Real *ub = u.at(slot);
-    const int pbase = ((4 * (o >> 2)) << 6) + ((4 * ((o >> 1) & 1) + (y >> 1)) << 3) + 4 * (o & 1) + (x >> 1);
     Real d[4];
+    if (ps >= 0) {
+      const Real *pu = u.at(ps);
+      const Real *pus = us.at(ps);
+      const int pbase = ((4 * (o >> 2)) << 6) + ((4 * ((o >> 1) & 1) + (y >> 1)) << 3) + 4 * (o & 1) + (x >> 1);
 #pragma unroll
-    for (int kz = 0; kz < 4; kz++)
-      d[kz] = pu[pbase + (kz << 6)] - pus[pbase + (kz << 6)];
+      for (int kz = 0; kz < 4; kz++)
+        d[kz] = pu[pbase + (kz << 6)] - pus[pbase + (kz << 6)];
+    } else {  // correction u_c - us of a remote parent, received as 4^3 values (mg_get, main.c:4771)
+      const Real *q = precv + (size_t)(kRemote0 - ps) * 64;
+#pragma unroll
+      for (int kz = 0; kz < 4; kz++)
+        d[kz] = q[(kz * 4 + (y >> 1)) * 4 + (x >> 1)];
+    }
 #pragma unroll
     for (int k = 0; k < 8; k++)
       ub[k * 64 + t] += d[k >> 1];
@@ -287,7 +302,7 @@ struct Arr {
   SlotVec<Real> u0, u1, f, us;
 };
 
-inline LevelView view(const Level &v) { return LevelView{v.d_act, v.d_nbr, (int)v.act.size()}; }
+inline LevelView view(const Level &v) { return LevelView{v.d_act, v.d_nbr, (int)v.act.size(), v.d_frecv}; }
 
 inline int grid_for(const CupCtx *c, long long nwork, int per_sm) {
   long long g = (long long)c->num_sms * per_sm;
@@ -333,8 +348,8 @@ int launch_smooth0(CupCtx *c, int grid, LevelView lv, SlotVec<Real> src, SlotVec
 }
 
 template <typename Real>
-int smooth_level(CupCtx *c, const Level &v, int n, Arr<Real> &a, bool first_is_zero, const double *fmean) {
-  if (v.act.empty() || n == 0)
+int smooth_level(CupCtx *c, Level &v, int n, Arr<Real> &a, bool first_is_zero, const double *fmean) {
+  if (n == 0 || (v.act.empty() && v.gnact == 0))
     return CUP_OK;
   if (!v.uniform) {
     set_error("multigrid level %d has coarse-fine interfaces: AMR smoother not available in this build", v.L);
@@ -345,6 +360,10 @@ int smooth_level(CupCtx *c, const Level &v, int n, Arr<Real> &a, bool first_is_z
   for (int it = 0; it < n; it++) {
     SlotVec<Real> &src = (it & 1) ? a.u1 : a.u0;
     SlotVec<Real> &dst = (it & 1) ? a.u0 : a.u1;
+    if (!(it == 0 && first_is_zero))
+      CUP_TRY(halo_exchange<Real>(c, v, src));
+    if (v.act.empty())
+      continue;
     if (it == 0 && first_is_zero)
       k_smooth<Real, 1, 8><<<grid, TPB, 0, c->stream>>>(view(v), src, dst, a.f, (const Real *)c->d_W, h, invh, om,
                                                          fmean);
@@ -370,28 +389,36 @@ int vcycle_t(CupCtx *c, const Real *d_in, Real *d_out) {
   enum { MG_PRE = 2, MG_POST = 2, MG_BOT = 50 };  // main.c:4433
   // finest level holding blocks
   int top = c->top;
-  while (top > 0 && c->lv[top].act.empty())
+  while (top > 0 && c->lv[top].gnact == 0)
     top--;
   if (!c->leaf_uniform) {
     set_error("mg_vcycle on a multi-level mesh is not available in this build");
     return CUP_ERR_UNSUPPORTED;
   }
   for (int L = top; L >= 1; L--) {
-    const Level &v = c->lv[L];
+    Level &v = c->lv[L];
     // u == 0 on entry only at the finest level (vec_zero, :4834); coarser
     // levels start from the restricted u (FAS).
     CUP_TRY(smooth_level<Real>(c, v, MG_PRE, a, L == top, nullptr));
-    const int grid = grid_for(c, (long long)v.act.size(), 12);
-    k_down<Real><<<grid, TPB, 0, c->stream>>>(view(v), v.d_pslot, v.d_oct, a.u0, a.f, (Real)v.h);
-    c->launches++;
-    const Level &w = c->lv[L - 1];
-    const int gridw = grid_for(c, (long long)w.par.size(), 12);
-    k_apply<Real, true><<<gridw, TPB, 0, c->stream>>>(view(w), w.d_par, (int)w.par.size(), a.u0, a.f, a.us,
-                                                       (Real)w.h, nullptr, (Real)0);
-    c->launches++;
+    CUP_TRY(halo_exchange<Real>(c, v, a.u0));
+    if (!v.act.empty()) {
+      const int grid = grid_for(c, (long long)v.act.size(), 12);
+      k_down<Real><<<grid, TPB, 0, c->stream>>>(view(v), v.d_pslot, v.d_oct, a.u0, a.f, (Real)v.h,
+                                                 (Real *)v.d_rsend);
+      c->launches++;
+    }
+    CUP_TRY(restrict_exchange<Real>(c, v, a.f, a.u0));
+    Level &w = c->lv[L - 1];
+    CUP_TRY(halo_exchange<Real>(c, w, a.u0));
+    if (!w.par.empty()) {
+      const int gridw = grid_for(c, (long long)w.par.size(), 12);
+      k_apply<Real, true><<<gridw, TPB, 0, c->stream>>>(view(w), w.d_par, (int)w.par.size(), a.u0, a.f, a.us,
+                                                         (Real)w.h, nullptr, (Real)0);
+      c->launches++;
+    }
   }
   {
-    const Level &v = c->lv[0];
+    Level &v = c->lv[0];
     double *q = c->d_scal + 0;
     const double *fmean = nullptr;
     if (top == 0) {
@@ -399,16 +426,20 @@ int vcycle_t(CupCtx *c, const Real *d_in, Real *d_out) {
     }
     CUP_CUDA(cudaMemsetAsync(q, 0, sizeof(double), c->stream));
     k_level_sum<Real><<<grid_for(c, (long long)v.act.size(), 4), 256, 0, c->stream>>>(
-        view(v), a.f, q, 1.0 / (512.0 * (double)v.act.size()));
+        view(v), a.f, q, 1.0 / (512.0 * (double)v.gnact));
     c->launches++;
+    CUP_TRY(comm_allreduce(c, 0, 1));
     fmean = q;
     CUP_TRY(smooth_level<Real>(c, v, MG_BOT, a, top == 0, fmean));
   }
   for (int L = 1; L <= top; L++) {
-    const Level &v = c->lv[L];
-    const int grid = grid_for(c, (long long)v.act.size(), 16);
-    k_up<Real><<<grid, TPB, 0, c->stream>>>(view(v), v.d_pslot, v.d_oct, a.u0, a.us);
-    c->launches++;
+    Level &v = c->lv[L];
+    CUP_TRY(prolong_exchange<Real>(c, v, a.u0, a.us));
+    if (!v.act.empty()) {
+      const int grid = grid_for(c, (long long)v.act.size(), 16);
+      k_up<Real><<<grid, TPB, 0, c->stream>>>(view(v), v.d_pslot, v.d_oct, a.u0, a.us, (const Real *)v.d_rsend);
+      c->launches++;
+    }
     CUP_TRY(smooth_level<Real>(c, v, MG_POST, a, false, nullptr));
   }
   CUP_CUDA(cudaGetLastError());
@@ -453,9 +484,9 @@ int pois_op_t(CupCtx *c, const Real *d_in, Real *d_out) {
     return CUP_ERR_UNSUPPORTED;
   }
   int top = c->top;
-  while (top > 0 && c->lv[top].act.empty())
+  while (top > 0 && c->lv[top].gnact == 0)
     top--;
-  const Level &v = c->lv[top];
+  Level &v = c->lv[top];
   const int mc = c->prm.mean_constraint;
   const double *shift = nullptr;
   double *q = c->d_scal + 1;
@@ -463,20 +494,19 @@ int pois_op_t(CupCtx *c, const Real *d_in, Real *d_out) {
     CUP_CUDA(cudaMemsetAsync(q, 0, sizeof(double), c->stream));
     k_wsum<Real><<<grid_for(c, c->nblk, 8), 256, 0, c->stream>>>(d_in, (const Real *)c->d_hw, c->nblk, q);
     c->launches++;
+    CUP_TRY(comm_allreduce(c, 1, 1));
     if (mc == 2)
       shift = q;
   }
   const int nleaf = (int)c->nblk;
   SlotVec<Real> u{const_cast<Real *>(d_in), nullptr, nleaf}, o{d_out, nullptr, nleaf}, us{nullptr, nullptr, nleaf};
+  CUP_TRY(halo_exchange<Real>(c, v, u));
   const Real h = (Real)v.h;
   k_apply<Real, false><<<grid_for(c, c->nblk, 16), TPB, 0, c->stream>>>(view(v), nullptr, (int)v.act.size(), u, o,
                                                                          us, h, shift, h * h * h);
   c->launches++;
   if (mc == 1 || mc > 2) {
-    long long pin = -1;  // pois_pin: block (0,0,0), main.c:4888
-    for (long long i = 0; i < c->nblk; i++)
-      if (c->blk[i].ix == 0 && c->blk[i].iy == 0 && c->blk[i].iz == 0)
-        pin = i;
+    const long long pin = c->pin_local;  // pois_pin: block (0,0,0), main.c:4888 (on its owner only)
     if (pin >= 0) {
       k_pin<Real><<<1, 1, 0, c->stream>>>(d_in, d_out, pin * 512, q, mc);
       c->launches++;

@@ -44,7 +44,8 @@ __global__ void __launch_bounds__(TPB, 12)
   __shared__ __align__(128) Real s_x[2][64 * NCOL];
   __shared__ __align__(128) Real ex[512];
   __shared__ __align__(8) uint64_t mbar;
-  __shared__ int s_wall;  // bit f set: face f is a domain wall (ghost = own boundary plane)
+  __shared__ int s_wall;  // bit f: face f is a domain wall (ghost = own boundary plane); bit 8+f: face f
+                          // came from another rank (compact 8x8 plane out of lv.rface)
 
   const int t = threadIdx.x, x = t & 7, y = t >> 3;
   const int G = gridDim.x;
@@ -59,17 +60,31 @@ __global__ void __launch_bounds__(TPB, 12)
     int wall = 0;
 #pragma unroll
     for (int f = 0; f < 6; f++)
-      wall |= (nb[f] < 0) << f;
+      wall |= ((nb[f] == kWall) << f) | ((nb[f] <= kRemote0) << (8 + f));
     s_wall = wall;
-    mbar_arrive_expect_tx(&mbar, TmaCfg<Real>::BYTES);
+    const Real *rf = (const Real *)lv.rface;
+    // x faces from a local block arrive as 16-byte rows (NCOL values each), received ones compact
+    uint32_t bytes = TmaCfg<Real>::BYTES;
+    if (nb[0] <= kRemote0) bytes -= 64 * (NCOL - 1) * (uint32_t)sizeof(Real);
+    if (nb[1] <= kRemote0) bytes -= 64 * (NCOL - 1) * (uint32_t)sizeof(Real);
+    mbar_arrive_expect_tx(&mbar, bytes);
     const Real *own = usrc.at(slot);
     tma_load_1d(s_u, own, 512 * sizeof(Real), &mbar);
     tma_load_1d(s_f, fvec.at(slot), 512 * sizeof(Real), &mbar);
     // z faces: neighbour's opposite plane, or own plane at a wall
-    tma_load_1d(s_z[0], nb[4] >= 0 ? usrc.at(nb[4]) + 7 * 64 : own, 64 * sizeof(Real), &mbar);
-    tma_load_1d(s_z[1], nb[5] >= 0 ? usrc.at(nb[5]) : own + 7 * 64, 64 * sizeof(Real), &mbar);
+    tma_load_1d(s_z[0],
+                nb[4] >= 0 ? usrc.at(nb[4]) + 7 * 64 : (nb[4] == kWall ? own : rf + (size_t)(kRemote0 - nb[4]) * 64),
+                64 * sizeof(Real), &mbar);
+    tma_load_1d(s_z[1],
+                nb[5] >= 0 ? usrc.at(nb[5]) : (nb[5] == kWall ? own + 7 * 64 : rf + (size_t)(kRemote0 - nb[5]) * 64),
+                64 * sizeof(Real), &mbar);
 #pragma unroll
     for (int f = 0; f < 4; f++) {
+      if (nb[f] <= kRemote0) {  // received face: already a compact plane in the consumer's order
+        tma_load_1d(f < 2 ? (Real *)s_x[f] : (Real *)s_y[f - 2], rf + (size_t)(kRemote0 - nb[f]) * 64,
+                    64 * sizeof(Real), &mbar);
+        continue;
+      }
       const int ts = nb[f] >= 0 ? nb[f] : slot;
       const bool leaf = ts < usrc.nleaf;
       const int row0 = (leaf ? ts : ts - usrc.nleaf) * 8;
@@ -119,13 +134,15 @@ __global__ void __launch_bounds__(TPB, 12)
     {
       // ghost sums (see ghost_sum in mg_device.cuh); x-face column depends on wall-ness
       const int cxm = (wall & 1) ? 0 : NCOL - 1, cxp = (wall & 2) ? NCOL - 1 : 0;
+      const int stm = (wall & 0x100) ? 1 : NCOL, stp = (wall & 0x200) ? 1 : NCOL;
+      const int om = (wall & 0x100) ? 0 : cxm, op = (wall & 0x200) ? 0 : cxp;
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         Real g = 0;
         if (x == 0)
-          g += s_x[0][(k * 8 + y) * NCOL + cxm];
+          g += s_x[0][(k * 8 + y) * stm + om];
         if (x == 7)
-          g += s_x[1][(k * 8 + y) * NCOL + cxp];
+          g += s_x[1][(k * 8 + y) * stp + op];
         if (y == 0)
           g += s_y[0][k * 8 + x];
         if (y == 7)

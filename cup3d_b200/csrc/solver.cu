@@ -67,14 +67,8 @@ int pois_solve(CupCtx *c, CupSolveInfo *info) {
   const int mc = c->prm.mean_constraint;
   const double ptol = c->prm.ptol, ptol_rel = c->prm.ptol_rel;
   double H[KR_M + 1][KR_M], cs[KR_M], sn[KR_M], g[KR_M + 1], y[KR_M];
-  double vol = 0;
-  long long pin = -1;
-  for (long long i = 0; i < c->nblk; i++) {
-    const CupBlk &b = c->blk[i];
-    vol += 512 * (b.h * b.h * b.h);
-    if (b.ix == 0 && b.iy == 0 && b.iz == 0)
-      pin = i;
-  }
+  const double vol = c->gvol;          // sum over ALL ranks (MPI_Allreduce, main.c:4891)
+  const long long pin = c->pin_local;  // block (0,0,0) on its owner, else -1
   auto Vj = [&](int j) { return (void *)((char *)K.V + (size_t)j * N * rb); };
   // b = F_LHS (with the pinned cell zeroed for constraint 1 / >2), x = F_PRES
   CUP_CUDA(cudaMemcpyAsync(K.b, c->state[CUP_F_LHS], N * rb, cudaMemcpyDeviceToDevice, c->stream));

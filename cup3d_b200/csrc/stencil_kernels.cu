@@ -13,6 +13,7 @@
 
 #include "blas_kernels.cuh"
 #include "cup_internal.h"
+#include "comm.cuh"
 #include "mg_device.cuh"
 
 namespace cup {
@@ -319,7 +320,7 @@ inline int bgrid(const CupCtx *c, long long nb, int per_sm) {
 
 const Level *leaf_level(CupCtx *c) {
   int top = c->top;
-  while (top > 0 && c->lv[top].act.empty())
+  while (top > 0 && c->lv[top].gnact == 0)
     top--;
   return &c->lv[top];
 }
@@ -339,7 +340,11 @@ int need_uniform(CupCtx *c, const char *what) {
 template <typename Real>
 int stencil_t(CupCtx *c, CupStencilId id, const int *d_sub, long long nsub) {
   const Level &v = *leaf_level(c);
-  LevelView lv{v.d_act, v.d_nbr, (int)v.act.size()};
+  LevelView lv{v.d_act, v.d_nbr, (int)v.act.size(), v.d_frecv};
+  if (c->nranks > 1 && id != CUP_ST_LHS && id != CUP_ST_MG) {
+    set_error("stencil sweeps other than LHS/MG are single-rank in this build");
+    return CUP_ERR_UNSUPPORTED;
+  }
   if (d_sub) {
     set_error("stencil_run: block sub-lists are only supported for CUP_ST_MG/CUP_ST_LHS");
     return CUP_ERR_UNSUPPORTED;
@@ -440,13 +445,12 @@ int projection_t(CupCtx *c, CupSolveInfo *info) {
   }
   CUP_TRY(pois_solve(c, info));
   // subtract the volume-weighted mean (main.c:5871-5895)
-  double vol = 0;
-  for (long long i = 0; i < c->nblk; i++)
-    vol += 512 * (c->blk[i].h * c->blk[i].h * c->blk[i].h);
+  const double vol = c->gvol;
   double *q = c->d_scal + 5;
   CUP_CUDA(cudaMemsetAsync(q, 0, sizeof(double), c->stream));
   k_wsum_blk<Real><<<bgrid(c, c->nblk, 8), 256, 0, c->stream>>>(S[CUP_F_PRES], (const Real *)c->d_hw, c->nblk, q);
   c->launches++;
+  CUP_TRY(comm_allreduce(c, 5, 1));
   k_pres_fix<Real><<<sgrid(c, N), 256, 0, c->stream>>>(S[CUP_F_PRES],
                                                         c->prm.step > STEP_2ND ? (const Real *)c->p_old : nullptr, N, q,
                                                         vol);

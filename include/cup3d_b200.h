@@ -140,6 +140,29 @@ int cup_projection_udef_ready(CupCtx *ctx, int flag);
 int cup_comm_init(CupCtx *ctx, int rank, int nranks, const void *nccl_id, size_t id_bytes);
 int cup_nccl_unique_id(void *out, size_t bytes);
 
+/* Host-only view of one rank's exchange plan for one multigrid level (no GPU
+ * needed; used by the CPU tests that emulate the exchange over gloo).  Built
+ * from the GLOBAL block list + owner rank per block, exactly what
+ * cup_mesh_upload derives after its all-gather.  Arrays are malloc'ed; release
+ * with cup_plan_free. */
+typedef struct CupPlan {
+  long long nblk, nslot;      /* local leaves / local slots */
+  int nact;                   /* local active blocks of the level */
+  int nsend, nrecv;           /* faces sent / received per exchange */
+  int *act;                   /* [nact] local slot */
+  int *ijk;                   /* [nact][3] block index at this level */
+  int *nbr;                   /* [nact][6] local slot, -1 wall, <= -3: received face (-3 - code) */
+  int *send_slot, *send_plane;/* [nsend] local slot and plane (0..5) to pack, peer-major */
+  int *send_cnt, *recv_cnt;   /* [nranks] */
+  int *pslot, *oct;           /* [nact] parent slot (<= -3: entry of the restriction send buffer) */
+  int *res_send_cnt, *res_recv_cnt; /* [nranks] children sent to / received from each peer */
+  int nres_recv;
+  int *res_recv_slot, *res_recv_oct; /* [nres_recv] local parent slot + octant of received children */
+} CupPlan;
+int cup_plan_build(const CupBlk *gblk, long long nglobal, const int *owner, int nranks, int rank, const int bpd[3],
+                   int level_max, int level, CupPlan *out);
+void cup_plan_free(CupPlan *p);
+
 /* instrumentation: number of kernels launched by this context so far */
 long long cup_kernel_launches(const CupCtx *ctx);
 /* timing of an internal kernel class with CUDA events on the ctx stream:
