@@ -108,6 +108,9 @@ int cup_create(CupCtx **out, int device, int real_bytes) {
   CUP_CUDA(cudaMalloc((void **)&c->d_scal, SCAL_N * sizeof(double)));
   CUP_CUDA(cudaMemset(c->d_scal, 0, SCAL_N * sizeof(double)));
   CUP_CUDA(cudaMallocHost((void **)&c->h_scal, SCAL_N * sizeof(double)));
+  CUP_CUDA(cudaStreamCreateWithFlags(&c->cstream, cudaStreamNonBlocking));
+  CUP_CUDA(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+  CUP_CUDA(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
   *out = c;
   return CUP_OK;
 }
@@ -137,6 +140,9 @@ int cup_destroy(CupCtx *c) {
   cudaFree(c->d_hw);
   cudaFree(c->d_scal);
   cudaFreeHost(c->h_scal);
+  cudaStreamDestroy(c->cstream);
+  cudaEventDestroy(c->ev_ready);
+  cudaEventDestroy(c->ev_halo);
   delete c;
   return CUP_OK;
 }

@@ -86,6 +86,8 @@ struct CupCtx {
   int real_bytes = 8;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t cstream = nullptr;   // halo exchanges overlapped with interior sweeps
+  cudaEvent_t ev_ready = nullptr, ev_halo = nullptr;
   CupParams prm{};
   long long nblk = 0, nslot = 0;   // LOCAL leaves / local slots
   long long gblocks = 0;           // leaves over all ranks

@@ -27,6 +27,7 @@
 // a Hilbert key; nothing here depends on it).
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <unordered_map>
 
 #include "cup_internal.h"
@@ -51,6 +52,11 @@ struct Xent {  // one exchange entry before sorting
     return plane < o.plane;
   }
 };
+
+long long coarse_threshold() {
+  const char *e = getenv("CUP_COARSE_BLOCKS");
+  return e ? atoll(e) : 4096;
+}
 
 void count_by_peer(const std::vector<Xent> &v, int nranks, std::vector<int> &cnt) {
   cnt.assign(nranks, 0);
@@ -197,6 +203,17 @@ int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner_
       }
       nchild[(size_t)(ps - first)]++;
       g.pg[k] = ps;
+    }
+    // Small coarse levels are latency-bound and would cost one exchange per sweep
+    // for a handful of blocks per rank: below a threshold the whole level lives on
+    // rank 0 (one restriction/prolongation hop instead of ~7 halo exchanges per level).
+    {
+      long long nnext = 0;
+      for (const Ent &e : next)
+        nnext += (e.level == L - 1);
+      if (nranks > 1 && nnext <= coarse_threshold())
+        for (long long s2 = first; s2 < gnslot; s2++)
+          owner[s2] = 0;
     }
     for (size_t p = 0; p < nchild.size(); p++)
       if (nchild[p] != 8) {

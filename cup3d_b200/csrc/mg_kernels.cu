@@ -9,6 +9,7 @@
 // (read u, f; write u'), down 2.25, tau 4 per coarse cell, up 2.25.
 #include <cmath>
 #include <cstdlib>
+#include <utility>
 
 #include "cup_internal.h"
 #include "mg_device.cuh"
@@ -334,10 +335,15 @@ static int smooth_minb() {
 
 template <typename Real>
 int launch_smooth0(CupCtx *c, int grid, LevelView lv, SlotVec<Real> src, SlotVec<Real> dst, SlotVec<Real> f, Real h,
-                   Real invh, Real om, const double *fmean) {
+                   Real invh, Real om, const double *fmean, const int *sub = nullptr, int nsub = -1) {
   const Real *W = (const Real *)c->d_W;
   if (smooth_use_tma())
-    return smooth_tma_launch<Real>(c, grid, lv, src, dst, f, h, invh, om, fmean);
+    return smooth_tma_launch<Real>(c, c->stream, grid, lv, sub, nsub < 0 ? lv.nact : nsub, src, dst, f, h, invh, om,
+                                   fmean);
+  if (sub) {
+    set_error("block sub-lists need the TMA smoother");
+    return CUP_ERR_UNSUPPORTED;
+  }
   switch (smooth_minb()) {
   case 10: k_smooth<Real, 0, 10><<<grid, TPB, 0, c->stream>>>(lv, src, dst, f, W, h, invh, om, fmean); break;
   case 12: k_smooth<Real, 0, 12><<<grid, TPB, 0, c->stream>>>(lv, src, dst, f, W, h, invh, om, fmean); break;
@@ -360,7 +366,27 @@ int smooth_level(CupCtx *c, Level &v, int n, Arr<Real> &a, bool first_is_zero, c
   for (int it = 0; it < n; it++) {
     SlotVec<Real> &src = (it & 1) ? a.u1 : a.u0;
     SlotVec<Real> &dst = (it & 1) ? a.u0 : a.u1;
-    if (!(it == 0 && first_is_zero))
+    const bool zero = (it == 0 && first_is_zero);
+    // comm/compute overlap: blocks without a remote neighbour are swept while the faces of
+    // the others are packed and exchanged on a second stream
+    if (!zero && c->nranks > 1 && smooth_use_tma() && v.inner.size() >= 512 && !v.bnd.empty()) {
+      CUP_CUDA(cudaEventRecord(c->ev_ready, c->stream));
+      CUP_CUDA(cudaStreamWaitEvent(c->cstream, c->ev_ready, 0));
+      std::swap(c->stream, c->cstream);
+      int rc = halo_exchange<Real>(c, v, src);
+      cudaError_t e = cudaEventRecord(c->ev_halo, c->stream);
+      std::swap(c->stream, c->cstream);
+      CUP_TRY(rc);
+      CUP_CUDA(e);
+      CUP_TRY(launch_smooth0<Real>(c, grid_for(c, (long long)v.inner.size(), 12), view(v), src, dst, a.f, h, invh, om,
+                                   fmean, v.d_inner, (int)v.inner.size()));
+      CUP_CUDA(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+      CUP_TRY(launch_smooth0<Real>(c, grid_for(c, (long long)v.bnd.size(), 12), view(v), src, dst, a.f, h, invh, om,
+                                   fmean, v.d_bnd, (int)v.bnd.size()));
+      c->launches += 2;
+      continue;
+    }
+    if (!zero)
       CUP_TRY(halo_exchange<Real>(c, v, src));
     if (v.act.empty())
       continue;

@@ -32,7 +32,7 @@ struct TmaCfg {
 
 template <typename Real>
 __global__ void __launch_bounds__(TPB, 12)
-    k_smooth_tma(LevelView lv, SlotVec<Real> usrc, SlotVec<Real> udst, SlotVec<Real> fvec, const Real *__restrict__ Wl,
+    k_smooth_tma(LevelView lv, const int *__restrict__ sub, int nsub, SlotVec<Real> usrc, SlotVec<Real> udst, SlotVec<Real> fvec, const Real *__restrict__ Wl,
                  Real h, Real invh, Real omega, const double *__restrict__ fmean,
                  const __grid_constant__ CUtensorMap mx_leaf, const __grid_constant__ CUtensorMap my_leaf,
                  const __grid_constant__ CUtensorMap mx_extra, const __grid_constant__ CUtensorMap my_extra) {
@@ -102,25 +102,29 @@ __global__ void __launch_bounds__(TPB, 12)
     mbar_fence_init();
   }
   __syncthreads();
-  int b = blockIdx.x;
-  if (t == 0 && b < lv.nact) {
+  // work items: sub[i] (indices into act[]) or 0..nsub-1
+  int i = blockIdx.x;
+  if (t == 0 && i < nsub) {
+    const int b0 = sub ? sub[i] : i;
     int nb[6];
 #pragma unroll
     for (int f = 0; f < 6; f++)
-      nb[f] = lv.nbr[(size_t)b * 6 + f];
-    issue(lv.act[b], nb);
+      nb[f] = lv.nbr[(size_t)b0 * 6 + f];
+    issue(lv.act[b0], nb);
   }
   uint32_t phase = 0;
-  for (; b < lv.nact; b += G) {
+  for (; i < nsub; i += G) {
+    const int b = sub ? sub[i] : i;
     const int slot = lv.act[b];
     // producer: fetch the NEXT block's indices now so they are in registers when needed
     int nslot = 0, nnb[6] = {0, 0, 0, 0, 0, 0};
-    const bool more = (b + G) < lv.nact;
+    const bool more = (i + G) < nsub;
     if (t == 0 && more) {
-      nslot = lv.act[b + G];
+      const int bn = sub ? sub[i + G] : i + G;
+      nslot = lv.act[bn];
 #pragma unroll
       for (int f = 0; f < 6; f++)
-        nnb[f] = lv.nbr[(size_t)(b + G) * 6 + f];
+        nnb[f] = lv.nbr[(size_t)bn * 6 + f];
     }
     mbar_wait(&mbar, phase);
     phase ^= 1;
@@ -283,7 +287,8 @@ void free_tma_cache(CupCtx *c) {
 }
 
 template <typename Real>
-int smooth_tma_launch(CupCtx *c, int grid, LevelView lv, SlotVec<Real> src, SlotVec<Real> dst, SlotVec<Real> f, Real h,
+int smooth_tma_launch(CupCtx *c, cudaStream_t stream, int grid, LevelView lv, const int *sub, int nsub,
+                      SlotVec<Real> src, SlotVec<Real> dst, SlotVec<Real> f, Real h,
                       Real invh, Real om, const double *fmean) {
   CUtensorMap mxl, myl, mxe, mye;
   const long long nleaf = c->nblk, nx = c->nslot - c->nblk + 1;
@@ -294,14 +299,14 @@ int smooth_tma_launch(CupCtx *c, int grid, LevelView lv, SlotVec<Real> src, Slot
   CUP_TRY(get_map(c, lb, src.leaf ? nleaf : 1, 1, &myl));
   CUP_TRY(get_map(c, eb, src.extra ? nx : 1, 0, &mxe));
   CUP_TRY(get_map(c, eb, src.extra ? nx : 1, 1, &mye));
-  k_smooth_tma<Real><<<grid, TPB, 0, c->stream>>>(lv, src, dst, f, (const Real *)c->d_W, h, invh, om, fmean, mxl, myl,
+  k_smooth_tma<Real><<<grid, TPB, 0, stream>>>(lv, sub, nsub, src, dst, f, (const Real *)c->d_W, h, invh, om, fmean, mxl, myl,
                                                    mxe, mye);
   return CUP_OK;
 }
 
-template int smooth_tma_launch<double>(CupCtx *, int, LevelView, SlotVec<double>, SlotVec<double>, SlotVec<double>,
+template int smooth_tma_launch<double>(CupCtx *, cudaStream_t, int, LevelView, const int *, int, SlotVec<double>, SlotVec<double>, SlotVec<double>,
                                        double, double, double, const double *);
-template int smooth_tma_launch<float>(CupCtx *, int, LevelView, SlotVec<float>, SlotVec<float>, SlotVec<float>, float,
+template int smooth_tma_launch<float>(CupCtx *, cudaStream_t, int, LevelView, const int *, int, SlotVec<float>, SlotVec<float>, SlotVec<float>, float,
                                       float, float, const double *);
 
 }  // namespace cup

@@ -43,8 +43,9 @@ def a2a(send, scnt, rcnt, width):
     return out.numpy().reshape(-1, width)
 
 
-def worker(rank, world, port, level, bpd):
+def worker(rank, world, port, level, bpd, coarse):
     sys.path.insert(0, ROOT)
+    os.environ["CUP_COARSE_BLOCKS"] = str(coarse)  # 0: parents follow their children's owner
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -117,6 +118,7 @@ def free_port():
     return p
 
 
-@pytest.mark.parametrize("world,level,bpd", [(2, 2, (1, 1, 1)), (3, 2, (1, 1, 1)), (2, 1, (2, 1, 3))])
-def test_exchange_plans_over_gloo(built, world, level, bpd):
-    mp.spawn(worker, args=(world, free_port(), level, bpd), nprocs=world, join=True)
+@pytest.mark.parametrize("world,level,bpd,coarse", [(2, 2, (1, 1, 1), 0), (3, 2, (1, 1, 1), 0), (2, 1, (2, 1, 3), 0),
+                                                    (3, 2, (1, 1, 1), 4096)])
+def test_exchange_plans_over_gloo(built, world, level, bpd, coarse):
+    mp.spawn(worker, args=(world, free_port(), level, bpd, coarse), nprocs=world, join=True)

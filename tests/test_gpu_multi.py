@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def worker(rank, world, nid, name, q):
+def worker(rank, world, nid, name, coarse, q):
+    os.environ["CUP_COARSE_BLOCKS"] = str(coarse)
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -46,8 +47,8 @@ def worker(rank, world, nid, name, q):
     ctx.close()
 
 
-@pytest.mark.parametrize("name", ["u32", "u64"])
-def test_two_rank_matches_single_rank_reference(built, name):
+@pytest.mark.parametrize("name,coarse", [("u32", 0), ("u64", 0), ("u64", 4096)])
+def test_two_rank_matches_single_rank_reference(built, name, coarse):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -57,7 +58,7 @@ def test_two_rank_matches_single_rank_reference(built, name):
     nid = capi.nccl_unique_id()
     ctxm = mp.get_context("spawn")
     q = ctxm.Queue()
-    ps = [ctxm.Process(target=worker, args=(r, 2, nid, name, q)) for r in range(2)]
+    ps = [ctxm.Process(target=worker, args=(r, 2, nid, name, coarse, q)) for r in range(2)]
     for p in ps:
         p.start()
     got = [q.get(timeout=300) for _ in ps]
