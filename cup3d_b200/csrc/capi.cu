@@ -108,6 +108,10 @@ int cup_create(CupCtx **out, int device, int real_bytes) {
   CUP_CUDA(cudaMalloc((void **)&c->d_scal, SCAL_N * sizeof(double)));
   CUP_CUDA(cudaMemset(c->d_scal, 0, SCAL_N * sizeof(double)));
   CUP_CUDA(cudaMallocHost((void **)&c->h_scal, SCAL_N * sizeof(double)));
+  // the NULL stream cannot be captured into a CUDA graph: work goes to an own BLOCKING stream
+  // (implicitly ordered against legacy-default-stream work of the caller) unless one is set
+  CUP_CUDA(cudaStreamCreate(&c->own_stream));
+  c->stream = c->own_stream;
   CUP_CUDA(cudaStreamCreateWithFlags(&c->cstream, cudaStreamNonBlocking));
   CUP_CUDA(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
   CUP_CUDA(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
@@ -121,6 +125,7 @@ int cup_destroy(CupCtx *c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   free_krylov(c);
+  free_graph_cache(c);
   comm_free_level_buffers(c);
   free_mesh(c);
   free_tma_cache(c);
@@ -141,6 +146,7 @@ int cup_destroy(CupCtx *c) {
   cudaFree(c->d_scal);
   cudaFreeHost(c->h_scal);
   cudaStreamDestroy(c->cstream);
+  cudaStreamDestroy(c->own_stream);
   cudaEventDestroy(c->ev_ready);
   cudaEventDestroy(c->ev_halo);
   delete c;
@@ -148,7 +154,7 @@ int cup_destroy(CupCtx *c) {
 }
 
 int cup_set_stream(CupCtx *c, void *stream) {
-  c->stream = (cudaStream_t)stream;
+  c->stream = stream ? (cudaStream_t)stream : c->own_stream;
   return CUP_OK;
 }
 
@@ -170,6 +176,7 @@ int cup_mesh_upload(CupCtx *c, const CupBlk *blk, long long n, const int bpd[3],
   CUP_CUDA(cudaSetDevice(c->device));
   CUP_CUDA(cudaStreamSynchronize(c->stream));
   free_krylov(c);
+  free_graph_cache(c);
   comm_free_level_buffers(c);
   // tree_sync (main.c:2928): all ranks learn all blocks; owner = contributing rank
   std::vector<CupBlk> gblk;

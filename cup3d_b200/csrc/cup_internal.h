@@ -85,7 +85,8 @@ struct CupCtx {
   int device = 0;
   int real_bytes = 8;
   int num_sms = 148;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;    // where all work is enqueued (own_stream unless the caller set one)
+  cudaStream_t own_stream = nullptr;  // blocking stream: ordered against the legacy default stream
   cudaStream_t cstream = nullptr;   // halo exchanges overlapped with interior sweeps
   cudaEvent_t ev_ready = nullptr, ev_halo = nullptr;
   CupParams prm{};
@@ -116,6 +117,7 @@ struct CupCtx {
   cup::Krylov *kr = nullptr;
   long long launches = 0;
   void *p_old = nullptr;        // projection(): previous pressure
+  void *graph_cache = nullptr;  // captured V-cycles keyed by (in, out) (mg_kernels.cu)
   void *tma_cache = nullptr;    // tensor-map cache (smooth_tma.cu)
   bool keep_tmp_udef = false;   // projection(): F_TMP already holds fish_tmpv()'s udef
 };
@@ -130,6 +132,7 @@ void free_mesh(CupCtx *c);
 
 // mg_kernels.cu
 int mg_setup(CupCtx *c);  // constants + scratch after build_mesh
+void free_graph_cache(CupCtx *c);
 int mg_vcycle_dev(CupCtx *c, const void *d_in, void *d_out);
 int pois_op_dev(CupCtx *c, const void *d_in, void *d_out);
 int mg_smooth_slots(CupCtx *c, int level, int n, void *d_u, const void *d_f);

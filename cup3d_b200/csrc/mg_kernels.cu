@@ -9,6 +9,7 @@
 // (read u, f; write u'), down 2.25, tau 4 per coarse cell, up 2.25.
 #include <cmath>
 #include <cstdlib>
+#include <map>
 #include <utility>
 
 #include "cup_internal.h"
@@ -612,13 +613,89 @@ int mg_setup(CupCtx *c) {
   return CUP_OK;
 }
 
+// ---------------------------------------------------------------------------
+// CUDA-graph replay of the V-cycle.  A cycle is ~100 small launches (plus the
+// NCCL exchanges on several ranks); on the coarse levels and with the work
+// split over GPUs the host cannot issue them as fast as the device retires
+// them.  The launch sequence depends only on the mesh and on the (in, out)
+// pointers, so it is captured once per pointer pair and replayed.
+struct GraphEntry {
+  cudaGraphExec_t exec = nullptr;
+  long long launches = 0;
+};
+struct GraphCache {
+  std::map<std::pair<const void *, void *>, GraphEntry> m;
+  bool warmed = false;  // one eager cycle first (NCCL sets up its connections lazily)
+};
+
+void free_graph_cache(CupCtx *c) {
+  GraphCache *g = (GraphCache *)c->graph_cache;
+  if (!g)
+    return;
+  for (auto &kv : g->m)
+    if (kv.second.exec)
+      cudaGraphExecDestroy(kv.second.exec);
+  delete g;
+  c->graph_cache = nullptr;
+}
+
+static bool use_graphs() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("CUP_GRAPH");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
+static int vcycle_eager(CupCtx *c, const void *d_in, void *d_out) {
+  return c->real_bytes == 8 ? vcycle_t<double>(c, (const double *)d_in, (double *)d_out)
+                            : vcycle_t<float>(c, (const float *)d_in, (float *)d_out);
+}
+
 int mg_vcycle_dev(CupCtx *c, const void *d_in, void *d_out) {
   if (c->nblk == 0) {
     set_error("mg_vcycle: no mesh uploaded");
     return CUP_ERR_STATE;
   }
-  return c->real_bytes == 8 ? vcycle_t<double>(c, (const double *)d_in, (double *)d_out)
-                            : vcycle_t<float>(c, (const float *)d_in, (float *)d_out);
+  if (!use_graphs())
+    return vcycle_eager(c, d_in, d_out);
+  if (!c->graph_cache)
+    c->graph_cache = new GraphCache;
+  GraphCache *g = (GraphCache *)c->graph_cache;
+  if (!g->warmed) {
+    g->warmed = true;
+    return vcycle_eager(c, d_in, d_out);
+  }
+  auto key = std::make_pair(d_in, d_out);
+  auto it = g->m.find(key);
+  if (it == g->m.end()) {
+    if (g->m.size() >= 128) {  // bounded: drop everything rather than grow without limit
+      for (auto &kv : g->m)
+        cudaGraphExecDestroy(kv.second.exec);
+      g->m.clear();
+    }
+    GraphEntry e;
+    const long long l0 = c->launches;
+    CUP_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = vcycle_eager(c, d_in, d_out);
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+    e.launches = c->launches - l0;
+    c->launches = l0;
+    if (rc != CUP_OK) {
+      if (graph)
+        cudaGraphDestroy(graph);
+      return rc;
+    }
+    CUP_CUDA(ce);
+    CUP_CUDA(cudaGraphInstantiate(&e.exec, graph, 0));
+    cudaGraphDestroy(graph);
+    it = g->m.emplace(key, e).first;
+  }
+  CUP_CUDA(cudaGraphLaunch(it->second.exec, c->stream));
+  c->launches += it->second.launches;
+  return CUP_OK;
 }
 
 int pois_op_dev(CupCtx *c, const void *d_in, void *d_out) {
