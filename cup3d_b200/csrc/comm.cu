@@ -72,6 +72,13 @@ struct Comm {
   ncclComm_t nccl = nullptr;
   void *gather_dev = nullptr;
   size_t gather_bytes = 0;
+  // ---- one-sided mode: every rank exposes one receive window through CUDA IPC ----
+  bool p2p = false;
+  char *win = nullptr;                 // [flags | per-level receive areas]
+  size_t flag_bytes = 0;
+  std::vector<char *> peer_win;        // mapped base of every rank's window (own = win)
+  char **d_peer_win = nullptr;
+  unsigned long long *d_seq = nullptr; // [levels][3] exchange counters of THIS rank (face, restrict, prolong)
 };
 
 #define CUP_NCCL(call)                                                                      \
@@ -191,6 +198,22 @@ int comm_allreduce(CupCtx *c, int first, int n) {
   return CUP_OK;
 }
 
+// ===========================================================================
+// Exchanges.  Two transports behind one post/wait interface:
+//
+//  * one-sided (default): the producer's pack kernel stores straight into the
+//    consumer's receive window over NVLink (CUDA-IPC mapped peer memory), a
+//    1-CTA signal kernel bumps the level's sequence number and writes it into
+//    the peers' flag words, and the consumer runs a 1-CTA wait kernel before
+//    its boundary blocks.  No NCCL kernel has to find room on SMs that the
+//    persistent sweep kernels occupy, so the exchange really overlaps the
+//    interior sweep.  Face areas are double buffered by sequence parity.
+//    Everything is replayable from a CUDA graph: epochs live in device memory.
+//  * NCCL (CUP_P2P=0 or IPC unavailable): pack to a staging buffer, grouped
+//    ncclSend/ncclRecv per peer.
+// ===========================================================================
+enum { K_FACE = 0, K_RES = 1, K_PRO = 2 };
+
 // grouped point-to-point exchange: entries of `entry_bytes` bytes, peer-major on both sides
 static int exchange(CupCtx *c, const void *sbuf, const std::vector<int> &scnt, void *rbuf,
                     const std::vector<int> &rcnt, size_t entry_bytes) {
@@ -212,14 +235,18 @@ static int exchange(CupCtx *c, const void *sbuf, const std::vector<int> &scnt, v
 }
 
 // ---------------------------------------------------------------------------
-// pack kernels
+// kernels
 // ---------------------------------------------------------------------------
 // one 64-thread CTA per face: plane p of block `slot`, element (a, c) = (t&7, t>>3) in the
-// receiver's convention (mg_device.cuh load_halo): x planes (y,z), y planes (x,z), z planes (x,y)
+// receiver's convention (mg_device.cuh load_halo): x planes (y,z), y planes (x,z), z planes (x,y).
+// dst0/dst1: per-entry destination for even / odd sequence numbers (may be peer memory).
 template <typename Real>
 __global__ void __launch_bounds__(64) k_pack_faces(const int *__restrict__ sslot, const int *__restrict__ splane,
-                                                   int n, SlotVec<Real> u, Real *__restrict__ out) {
+                                                   int n, SlotVec<Real> u, Real *const *__restrict__ dst0,
+                                                   Real *const *__restrict__ dst1,
+                                                   const unsigned long long *__restrict__ seq) {
   const int t = threadIdx.x, a = t & 7, cc = t >> 3;
+  const bool odd = seq ? ((*seq + 1) & 1) : false;  // the exchange being posted is number *seq + 1
   for (int e = blockIdx.x; e < n; e += gridDim.x) {
     const Real *b = u.at(sslot[e]);
     const int p = splane[e], q = (p & 1) ? 7 : 0;
@@ -230,7 +257,7 @@ __global__ void __launch_bounds__(64) k_pack_faces(const int *__restrict__ sslot
       idx = (cc << 6) + (q << 3) + a;
     else
       idx = (q << 6) + t;
-    out[(size_t)e * 64 + t] = b[idx];
+    (odd ? dst1 : dst0)[e][t] = b[idx];
   }
 }
 
@@ -250,13 +277,45 @@ __global__ void __launch_bounds__(64) k_put(const int *__restrict__ rslot, const
 // mg_get (main.c:4771): u_c - us of the parent's octant, for a remote child
 template <typename Real>
 __global__ void __launch_bounds__(64) k_get(const int *__restrict__ rslot, const int *__restrict__ roct, int n,
-                                            SlotVec<Real> u, SlotVec<Real> us, Real *__restrict__ out) {
+                                            SlotVec<Real> u, SlotVec<Real> us, Real *const *__restrict__ dst) {
   const int t = threadIdx.x, cx = t & 3, cy = (t >> 2) & 3, cz = t >> 4;
   for (int e = blockIdx.x; e < n; e += gridDim.x) {
     const int o = roct[e], ps = rslot[e];
     const int pidx = ((4 * (o >> 2) + cz) << 6) + ((4 * ((o >> 1) & 1) + cy) << 3) + 4 * (o & 1) + cx;
-    out[(size_t)e * 64 + t] = u.at(ps)[pidx] - us.at(ps)[pidx];
+    dst[e][t] = u.at(ps)[pidx] - us.at(ps)[pidx];
   }
+}
+
+// bump this rank's sequence number for (level, kind) and publish it to the peers' flag words
+__global__ void __launch_bounds__(64) k_signal(unsigned long long *seq, char *const *peer_win, const int *peers, int np,
+                                               size_t flag_index) {
+  __shared__ unsigned long long s;
+  if (threadIdx.x == 0) {
+    s = *seq + 1;
+    *seq = s;
+  }
+  __syncthreads();
+  __threadfence_system();  // the pack kernel's stores (previous kernel) are visible before the flag
+  for (int i = threadIdx.x; i < np; i += blockDim.x) {
+    volatile unsigned long long *f = (volatile unsigned long long *)peer_win[peers[i]] + flag_index;
+    *f = s;
+  }
+}
+
+// wait until every listed peer has published at least this rank's current sequence number
+__global__ void __launch_bounds__(64) k_wait(const unsigned long long *seq, const unsigned long long *my_flags,
+                                             const int *peers, int np) {
+  const unsigned long long want = *seq;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) {
+    const volatile unsigned long long *f = my_flags + peers[i];
+    long long spins = 0;
+    while (*f < want) {
+      __nanosleep(64);
+      if (++spins > (1LL << 26))  // several seconds: a lost peer is an error, not a hang
+        __trap();
+    }
+  }
+  __threadfence_system();
 }
 
 static inline int cgrid(const CupCtx *c, int n) {
@@ -271,66 +330,277 @@ static int sum(const std::vector<int> &v) {
   return s;
 }
 
-// scratch of one level: faces out/in, restriction out/in (prolongation reuses them reversed)
-int comm_alloc_level_buffers(CupCtx *c) {
-  const size_t rb = (size_t)c->real_bytes;
+template <typename T>
+static int up(T **d, const std::vector<T> &h) {
+  *d = nullptr;
+  if (h.empty())
+    return CUP_OK;
+  CUP_CUDA(cudaMalloc((void **)d, h.size() * sizeof(T)));
+  CUP_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return CUP_OK;
+}
+
+static std::vector<int> peers_of(const std::vector<int> &cnt) {
+  std::vector<int> p;
+  for (size_t i = 0; i < cnt.size(); i++)
+    if (cnt[i])
+      p.push_back((int)i);
+  return p;
+}
+
+void comm_free_level_buffers(CupCtx *c) {
+  Comm *cm = (Comm *)c->comm;
+  if (cm && cm->p2p) {
+    // nobody may still be writing into a window that is about to disappear
+    cudaStreamSynchronize(c->stream);
+    double *d = c->d_scal + SCAL_N - 1;
+    g_nccl.AllReduce(d, d, 1, ncclDouble, ncclSum, cm->nccl, c->stream);
+    cudaStreamSynchronize(c->stream);
+    for (int p = 0; p < c->nranks; p++)
+      if (p != c->rank && cm->peer_win.size() > (size_t)p && cm->peer_win[p])
+        cudaIpcCloseMemHandle(cm->peer_win[p]);
+    cm->peer_win.clear();
+    cudaFree(cm->win);
+    cudaFree(cm->d_peer_win);
+    cudaFree(cm->d_seq);
+    cm->win = nullptr;
+    cm->d_peer_win = nullptr;
+    cm->d_seq = nullptr;
+    cm->p2p = false;
+    for (auto &v : c->lv)
+      v.d_frecv = v.d_rrecv = v.d_precv = nullptr;  // lived inside the window
+  }
   for (auto &v : c->lv) {
     cudaFree(v.d_fsend);
     cudaFree(v.d_frecv);
     cudaFree(v.d_rsend);
     cudaFree(v.d_rrecv);
-    v.d_fsend = v.d_frecv = v.d_rsend = v.d_rrecv = nullptr;
-    if (c->nranks == 1)
-      continue;
+    cudaFree(v.d_fptr0);
+    cudaFree(v.d_fptr1);
+    cudaFree(v.d_rptr);
+    cudaFree(v.d_pptr);
+    for (int k = 0; k < 3; k++) {
+      cudaFree(v.d_speers[k]);
+      cudaFree(v.d_rpeers[k]);
+      v.d_speers[k] = v.d_rpeers[k] = nullptr;
+    }
+    v.d_fsend = v.d_frecv = v.d_rsend = v.d_rrecv = v.d_precv = nullptr;
+    v.d_fptr0 = v.d_fptr1 = v.d_rptr = v.d_pptr = nullptr;
+  }
+}
+
+static bool want_p2p() {
+  const char *e = getenv("CUP_P2P");
+  return !(e && atoi(e) == 0);
+}
+
+// open every rank's receive window; false if CUDA IPC is not usable here
+static int open_windows(CupCtx *c, bool *ok) {
+  Comm *cm = (Comm *)c->comm;
+  const int R = c->nranks;
+  const size_t rb = (size_t)c->real_bytes;
+  *ok = false;
+  cm->flag_bytes = (((size_t)(c->top + 1) * 3 * R * sizeof(unsigned long long)) + 255) / 256 * 256;
+  const size_t bytes = cm->flag_bytes + (size_t)c->win_reals[c->rank] * rb + 256;
+  CUP_CUDA(cudaMalloc((void **)&cm->win, bytes));
+  CUP_CUDA(cudaMemset(cm->win, 0, bytes));
+  CUP_CUDA(cudaDeviceSynchronize());
+  // all-gather the IPC handles (and a usable flag) through NCCL
+  struct Msg {
+    cudaIpcMemHandle_t h;
+    int ok, pad[15];
+  };
+  Msg mine;
+  memset(&mine, 0, sizeof mine);
+  mine.ok = cudaIpcGetMemHandle(&mine.h, cm->win) == cudaSuccess;
+  cudaGetLastError();
+  char *d;
+  CUP_CUDA(cudaMalloc((void **)&d, sizeof(Msg) * (size_t)(R + 1)));
+  CUP_CUDA(cudaMemcpyAsync(d + sizeof(Msg) * R, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+  CUP_NCCL(g_nccl.AllGather(d + sizeof(Msg) * R, d, sizeof(Msg), ncclChar, cm->nccl, c->stream));
+  std::vector<Msg> all((size_t)R);
+  CUP_CUDA(cudaMemcpyAsync(all.data(), d, sizeof(Msg) * (size_t)R, cudaMemcpyDeviceToHost, c->stream));
+  CUP_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d);
+  bool good = true;
+  for (int p = 0; p < R; p++)
+    good = good && all[p].ok;
+  cm->peer_win.assign((size_t)R, nullptr);
+  cm->peer_win[c->rank] = cm->win;
+  int opened = 1;
+  if (good)
+    for (int p = 0; p < R; p++) {
+      if (p == c->rank)
+        continue;
+      void *ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, all[p].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        good = false;
+        break;
+      }
+      cm->peer_win[p] = (char *)ptr;
+      opened++;
+    }
+  // everyone must agree on the transport
+  double flag = good ? 0.0 : 1.0, *dflag = c->d_scal + SCAL_N - 1;
+  CUP_CUDA(cudaMemcpyAsync(dflag, &flag, sizeof flag, cudaMemcpyHostToDevice, c->stream));
+  CUP_NCCL(g_nccl.AllReduce(dflag, dflag, 1, ncclDouble, ncclSum, cm->nccl, c->stream));
+  CUP_CUDA(cudaMemcpyAsync(&flag, dflag, sizeof flag, cudaMemcpyDeviceToHost, c->stream));
+  CUP_CUDA(cudaStreamSynchronize(c->stream));
+  if (flag != 0.0) {
+    for (int p = 0; p < R; p++)
+      if (p != c->rank && cm->peer_win[p])
+        cudaIpcCloseMemHandle(cm->peer_win[p]);
+    cm->peer_win.clear();
+    cudaFree(cm->win);
+    cm->win = nullptr;
+    return CUP_OK;
+  }
+  CUP_TRY(up(&cm->d_peer_win, cm->peer_win));
+  CUP_CUDA(cudaMalloc((void **)&cm->d_seq, (size_t)(c->top + 1) * 3 * sizeof(unsigned long long)));
+  CUP_CUDA(cudaMemset(cm->d_seq, 0, (size_t)(c->top + 1) * 3 * sizeof(unsigned long long)));
+  *ok = true;
+  return CUP_OK;
+}
+
+// scratch of one level + destination pointers of every entry
+int comm_alloc_level_buffers(CupCtx *c) {
+  const size_t rb = (size_t)c->real_bytes;
+  comm_free_level_buffers(c);
+  if (c->nranks == 1)
+    return CUP_OK;
+  Comm *cm = (Comm *)c->comm;
+  bool p2p = false;
+  if (want_p2p())
+    CUP_TRY(open_windows(c, &p2p));
+  cm->p2p = p2p;
+  const int me = c->rank;
+  for (auto &v : c->lv) {
     const size_t ns = v.face_sslot.size(), nr = (size_t)v.nface_recv;
     const size_t cs = (size_t)sum(v.res_scnt), cr = (size_t)sum(v.res_rcnt);
-    if (ns)
-      CUP_CUDA(cudaMalloc(&v.d_fsend, ns * 64 * rb));
-    if (nr)
-      CUP_CUDA(cudaMalloc(&v.d_frecv, nr * 64 * rb));
-    if (cs)
-      CUP_CUDA(cudaMalloc(&v.d_rsend, cs * 128 * rb));
-    if (cr)
-      CUP_CUDA(cudaMalloc(&v.d_rrecv, cr * 128 * rb));
+    std::vector<char *> f0(ns), f1(ns), rp(cs), pp(cr);
+    if (p2p) {
+      char *base = cm->win + cm->flag_bytes;
+      v.d_frecv = base + (size_t)v.win_face[me] * rb;
+      v.d_rrecv = base + (size_t)v.win_res[me] * rb;
+      v.d_precv = base + (size_t)v.win_pro[me] * rb;
+      for (size_t e = 0; e < ns; e++) {
+        const int p = v.face_speer[e];
+        char *pb = cm->peer_win[p] + cm->flag_bytes + (size_t)v.win_face[p] * rb;
+        f0[e] = pb + (size_t)v.face_sidx[e] * 64 * rb;
+        f1[e] = f0[e] + (size_t)v.win_nrecv[p] * 64 * rb;
+      }
+      for (size_t q = 0; q < cs; q++) {
+        const int p = v.res_speer[q];
+        rp[q] = cm->peer_win[p] + cm->flag_bytes + ((size_t)v.win_res[p] + (size_t)v.res_sidx[q] * 128) * rb;
+      }
+      for (size_t e = 0; e < cr; e++) {
+        const int p = v.pro_speer[e];
+        pp[e] = cm->peer_win[p] + cm->flag_bytes + ((size_t)v.win_pro[p] + (size_t)v.pro_sidx[e] * 64) * rb;
+      }
+    } else {
+      if (ns)
+        CUP_CUDA(cudaMalloc(&v.d_fsend, ns * 64 * rb));
+      if (nr)
+        CUP_CUDA(cudaMalloc(&v.d_frecv, nr * 64 * rb));
+      if (cs)
+        CUP_CUDA(cudaMalloc(&v.d_rsend, cs * 128 * rb));
+      if (cr)
+        CUP_CUDA(cudaMalloc(&v.d_rrecv, cr * 128 * rb));
+      v.d_precv = v.d_rsend;  // prolongation arrives where the restriction was staged
+      for (size_t e = 0; e < ns; e++)
+        f0[e] = f1[e] = (char *)v.d_fsend + e * 64 * rb;
+      for (size_t q = 0; q < cs; q++)
+        rp[q] = (char *)v.d_rsend + q * 128 * rb;
+      for (size_t e = 0; e < cr; e++)
+        pp[e] = (char *)v.d_rrecv + e * 64 * rb;
+    }
+    CUP_TRY(up((char ***)&v.d_fptr0, f0));
+    CUP_TRY(up((char ***)&v.d_fptr1, f1));
+    CUP_TRY(up((char ***)&v.d_rptr, rp));
+    CUP_TRY(up((char ***)&v.d_pptr, pp));
+    v.speers[K_FACE] = peers_of(v.face_scnt);
+    v.rpeers[K_FACE] = peers_of(v.face_rcnt);
+    v.speers[K_RES] = peers_of(v.res_scnt);
+    v.rpeers[K_RES] = peers_of(v.res_rcnt);
+    v.speers[K_PRO] = v.rpeers[K_RES];  // corrections flow back along the same edges
+    v.rpeers[K_PRO] = v.speers[K_RES];
+    for (int k = 0; k < 3; k++) {
+      CUP_TRY(up(&v.d_speers[k], v.speers[k]));
+      CUP_TRY(up(&v.d_rpeers[k], v.rpeers[k]));
+    }
+    v.p2p = p2p;
+    v.rface_stride = p2p ? (long long)nr * 64 : 0;
+    v.d_seq = p2p ? cm->d_seq + (size_t)v.L * 3 : nullptr;
   }
   return CUP_OK;
 }
 
-void comm_free_level_buffers(CupCtx *c) {
-  for (auto &v : c->lv) {
-    cudaFree(v.d_fsend);
-    cudaFree(v.d_frecv);
-    cudaFree(v.d_rsend);
-    cudaFree(v.d_rrecv);
-    v.d_fsend = v.d_frecv = v.d_rsend = v.d_rrecv = nullptr;
-  }
+static int post(CupCtx *c, Level &v, int kind) {
+  Comm *cm = (Comm *)c->comm;
+  const size_t fidx = ((size_t)v.L * 3 + kind) * c->nranks + c->rank;
+  k_signal<<<1, 64, 0, c->stream>>>(cm->d_seq + (size_t)v.L * 3 + kind, cm->d_peer_win, v.d_speers[kind],
+                                    (int)v.speers[kind].size(), fidx);
+  c->launches++;
+  return CUP_OK;
 }
 
+static int wait(CupCtx *c, Level &v, int kind) {
+  Comm *cm = (Comm *)c->comm;
+  if (v.rpeers[kind].empty())
+    return CUP_OK;
+  const unsigned long long *flags = (const unsigned long long *)cm->win + ((size_t)v.L * 3 + kind) * c->nranks;
+  k_wait<<<1, 64, 0, c->stream>>>(cm->d_seq + (size_t)v.L * 3 + kind, flags, v.d_rpeers[kind],
+                                  (int)v.rpeers[kind].size());
+  c->launches++;
+  return CUP_OK;
+}
+
+static bool level_has_faces(const CupCtx *c, const Level &v) {
+  return c->nranks > 1 && (!v.face_sslot.empty() || v.nface_recv > 0);
+}
+
+// publish the ghost faces of `u` (this rank's boundary blocks of level v) to their consumers
 template <typename Real>
-int halo_exchange(CupCtx *c, Level &v, SlotVec<Real> u) {
-  if (c->nranks == 1)
+int halo_post(CupCtx *c, Level &v, SlotVec<Real> u) {
+  if (!level_has_faces(c, v))
     return CUP_OK;
   const int ns = (int)v.face_sslot.size();
-  if (ns == 0 && v.nface_recv == 0)
-    return CUP_OK;
   if (ns) {
-    k_pack_faces<Real><<<cgrid(c, ns), 64, 0, c->stream>>>(v.d_face_sslot, v.d_face_splane, ns, u, (Real *)v.d_fsend);
+    k_pack_faces<Real><<<cgrid(c, ns), 64, 0, c->stream>>>(v.d_face_sslot, v.d_face_splane, ns, u,
+                                                           (Real *const *)v.d_fptr0, (Real *const *)v.d_fptr1,
+                                                           (const unsigned long long *)v.d_seq);
     c->launches++;
   }
-  CUP_TRY(exchange(c, v.d_fsend, v.face_scnt, v.d_frecv, v.face_rcnt, 64 * sizeof(Real)));
+  if (v.p2p)
+    CUP_TRY(post(c, v, K_FACE));
+  else
+    CUP_TRY(exchange(c, v.d_fsend, v.face_scnt, v.d_frecv, v.face_rcnt, 64 * sizeof(Real)));
   CUP_CUDA(cudaGetLastError());
   return CUP_OK;
 }
 
-// after k_down wrote the children with remote parents into v.d_rsend
+// the faces posted last are complete in this rank's receive area
+int halo_wait(CupCtx *c, Level &v) {
+  if (!level_has_faces(c, v) || !v.p2p)
+    return CUP_OK;
+  return wait(c, v, K_FACE);
+}
+
+// after k_down stored the children with remote parents through v.d_rptr
 template <typename Real>
 int restrict_exchange(CupCtx *c, Level &v, SlotVec<Real> f, SlotVec<Real> u) {
   if (c->nranks == 1)
     return CUP_OK;
-  const int cr = sum(v.res_rcnt);
-  if (cr == 0 && sum(v.res_scnt) == 0)
+  const int cr = sum(v.res_rcnt), cs = sum(v.res_scnt);
+  if (cr == 0 && cs == 0)
     return CUP_OK;
-  CUP_TRY(exchange(c, v.d_rsend, v.res_scnt, v.d_rrecv, v.res_rcnt, 128 * sizeof(Real)));
+  if (v.p2p) {
+    CUP_TRY(post(c, v, K_RES));
+    CUP_TRY(wait(c, v, K_RES));
+  } else {
+    CUP_TRY(exchange(c, v.d_rsend, v.res_scnt, v.d_rrecv, v.res_rcnt, 128 * sizeof(Real)));
+  }
   if (cr) {
     k_put<Real><<<cgrid(c, cr), 64, 0, c->stream>>>(v.d_res_rslot, v.d_res_roct, cr, (const Real *)v.d_rrecv, f, u);
     c->launches++;
@@ -339,25 +609,30 @@ int restrict_exchange(CupCtx *c, Level &v, SlotVec<Real> f, SlotVec<Real> u) {
   return CUP_OK;
 }
 
-// before k_up: parents' owners send u_c - us to remote children; lands in v.d_rsend (as receive buffer)
+// before k_up: parents' owners send u_c - us to remote children; lands in v.d_precv
 template <typename Real>
 int prolong_exchange(CupCtx *c, Level &v, SlotVec<Real> u, SlotVec<Real> us) {
   if (c->nranks == 1)
     return CUP_OK;
-  const int cr = sum(v.res_rcnt);
-  if (cr == 0 && sum(v.res_scnt) == 0)
+  const int cr = sum(v.res_rcnt), cs = sum(v.res_scnt);
+  if (cr == 0 && cs == 0)
     return CUP_OK;
   if (cr) {
-    k_get<Real><<<cgrid(c, cr), 64, 0, c->stream>>>(v.d_res_rslot, v.d_res_roct, cr, u, us, (Real *)v.d_rrecv);
+    k_get<Real><<<cgrid(c, cr), 64, 0, c->stream>>>(v.d_res_rslot, v.d_res_roct, cr, u, us, (Real *const *)v.d_pptr);
     c->launches++;
   }
-  CUP_TRY(exchange(c, v.d_rrecv, v.res_rcnt, v.d_rsend, v.res_scnt, 64 * sizeof(Real)));
+  if (v.p2p) {
+    CUP_TRY(post(c, v, K_PRO));
+    CUP_TRY(wait(c, v, K_PRO));
+  } else {
+    CUP_TRY(exchange(c, v.d_rrecv, v.res_rcnt, v.d_precv, v.res_scnt, 64 * sizeof(Real)));
+  }
   CUP_CUDA(cudaGetLastError());
   return CUP_OK;
 }
 
-template int halo_exchange<double>(CupCtx *, Level &, SlotVec<double>);
-template int halo_exchange<float>(CupCtx *, Level &, SlotVec<float>);
+template int halo_post<double>(CupCtx *, Level &, SlotVec<double>);
+template int halo_post<float>(CupCtx *, Level &, SlotVec<float>);
 template int restrict_exchange<double>(CupCtx *, Level &, SlotVec<double>, SlotVec<double>);
 template int restrict_exchange<float>(CupCtx *, Level &, SlotVec<float>, SlotVec<float>);
 template int prolong_exchange<double>(CupCtx *, Level &, SlotVec<double>, SlotVec<double>);

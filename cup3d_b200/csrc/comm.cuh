@@ -10,8 +10,15 @@ int comm_allreduce(CupCtx *c, int first, int n);  // in-place sum of d_scal[firs
 int comm_alloc_level_buffers(CupCtx *c);
 void comm_free_level_buffers(CupCtx *c);
 void comm_free(CupCtx *c);
+// publish the ghost faces of u to the neighbours' owners / make sure the last posted ones arrived
 template <typename Real>
-int halo_exchange(CupCtx *c, Level &v, SlotVec<Real> u);  // faces of u -> v.d_frecv on the neighbours' owners
+int halo_post(CupCtx *c, Level &v, SlotVec<Real> u);
+int halo_wait(CupCtx *c, Level &v);
+template <typename Real>
+inline int halo_exchange(CupCtx *c, Level &v, SlotVec<Real> u) {
+  int rc = halo_post<Real>(c, v, u);
+  return rc != CUP_OK ? rc : halo_wait(c, v);
+}
 template <typename Real>
 int restrict_exchange(CupCtx *c, Level &v, SlotVec<Real> f, SlotVec<Real> u);
 template <typename Real>

@@ -62,8 +62,23 @@ struct Level {
   std::vector<int> res_scnt, res_rcnt;     // [nranks] children sent to / received from each peer
   std::vector<int> res_rslot, res_roct;    // received children: local parent slot, octant
   int *d_res_rslot = nullptr, *d_res_roct = nullptr;
+  // ---- one-sided (peer-to-peer) addressing: where each entry lands in the DESTINATION rank's
+  // receive window.  Derived from the global mesh, so no plan negotiation is needed.
+  std::vector<int> face_speer, face_sidx;  // [nsend] destination rank, entry number in its face area
+  std::vector<int> res_speer, res_sidx;    // [children with remote parent] dest rank, entry in its restrict area
+  std::vector<int> pro_speer, pro_sidx;    // [received children] dest rank (the child's owner), entry in its prolong area
+  std::vector<long long> win_face, win_res, win_pro;  // [nranks] offsets (Reals) of rank p's areas for this level
+  std::vector<int> win_nrecv;              // [nranks] faces rank p receives per exchange (parity stride / 64)
   // device scratch (comm.cu): faces out/in [n][64], restriction out/in [n][128]
   void *d_fsend = nullptr, *d_frecv = nullptr, *d_rsend = nullptr, *d_rrecv = nullptr;
+  void *d_precv = nullptr;                 // prolongation corrections for children with a remote parent
+  // per-entry destination pointers (local staging, or peer memory in one-sided mode)
+  void **d_fptr0 = nullptr, **d_fptr1 = nullptr, **d_rptr = nullptr, **d_pptr = nullptr;
+  std::vector<int> speers[3], rpeers[3];   // ranks signalled / awaited per kind (face, restrict, prolong)
+  int *d_speers[3] = {nullptr, nullptr, nullptr}, *d_rpeers[3] = {nullptr, nullptr, nullptr};
+  bool p2p = false;
+  long long rface_stride = 0;              // Reals between the two parities of the face area
+  void *d_seq = nullptr;                   // this level's sequence numbers (one-sided mode)
 };
 
 // pure-host result of the topology build (mesh.cpp); also what the CPU tests inspect
@@ -71,6 +86,7 @@ struct HostMesh {
   int nranks = 1, rank = 0, top = -1, level_max = 1;
   int bpd[3] = {1, 1, 1};
   long long nblk = 0, nslot = 0, gblocks = 0, gnslot = 0, pin_local = -1;
+  std::vector<long long> win_reals;  // [nranks] size of every rank's receive window, in Reals
   double gvol = 0;
   bool leaf_uniform = true;
   std::vector<CupBlk> blk;
@@ -95,6 +111,7 @@ struct CupCtx {
   double gvol = 0;                 // volume over all ranks (pois_solve's vol)
   long long pin_local = -1;        // local index of block (0,0,0) or -1 (pois_pin)
   int rank = 0, nranks = 1;
+  std::vector<long long> win_reals;  // [nranks] receive-window sizes (Reals)
   void *comm = nullptr;            // cup::Comm (comm.cu)
   int top = -1;
   int bpd[3] = {1, 1, 1};

@@ -240,6 +240,19 @@ int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner_
     v.h = h0 / (double)(1 << L);
     v.gnact = (long long)g.act.size();
     std::vector<Xent> rx, sx;  // face recv / send
+    // traffic matrices of this level over ALL ranks: fmat[s][d] faces, rmat[s][d] restricted children
+    std::vector<long long> fmat((size_t)nranks * nranks, 0), rmat((size_t)nranks * nranks, 0);
+    if (nranks > 1)
+      for (size_t k = 0; k < g.act.size(); k++) {
+        const int os = owner[g.act[k].gslot];
+        for (int f = 0; f < 6; f++) {
+          const int gn = g.nbr[k * 6 + f];
+          if (gn >= 0 && owner[gn] != os)
+            fmat[(size_t)os * nranks + owner[gn]]++;  // os sends its plane f to the neighbour's owner
+        }
+        if (L >= 1 && owner[g.pg[k]] != os)
+          rmat[(size_t)os * nranks + owner[g.pg[k]]]++;
+      }
     for (size_t k = 0; k < g.act.size(); k++) {
       const int gs = g.act[k].gslot;
       if (owner[gs] != rank)
@@ -282,9 +295,21 @@ int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner_
     count_by_peer(sx, nranks, v.face_scnt);
     for (size_t i = 0; i < rx.size(); i++)
       v.nbr[(size_t)rx[i].ref] = NBR_REMOTE0 - (int)i;
-    for (const Xent &e : sx) {
-      v.face_sslot.push_back(e.ref);
-      v.face_splane.push_back(e.plane);
+    {
+      int prev = -1, j = 0;
+      for (const Xent &e : sx) {
+        v.face_sslot.push_back(e.ref);
+        v.face_splane.push_back(e.plane);
+        if (e.peer != prev) {
+          prev = e.peer;
+          j = 0;
+        }
+        long long base = 0;  // entries of lower ranks come first in the destination's face area
+        for (int q = 0; q < rank; q++)
+          base += fmat[(size_t)q * nranks + e.peer];
+        v.face_speer.push_back(e.peer);
+        v.face_sidx.push_back((int)(base + j++));
+      }
     }
     v.nface_recv = (int)rx.size();
     // restrict / prolong plans (L >= 1)
@@ -312,11 +337,38 @@ int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner_
       std::sort(rr.begin(), rr.end());
       count_by_peer(rs, nranks, v.res_scnt);
       count_by_peer(rr, nranks, v.res_rcnt);
-      for (size_t i = 0; i < rs.size(); i++)
-        v.pslot[(size_t)rs[i].ref] = NBR_REMOTE0 - (int)i;
-      for (const Xent &e : rr) {
-        v.res_rslot.push_back(e.ref);
-        v.res_roct.push_back(e.plane);
+      {
+        int prev = -1, j = 0;
+        for (size_t i = 0; i < rs.size(); i++) {
+          v.pslot[(size_t)rs[i].ref] = NBR_REMOTE0 - (int)i;
+          if (rs[i].peer != prev) {
+            prev = rs[i].peer;
+            j = 0;
+          }
+          long long base = 0;
+          for (int q = 0; q < rank; q++)
+            base += rmat[(size_t)q * nranks + rs[i].peer];
+          v.res_speer.push_back(rs[i].peer);
+          v.res_sidx.push_back((int)(base + j++));
+        }
+      }
+      {
+        int prev = -1, j = 0;
+        for (const Xent &e : rr) {
+          v.res_rslot.push_back(e.ref);
+          v.res_roct.push_back(e.plane);
+          if (e.peer != prev) {
+            prev = e.peer;
+            j = 0;
+          }
+          // the child's owner s keeps its remote-parent children ordered by (parent owner, position):
+          // ours start after those it sends to lower ranks
+          long long base = 0;
+          for (int d = 0; d < rank; d++)
+            base += rmat[(size_t)e.peer * nranks + d];
+          v.pro_speer.push_back(e.peer);
+          v.pro_sidx.push_back((int)(base + j++));
+        }
       }
     } else {
       v.res_scnt.assign(nranks, 0);
@@ -326,6 +378,17 @@ int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner_
     for (size_t k = 0; k < v.act.size(); k++)
       if (v.act[k] >= m->nblk)
         v.par.push_back((int)k);
+    // receive-window bookkeeping of every rank for this level (sizes in entries)
+    v.win_nrecv.assign(nranks, 0);
+    v.win_face.assign(nranks, 0);  // reused below as: res entries, pro entries (temporarily)
+    v.win_res.assign(nranks, 0);
+    v.win_pro.assign(nranks, 0);
+    for (int p = 0; p < nranks; p++)
+      for (int q = 0; q < nranks; q++) {
+        v.win_nrecv[p] += (int)fmat[(size_t)q * nranks + p];
+        v.win_res[p] += rmat[(size_t)q * nranks + p];   // children received by p
+        v.win_pro[p] += rmat[(size_t)p * nranks + q];   // corrections received by p
+      }
     // interior / boundary split for comm-compute overlap
     for (size_t k = 0; k < v.act.size(); k++) {
       bool rem = false;
@@ -333,6 +396,22 @@ int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner_
         rem |= v.nbr[k * 6 + f] <= NBR_REMOTE0;
       (rem ? v.bnd : v.inner).push_back((int)k);
     }
+  }
+  // lay out every rank's receive window: per level [faces parity 0][faces parity 1][restrict][prolong]
+  m->win_reals.assign(nranks, 0);
+  for (int p = 0; p < nranks; p++) {
+    long long off = 0;
+    for (int L = 0; L <= m->top; L++) {
+      Level &v = m->lv[L];
+      const long long nres = v.win_res[p], npro = v.win_pro[p];
+      v.win_face[p] = off;
+      off += 2LL * v.win_nrecv[p] * 64;
+      v.win_res[p] = off;
+      off += nres * 128;
+      v.win_pro[p] = off;
+      off += npro * 64;
+    }
+    m->win_reals[p] = off;
   }
   return CUP_OK;
 }
@@ -379,6 +458,7 @@ int build_mesh(CupCtx *c, const CupBlk *gblk, long long G, const int *owner, con
   }
   c->blk.swap(m.blk);
   c->lv.swap(m.lv);
+  c->win_reals.swap(m.win_reals);
   c->nblk = m.nblk;
   c->nslot = m.nslot;
   c->gblocks = m.gblocks;

@@ -37,7 +37,19 @@ struct LevelView {
   const int *nbr;  // [nact][6]
   int nact;
   const void *rface;  // faces received from other ranks: [nface][64] Reals, plane order (a, c)
+  // one-sided transport: the face area is double buffered by the parity of the level's
+  // exchange counter (device memory, so a captured CUDA graph stays valid on replay)
+  const unsigned long long *seq;
+  long long rface_stride;  // Reals between the two copies
 };
+
+template <typename Real>
+__device__ __forceinline__ const Real *rface_of(const LevelView &lv) {
+  const Real *p = (const Real *)lv.rface;
+  if (lv.seq && (*lv.seq & 1))
+    p += lv.rface_stride;
+  return p;
+}
 
 // 8-point DST-I matrix S[j][k] = sqrt(2/9) sin(pi (j+1)(k+1)/9), k < 4 only:
 // S[j][7-k] = (-1)^j S[j][k]  (pois_init, main.c:4322-4329).

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_smooth(LevelView lv, SlotVec<Real
 #pragma unroll
       for (int k = 0; k < 8; k++)
         uu[k] = ub[k * 64 + t];
-      load_halo<Real>(usrc, ub, lv.nbr + (size_t)b * 6, t, halo, (const Real *)lv.rface);
+      load_halo<Real>(usrc, ub, lv.nbr + (size_t)b * 6, t, halo, rface_of<Real>(lv));
       __syncthreads();
 #pragma unroll
       for (int k = 0; k < 8; k++)
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_smooth(LevelView lv, SlotVec<Real
 template <typename Real>
 __global__ void __launch_bounds__(TPB) k_down(LevelView lv, const int *__restrict__ pslot,
                                               const int *__restrict__ oct, SlotVec<Real> u, SlotVec<Real> f, Real h,
-                                              Real *__restrict__ rsend) {
+                                              Real *const *__restrict__ rptr) {
   __shared__ Real tu[512];
   __shared__ Real tr[512];
   __shared__ Real halo[6][64];
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(TPB) k_down(LevelView lv, const int *__restric
       ff[k] = fb[k * 64 + t];
       tu[k * 64 + t] = uu[k];
     }
-    load_halo<Real>(u, ub, lv.nbr + (size_t)b * 6, t, halo, (const Real *)lv.rface);
+    load_halo<Real>(u, ub, lv.nbr + (size_t)b * 6, t, halo, rface_of<Real>(lv));
     __syncthreads();
     lap_line<Real>(tu, halo, uu, x, y, t, h, tt);
 #pragma unroll
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(TPB) k_down(LevelView lv, const int *__restric
         f.at(ps)[pidx] = sr;
         u.at(ps)[pidx] = (Real)0.125 * su;
       } else {  // parent lives on another rank: 64 r + 64 u (MG_M layout, main.c:4750)
-        Real *q = rsend + (size_t)(kRemote0 - ps) * 128;
+        Real *q = rptr[kRemote0 - ps];  // staging buffer or the owner's receive window (NVLink)
         q[t] = sr;
         q[64 + t] = (Real)0.125 * su;
       }
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(TPB) k_apply(LevelView lv, const int *__restri
       uu[k] = ub[k * 64 + t];
       tu[k * 64 + t] = uu[k];
     }
-    load_halo<Real>(u, ub, lv.nbr + (size_t)b * 6, t, halo, (const Real *)lv.rface);
+    load_halo<Real>(u, ub, lv.nbr + (size_t)b * 6, t, halo, rface_of<Real>(lv));
     __syncthreads();
     lap_line<Real>(tu, halo, uu, x, y, t, h, tt);
     Real *ob = out.at(slot);
@@ -304,7 +304,10 @@ struct Arr {
   SlotVec<Real> u0, u1, f, us;
 };
 
-inline LevelView view(const Level &v) { return LevelView{v.d_act, v.d_nbr, (int)v.act.size(), v.d_frecv}; }
+inline LevelView view(const Level &v) {
+  return LevelView{v.d_act, v.d_nbr, (int)v.act.size(), v.d_frecv, (const unsigned long long *)v.d_seq,
+                   v.rface_stride};
+}
 
 inline int grid_for(const CupCtx *c, long long nwork, int per_sm) {
   long long g = (long long)c->num_sms * per_sm;
@@ -368,35 +371,31 @@ int smooth_level(CupCtx *c, Level &v, int n, Arr<Real> &a, bool first_is_zero, c
     SlotVec<Real> &src = (it & 1) ? a.u1 : a.u0;
     SlotVec<Real> &dst = (it & 1) ? a.u0 : a.u1;
     const bool zero = (it == 0 && first_is_zero);
-    // comm/compute overlap: blocks without a remote neighbour are swept while the faces of
-    // the others are packed and exchanged on a second stream
-    if (!zero && c->nranks > 1 && smooth_use_tma() && v.inner.size() >= 512 && !v.bnd.empty()) {
-      CUP_CUDA(cudaEventRecord(c->ev_ready, c->stream));
-      CUP_CUDA(cudaStreamWaitEvent(c->cstream, c->ev_ready, 0));
-      std::swap(c->stream, c->cstream);
-      int rc = halo_exchange<Real>(c, v, src);
-      cudaError_t e = cudaEventRecord(c->ev_halo, c->stream);
-      std::swap(c->stream, c->cstream);
-      CUP_TRY(rc);
-      CUP_CUDA(e);
-      CUP_TRY(launch_smooth0<Real>(c, grid_for(c, (long long)v.inner.size(), 12), view(v), src, dst, a.f, h, invh, om,
-                                   fmean, v.d_inner, (int)v.inner.size()));
-      CUP_CUDA(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+    // Every sweep CONSUMES the ghost faces of `src` posted by whoever produced it and POSTS the
+    // faces of `dst` as soon as its boundary blocks are done; blocks without a remote neighbour
+    // are swept while those faces travel (comm/compute overlap on one stream).
+    if (!zero)
+      CUP_TRY(halo_wait(c, v));
+    if (!zero && c->nranks > 1 && smooth_use_tma() && v.inner.size() >= 256 && !v.bnd.empty()) {
       CUP_TRY(launch_smooth0<Real>(c, grid_for(c, (long long)v.bnd.size(), 12), view(v), src, dst, a.f, h, invh, om,
                                    fmean, v.d_bnd, (int)v.bnd.size()));
+      CUP_TRY(halo_post<Real>(c, v, dst));
+      CUP_TRY(launch_smooth0<Real>(c, grid_for(c, (long long)v.inner.size(), 12), view(v), src, dst, a.f, h, invh, om,
+                                   fmean, v.d_inner, (int)v.inner.size()));
       c->launches += 2;
       continue;
     }
-    if (!zero)
-      CUP_TRY(halo_exchange<Real>(c, v, src));
-    if (v.act.empty())
+    if (v.act.empty()) {
+      CUP_TRY(halo_post<Real>(c, v, dst));
       continue;
+    }
     if (it == 0 && first_is_zero)
       k_smooth<Real, 1, 8><<<grid, TPB, 0, c->stream>>>(view(v), src, dst, a.f, (const Real *)c->d_W, h, invh, om,
                                                          fmean);
     else
       CUP_TRY(launch_smooth0<Real>(c, grid, view(v), src, dst, a.f, h, invh, om, fmean));
     c->launches++;
+    CUP_TRY(halo_post<Real>(c, v, dst));
   }
   if (n & 1) {
     set_error("odd smoothing count %d not supported (ping-pong)", n);
@@ -427,16 +426,17 @@ int vcycle_t(CupCtx *c, const Real *d_in, Real *d_out) {
     // u == 0 on entry only at the finest level (vec_zero, :4834); coarser
     // levels start from the restricted u (FAS).
     CUP_TRY(smooth_level<Real>(c, v, MG_PRE, a, L == top, nullptr));
-    CUP_TRY(halo_exchange<Real>(c, v, a.u0));
+    CUP_TRY(halo_wait(c, v));  // faces of u0 were posted by the last sweep
     if (!v.act.empty()) {
       const int grid = grid_for(c, (long long)v.act.size(), 12);
       k_down<Real><<<grid, TPB, 0, c->stream>>>(view(v), v.d_pslot, v.d_oct, a.u0, a.f, (Real)v.h,
-                                                 (Real *)v.d_rsend);
+                                                 (Real *const *)v.d_rptr);
       c->launches++;
     }
     CUP_TRY(restrict_exchange<Real>(c, v, a.f, a.u0));
     Level &w = c->lv[L - 1];
-    CUP_TRY(halo_exchange<Real>(c, w, a.u0));
+    CUP_TRY(halo_post<Real>(c, w, a.u0));  // restricted u: consumed by tau and by the first sweep of level L-1
+    CUP_TRY(halo_wait(c, w));
     if (!w.par.empty()) {
       const int gridw = grid_for(c, (long long)w.par.size(), 12);
       k_apply<Real, true><<<gridw, TPB, 0, c->stream>>>(view(w), w.d_par, (int)w.par.size(), a.u0, a.f, a.us,
@@ -464,9 +464,10 @@ int vcycle_t(CupCtx *c, const Real *d_in, Real *d_out) {
     CUP_TRY(prolong_exchange<Real>(c, v, a.u0, a.us));
     if (!v.act.empty()) {
       const int grid = grid_for(c, (long long)v.act.size(), 16);
-      k_up<Real><<<grid, TPB, 0, c->stream>>>(view(v), v.d_pslot, v.d_oct, a.u0, a.us, (const Real *)v.d_rsend);
+      k_up<Real><<<grid, TPB, 0, c->stream>>>(view(v), v.d_pslot, v.d_oct, a.u0, a.us, (const Real *)v.d_precv);
       c->launches++;
     }
+    CUP_TRY(halo_post<Real>(c, v, a.u0));
     CUP_TRY(smooth_level<Real>(c, v, MG_POST, a, false, nullptr));
   }
   CUP_CUDA(cudaGetLastError());

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(TPB, 12)
     for (int f = 0; f < 6; f++)
       wall |= ((nb[f] == kWall) << f) | ((nb[f] <= kRemote0) << (8 + f));
     s_wall = wall;
-    const Real *rf = (const Real *)lv.rface;
+    const Real *rf = rface_of<Real>(lv);
     // x faces from a local block arrive as 16-byte rows (NCOL values each), received ones compact
     uint32_t bytes = TmaCfg<Real>::BYTES;
     if (nb[0] <= kRemote0) bytes -= 64 * (NCOL - 1) * (uint32_t)sizeof(Real);

@@ -340,7 +340,7 @@ int need_uniform(CupCtx *c, const char *what) {
 template <typename Real>
 int stencil_t(CupCtx *c, CupStencilId id, const int *d_sub, long long nsub) {
   const Level &v = *leaf_level(c);
-  LevelView lv{v.d_act, v.d_nbr, (int)v.act.size(), v.d_frecv};
+  LevelView lv{v.d_act, v.d_nbr, (int)v.act.size(), v.d_frecv, (const unsigned long long *)v.d_seq, v.rface_stride};
   if (c->nranks > 1 && id != CUP_ST_LHS && id != CUP_ST_MG) {
     set_error("stencil sweeps other than LHS/MG are single-rank in this build");
     return CUP_ERR_UNSUPPORTED;
