@@ -14,6 +14,8 @@
 #include "comm.cuh"
 #include "cup_internal.h"
 #include "mg_device.cuh"
+#include "smooth_tma.cuh"
+#include <map>
 
 namespace cup {
 
@@ -375,6 +377,11 @@ void comm_free_level_buffers(CupCtx *c) {
     cudaFree(v.d_frecv);
     cudaFree(v.d_rsend);
     cudaFree(v.d_rrecv);
+    cudaFree(v.d_order);
+    cudaFree(v.d_bsend);
+    cudaFree(v.d_counters);
+    v.d_order = v.d_bsend = nullptr;
+    v.d_counters = nullptr;
     cudaFree(v.d_fptr0);
     cudaFree(v.d_fptr1);
     cudaFree(v.d_rptr);
@@ -529,6 +536,22 @@ int comm_alloc_level_buffers(CupCtx *c) {
       CUP_TRY(up(&v.d_speers[k], v.speers[k]));
       CUP_TRY(up(&v.d_rpeers[k], v.rpeers[k]));
     }
+    if (p2p && !v.bnd.empty()) {
+      std::map<std::pair<int, int>, int> ent;
+      for (size_t e = 0; e < ns; e++)
+        ent[{v.face_sslot[e], v.face_splane[e]}] = (int)e;
+      v.bsend.assign(v.act.size() * 6, -1);
+      for (size_t k = 0; k < v.act.size(); k++)
+        for (int f = 0; f < 6; f++)
+          if (v.nbr[k * 6 + f] <= NBR_REMOTE0)
+            v.bsend[k * 6 + f] = ent.at({v.act[k], f});
+      v.order = v.bnd;
+      v.order.insert(v.order.end(), v.inner.begin(), v.inner.end());
+      CUP_TRY(up(&v.d_bsend, v.bsend));
+      CUP_TRY(up(&v.d_order, v.order));
+      CUP_CUDA(cudaMalloc((void **)&v.d_counters, 2 * sizeof(unsigned int)));
+      CUP_CUDA(cudaMemset(v.d_counters, 0, 2 * sizeof(unsigned int)));
+    }
     v.p2p = p2p;
     v.rface_stride = p2p ? (long long)nr * 64 : 0;
     v.d_seq = p2p ? cm->d_seq + (size_t)v.L * 3 : nullptr;
@@ -554,6 +577,26 @@ static int wait(CupCtx *c, Level &v, int kind) {
                                   (int)v.rpeers[kind].size());
   c->launches++;
   return CUP_OK;
+}
+
+bool comm_fused_desc(CupCtx *c, Level &v, FusedComm *out) {
+  Comm *cm = (Comm *)c->comm;
+  if (!cm || !v.p2p || v.bnd.empty() || !v.d_order)
+    return false;
+  out->bsend = v.d_bsend;
+  out->fptr0 = v.d_fptr0;
+  out->fptr1 = v.d_fptr1;
+  out->seq = cm->d_seq + (size_t)v.L * 3 + K_FACE;
+  out->my_flags = (const unsigned long long *)cm->win + ((size_t)v.L * 3 + K_FACE) * c->nranks;
+  out->rpeers = v.d_rpeers[K_FACE];
+  out->nrp = (int)v.rpeers[K_FACE].size();
+  out->peer_win = cm->d_peer_win;
+  out->speers = v.d_speers[K_FACE];
+  out->nsp = (int)v.speers[K_FACE].size();
+  out->flag_index = ((size_t)v.L * 3 + K_FACE) * c->nranks + c->rank;
+  out->counters = v.d_counters;
+  out->nbnd = (int)v.bnd.size();
+  return true;
 }
 
 static bool level_has_faces(const CupCtx *c, const Level &v) {

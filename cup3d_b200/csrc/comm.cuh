@@ -8,6 +8,9 @@ namespace cup {
 int comm_gather_blocks(CupCtx *c, const CupBlk *blk, long long n, std::vector<CupBlk> &gblk, std::vector<int> &owner);
 int comm_allreduce(CupCtx *c, int first, int n);  // in-place sum of d_scal[first..first+n) over ranks
 int comm_alloc_level_buffers(CupCtx *c);
+struct FusedComm;
+// descriptor of the fused sweep+exchange for level v; false when the level cannot use it
+bool comm_fused_desc(CupCtx *c, Level &v, FusedComm *out);
 void comm_free_level_buffers(CupCtx *c);
 void comm_free(CupCtx *c);
 // publish the ghost faces of u to the neighbours' owners / make sure the last posted ones arrived

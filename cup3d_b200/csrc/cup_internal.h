@@ -79,6 +79,10 @@ struct Level {
   bool p2p = false;
   long long rface_stride = 0;              // Reals between the two parities of the face area
   void *d_seq = nullptr;                   // this level's sequence numbers (one-sided mode)
+  // fused sweep + exchange (smooth_tma.cu): work order = boundary blocks first, then interior
+  std::vector<int> order, bsend;           // [nact] act indices; [nact][6] send entry of (block, plane) or -1
+  int *d_order = nullptr, *d_bsend = nullptr;
+  unsigned int *d_counters = nullptr;      // [2] retired boundary blocks / CTAs
 };
 
 // pure-host result of the topology build (mesh.cpp); also what the CPU tests inspect

@@ -328,6 +328,15 @@ static bool smooth_use_tma() {
   return v == 1;
 }
 
+static bool fused_ok() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("CUP_FUSED");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static int smooth_minb() {
   static int v = -1;
   if (v < 0) {
@@ -339,11 +348,12 @@ static int smooth_minb() {
 
 template <typename Real>
 int launch_smooth0(CupCtx *c, int grid, LevelView lv, SlotVec<Real> src, SlotVec<Real> dst, SlotVec<Real> f, Real h,
-                   Real invh, Real om, const double *fmean, const int *sub = nullptr, int nsub = -1) {
+                   Real invh, Real om, const double *fmean, const int *sub = nullptr, int nsub = -1,
+                   const FusedComm *fused = nullptr) {
   const Real *W = (const Real *)c->d_W;
   if (smooth_use_tma())
     return smooth_tma_launch<Real>(c, c->stream, grid, lv, sub, nsub < 0 ? lv.nact : nsub, src, dst, f, h, invh, om,
-                                   fmean);
+                                   fmean, fused);
   if (sub) {
     set_error("block sub-lists need the TMA smoother");
     return CUP_ERR_UNSUPPORTED;
@@ -374,6 +384,15 @@ int smooth_level(CupCtx *c, Level &v, int n, Arr<Real> &a, bool first_is_zero, c
     // Every sweep CONSUMES the ghost faces of `src` posted by whoever produced it and POSTS the
     // faces of `dst` as soon as its boundary blocks are done; blocks without a remote neighbour
     // are swept while those faces travel (comm/compute overlap on one stream).
+    FusedComm fc;
+    if (!zero && smooth_use_tma() && fused_ok() && comm_fused_desc(c, v, &fc)) {
+      // ONE kernel: wait for the peers' faces, sweep boundary blocks, push their new faces over
+      // NVLink and publish them, sweep the interior meanwhile
+      CUP_TRY(launch_smooth0<Real>(c, grid, view(v), src, dst, a.f, h, invh, om, fmean, v.d_order,
+                                   (int)v.act.size(), &fc));
+      c->launches++;
+      continue;
+    }
     if (!zero)
       CUP_TRY(halo_wait(c, v));
     if (!zero && c->nranks > 1 && smooth_use_tma() && v.inner.size() >= 256 && !v.bnd.empty()) {

@@ -20,6 +20,7 @@
 
 #include "cup_internal.h"
 #include "mg_device.cuh"
+#include "smooth_tma.cuh"
 #include "tma.cuh"
 
 namespace cup {
@@ -30,9 +31,9 @@ struct TmaCfg {
   static constexpr uint32_t BYTES = (512 * 2 + 64 * 2 + 64 * 2 + 64 * NCOL * 2) * (uint32_t)sizeof(Real);
 };
 
-template <typename Real>
+template <typename Real, bool COMM>
 __global__ void __launch_bounds__(TPB, 12)
-    k_smooth_tma(LevelView lv, const int *__restrict__ sub, int nsub, SlotVec<Real> usrc, SlotVec<Real> udst, SlotVec<Real> fvec, const Real *__restrict__ Wl,
+    k_smooth_tma(LevelView lv, const int *__restrict__ sub, int nsub, FusedComm fc, SlotVec<Real> usrc, SlotVec<Real> udst, SlotVec<Real> fvec, const Real *__restrict__ Wl,
                  Real h, Real invh, Real omega, const double *__restrict__ fmean,
                  const __grid_constant__ CUtensorMap mx_leaf, const __grid_constant__ CUtensorMap my_leaf,
                  const __grid_constant__ CUtensorMap mx_extra, const __grid_constant__ CUtensorMap my_extra) {
@@ -54,6 +55,16 @@ __global__ void __launch_bounds__(TPB, 12)
   for (int k = 0; k < 8; k++)
     w[k] = Wl[k * 64 + t];
   const Real q0 = fmean ? (Real)(*fmean) : (Real)0;
+  // sequence number of the faces this sweep CONSUMES (its own faces go out as seq0 + 1)
+  unsigned long long seq0 = 0;
+  const Real *rf = (const Real *)lv.rface;
+  if (COMM) {
+    seq0 = *(volatile const unsigned long long *)fc.seq;
+    if (seq0 & 1)
+      rf += lv.rface_stride;
+  } else {
+    rf = rface_of<Real>(lv);
+  }
 
   // thread 0 is the TMA producer: stage one block (its u, f and six ghost faces)
   auto issue = [&](int slot, const int (&nb)[6]) {
@@ -62,7 +73,6 @@ __global__ void __launch_bounds__(TPB, 12)
     for (int f = 0; f < 6; f++)
       wall |= ((nb[f] == kWall) << f) | ((nb[f] <= kRemote0) << (8 + f));
     s_wall = wall;
-    const Real *rf = rface_of<Real>(lv);
     // x faces from a local block arrive as 16-byte rows (NCOL values each), received ones compact
     uint32_t bytes = TmaCfg<Real>::BYTES;
     if (nb[0] <= kRemote0) bytes -= 64 * (NCOL - 1) * (uint32_t)sizeof(Real);
@@ -104,6 +114,19 @@ __global__ void __launch_bounds__(TPB, 12)
   __syncthreads();
   // work items: sub[i] (indices into act[]) or 0..nsub-1
   int i = blockIdx.x;
+  if (COMM && t == 0 && i < fc.nbnd) {
+    // this CTA starts with blocks that read received faces: wait until every peer has published seq0
+    for (int p = 0; p < fc.nrp; p++) {
+      const volatile unsigned long long *f = fc.my_flags + fc.rpeers[p];
+      long long spins = 0;
+      while (*f < seq0) {
+        __nanosleep(32);
+        if (++spins > (1LL << 26))
+          __trap();
+      }
+    }
+    __threadfence_system();
+  }
   if (t == 0 && i < nsub) {
     const int b0 = sub ? sub[i] : i;
     int nb[6];
@@ -210,9 +233,73 @@ __global__ void __launch_bounds__(TPB, 12)
     dst8<Real>(v);
     Real *ob = udst.at(slot);
 #pragma unroll
-    for (int k = 0; k < 8; k++)
-      ob[k * 64 + t] = uu[k] + omega * (v[k] - uu[k]);
+    for (int k = 0; k < 8; k++) {
+      v[k] = uu[k] + omega * (v[k] - uu[k]);
+      ob[k * 64 + t] = v[k];
+    }
+    if (COMM && i < fc.nbnd) {
+      // push the new boundary planes to the neighbours' owners (plane order as load_halo expects)
+      void *const *fp = ((seq0 + 1) & 1) ? fc.fptr1 : fc.fptr0;
+      const int *bs = fc.bsend + (size_t)b * 6;
+      const int e0 = bs[0], e1 = bs[1], e2 = bs[2], e3 = bs[3], e4 = bs[4], e5 = bs[5];
+      if (e4 >= 0)
+        ((Real *)fp[e4])[t] = v[0];
+      if (e5 >= 0)
+        ((Real *)fp[e5])[t] = v[7];
+      if (e2 >= 0 && y == 0) {
+        Real *d = (Real *)fp[e2];
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          d[k * 8 + x] = v[k];
+      }
+      if (e3 >= 0 && y == 7) {
+        Real *d = (Real *)fp[e3];
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          d[k * 8 + x] = v[k];
+      }
+      if (e0 >= 0 && x == 0) {
+        Real *d = (Real *)fp[e0];
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          d[k * 8 + y] = v[k];
+      }
+      if (e1 >= 0 && x == 7) {
+        Real *d = (Real *)fp[e1];
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          d[k * 8 + y] = v[k];
+      }
+      if (i + G >= fc.nbnd) {
+        // that was this CTA's last boundary block: retire them; whoever retires the last one of
+        // the whole grid publishes the new sequence number to the peers
+        __threadfence_system();
+        __syncthreads();
+        if (t == 0) {
+          const unsigned int mine = (unsigned int)((fc.nbnd - 1 - (int)blockIdx.x) / G + 1);
+          const unsigned int old = atomicAdd(&fc.counters[0], mine);
+          if (old + mine == (unsigned int)fc.nbnd) {
+            __threadfence_system();
+            for (int p = 0; p < fc.nsp; p++) {
+              volatile unsigned long long *f = (volatile unsigned long long *)fc.peer_win[fc.speers[p]] + fc.flag_index;
+              *f = seq0 + 1;
+            }
+          }
+        }
+      }
+    }
     // next iteration's first ex write happens after its own __syncthreads: no extra barrier
+  }
+  if (COMM && t == 0) {
+    // the last CTA to leave advances this rank's own sequence number and re-arms the counters
+    __threadfence();
+    const unsigned int old = atomicAdd(&fc.counters[1], 1u);
+    if (old == (unsigned int)G - 1) {
+      fc.counters[0] = 0;
+      fc.counters[1] = 0;
+      *fc.seq = seq0 + 1;
+      __threadfence();
+    }
   }
 }
 
@@ -289,7 +376,7 @@ void free_tma_cache(CupCtx *c) {
 template <typename Real>
 int smooth_tma_launch(CupCtx *c, cudaStream_t stream, int grid, LevelView lv, const int *sub, int nsub,
                       SlotVec<Real> src, SlotVec<Real> dst, SlotVec<Real> f, Real h,
-                      Real invh, Real om, const double *fmean) {
+                      Real invh, Real om, const double *fmean, const FusedComm *fused) {
   CUtensorMap mxl, myl, mxe, mye;
   const long long nleaf = c->nblk, nx = c->nslot - c->nblk + 1;
   // a part that holds no blocks of this vector still needs a valid (unused) descriptor
@@ -299,14 +386,20 @@ int smooth_tma_launch(CupCtx *c, cudaStream_t stream, int grid, LevelView lv, co
   CUP_TRY(get_map(c, lb, src.leaf ? nleaf : 1, 1, &myl));
   CUP_TRY(get_map(c, eb, src.extra ? nx : 1, 0, &mxe));
   CUP_TRY(get_map(c, eb, src.extra ? nx : 1, 1, &mye));
-  k_smooth_tma<Real><<<grid, TPB, 0, stream>>>(lv, sub, nsub, src, dst, f, (const Real *)c->d_W, h, invh, om, fmean, mxl, myl,
-                                                   mxe, mye);
+  if (fused)
+    k_smooth_tma<Real, true><<<grid, TPB, 0, stream>>>(lv, sub, nsub, *fused, src, dst, f, (const Real *)c->d_W, h,
+                                                        invh, om, fmean, mxl, myl, mxe, mye);
+  else
+    k_smooth_tma<Real, false><<<grid, TPB, 0, stream>>>(lv, sub, nsub, FusedComm{}, src, dst, f,
+                                                         (const Real *)c->d_W, h, invh, om, fmean, mxl, myl, mxe, mye);
   return CUP_OK;
 }
 
-template int smooth_tma_launch<double>(CupCtx *, cudaStream_t, int, LevelView, const int *, int, SlotVec<double>, SlotVec<double>, SlotVec<double>,
-                                       double, double, double, const double *);
-template int smooth_tma_launch<float>(CupCtx *, cudaStream_t, int, LevelView, const int *, int, SlotVec<float>, SlotVec<float>, SlotVec<float>, float,
-                                      float, float, const double *);
+template int smooth_tma_launch<double>(CupCtx *, cudaStream_t, int, LevelView, const int *, int, SlotVec<double>,
+                                       SlotVec<double>, SlotVec<double>, double, double, double, const double *,
+                                       const FusedComm *);
+template int smooth_tma_launch<float>(CupCtx *, cudaStream_t, int, LevelView, const int *, int, SlotVec<float>,
+                                      SlotVec<float>, SlotVec<float>, float, float, float, const double *,
+                                      const FusedComm *);
 
 }  // namespace cup
