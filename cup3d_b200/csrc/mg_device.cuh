@@ -30,6 +30,9 @@ struct SlotVec {
   __device__ __forceinline__ Real *at(int slot) const {
     return slot < nleaf ? leaf + (size_t)slot * 512 : extra + (size_t)(slot - nleaf) * 512;
   }
+  Real *at_host(int slot) const {  // same mapping, evaluated on the host
+    return slot < nleaf ? leaf + (size_t)slot * 512 : extra + (size_t)(slot - nleaf) * 512;
+  }
 };
 
 struct LevelView {

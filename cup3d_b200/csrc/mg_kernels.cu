@@ -10,11 +10,13 @@
 #include <cmath>
 #include <cstdlib>
 #include <map>
+#include <string>
 #include <utility>
 
 #include "cup_internal.h"
 #include "mg_device.cuh"
 #include "smooth_tma.cuh"
+#include "stencil7_tma.cuh"
 #include "comm.cuh"
 
 namespace cup {
@@ -294,6 +296,97 @@ __global__ void __launch_bounds__(256) k_level_sum(LevelView lv, SlotVec<Real> f
 }
 
 // ---------------------------------------------------------------------------
+// mg_bottom (main.c:4808) when level 0 is ONE block (bpd = 1): subtract the
+// mean of f and run all MG_BOT = 50 sweeps inside a single CTA.  All six faces
+// are walls, so every ghost equals the adjacent own cell (OP_BC) and the ghost
+// sum is u times the number of wall faces touching the cell: no halo, u stays
+// in registers, one launch instead of 52.
+template <typename Real>
+__global__ void __launch_bounds__(TPB) k_bottom1(Real *__restrict__ u, const Real *__restrict__ f,
+                                                 const Real *__restrict__ Wl, Real h, Real invh, Real omega, int nsweep,
+                                                 int zero_init) {
+  __shared__ Real ex[512];
+  __shared__ double red[2];
+  const int t = threadIdx.x, x = t & 7, y = t >> 3;
+  Real w[8], ff[8], uu[8], v[8];
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    w[k] = Wl[k * 64 + t];
+    ff[k] = f[k * 64 + t];
+    uu[k] = zero_init ? (Real)0 : u[k * 64 + t];
+    s += (double)ff[k];
+  }
+  for (int o = 16; o > 0; o >>= 1)
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((t & 31) == 0)
+    red[t >> 5] = s;
+  __syncthreads();
+  const Real q0 = (Real)((red[0] + red[1]) / 512.0);
+  const int cxy = (x == 0) + (x == 7) + (y == 0) + (y == 7);
+  for (int it = 0; it < nsweep; it++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const Real cnt = (Real)(cxy + (k == 0) + (k == 7));
+      v[k] = invh * ((ff[k] - q0) - h * (cnt * uu[k]));
+    }
+    dst8<Real>(v);
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      ex[sw(x, y, k)] = v[k];
+    __syncthreads();
+    {
+      const int x2 = t & 7, z2 = t >> 3;
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        v[k] = ex[sw(x2, k, z2)];
+      dst8<Real>(v);
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        ex[sw(x2, k, z2)] = v[k];
+    }
+    __syncthreads();
+    {
+      const int y3 = t & 7, z3 = t >> 3;
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        v[k] = ex[sw(k, y3, z3)];
+      dst8<Real>(v);
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        v[k] *= w[k];
+      dst8<Real>(v);
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        ex[sw(k, y3, z3)] = v[k];
+    }
+    __syncthreads();
+    {
+      const int x2 = t & 7, z2 = t >> 3;
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        v[k] = ex[sw(x2, k, z2)];
+      dst8<Real>(v);
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        ex[sw(x2, k, z2)] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      v[k] = ex[sw(x, y, k)];
+    dst8<Real>(v);
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      uu[k] = uu[k] + omega * (v[k] - uu[k]);
+    __syncthreads();  // ex is rewritten by the next sweep
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    u[k * 64 + t] = uu[k];
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 namespace {
@@ -324,6 +417,24 @@ static bool smooth_use_tma() {
   if (v < 0) {
     const char *e = getenv("CUP_SMOOTH_IMPL");
     v = (e && strcmp(e, "ldg") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
+static int smooth_per_sm() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("CUP_SMOOTH_PER_SM");
+    v = e ? atoi(e) : 12;
+  }
+  return v;
+}
+
+static bool single_cta_bottom() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("CUP_BOTTOM1");
+    v = (e && atoi(e) == 0) ? 0 : 1;
   }
   return v == 1;
 }
@@ -375,7 +486,7 @@ int smooth_level(CupCtx *c, Level &v, int n, Arr<Real> &a, bool first_is_zero, c
     set_error("multigrid level %d has coarse-fine interfaces: AMR smoother not available in this build", v.L);
     return CUP_ERR_UNSUPPORTED;
   }
-  const int grid = grid_for(c, (long long)v.act.size(), smooth_use_tma() ? 12 : 16);
+  const int grid = grid_for(c, (long long)v.act.size(), smooth_use_tma() ? smooth_per_sm() : 16);
   const Real h = (Real)v.h, invh = (Real)(1.0 / v.h), om = (Real)0.8;  // mg_omega, main.c:4434
   for (int it = 0; it < n; it++) {
     SlotVec<Real> &src = (it & 1) ? a.u1 : a.u0;
@@ -423,9 +534,51 @@ int smooth_level(CupCtx *c, Level &v, int n, Arr<Real> &a, bool first_is_zero, c
   return CUP_OK;
 }
 
+// CUP_TRACE=1: time the phases of one eager V-cycle with CUDA events (debug aid)
+struct Trace {
+  std::vector<cudaEvent_t> ev;
+  std::vector<std::string> name;
+  bool on = false;
+  void mark(CupCtx *c, const std::string &n) {
+    if (!on)
+      return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, c->stream);
+    ev.push_back(e);
+    name.push_back(n);
+  }
+  void report(CupCtx *c) {
+    if (!on || ev.empty())
+      return;
+    cudaStreamSynchronize(c->stream);
+    std::map<std::string, float> acc;
+    float tot = 0;
+    for (size_t i = 1; i < ev.size(); i++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      acc[name[i]] += ms;
+      tot += ms;
+    }
+    fprintf(stderr, "[cup trace rank %d] total %.3f ms\n", c->rank, tot);
+    for (auto &kv : acc)
+      fprintf(stderr, "[cup trace rank %d]   %-14s %.3f ms\n", c->rank, kv.first.c_str(), kv.second);
+    for (auto e : ev)
+      cudaEventDestroy(e);
+    ev.clear();
+    name.clear();
+  }
+};
+static Trace g_tr;
+
 template <typename Real>
 int vcycle_t(CupCtx *c, const Real *d_in, Real *d_out) {
   const int nleaf = (int)c->nblk;
+  {
+    const char *e = getenv("CUP_TRACE");
+    g_tr.on = e && atoi(e) != 0;
+  }
+  g_tr.mark(c, "start");
   Arr<Real> a;
   a.u0 = SlotVec<Real>{d_out, (Real *)c->u0_x, nleaf};
   a.u1 = SlotVec<Real>{(Real *)c->u1_leaf, (Real *)c->u1_x, nleaf};
@@ -445,23 +598,33 @@ int vcycle_t(CupCtx *c, const Real *d_in, Real *d_out) {
     // u == 0 on entry only at the finest level (vec_zero, :4834); coarser
     // levels start from the restricted u (FAS).
     CUP_TRY(smooth_level<Real>(c, v, MG_PRE, a, L == top, nullptr));
+    g_tr.mark(c, "L" + std::to_string(L) + " pre");
     CUP_TRY(halo_wait(c, v));  // faces of u0 were posted by the last sweep
     if (!v.act.empty()) {
       const int grid = grid_for(c, (long long)v.act.size(), 12);
-      k_down<Real><<<grid, TPB, 0, c->stream>>>(view(v), v.d_pslot, v.d_oct, a.u0, a.f, (Real)v.h,
-                                                 (Real *const *)v.d_rptr);
+      if (smooth_use_tma())
+        CUP_TRY(down_tma_launch<Real>(c, view(v), v.d_pslot, v.d_oct, a.u0, a.f, (Real)v.h, v.d_rptr));
+      else
+        k_down<Real><<<grid, TPB, 0, c->stream>>>(view(v), v.d_pslot, v.d_oct, a.u0, a.f, (Real)v.h,
+                                                   (Real *const *)v.d_rptr);
       c->launches++;
     }
+    g_tr.mark(c, "L" + std::to_string(L) + " down");
     CUP_TRY(restrict_exchange<Real>(c, v, a.f, a.u0));
     Level &w = c->lv[L - 1];
     CUP_TRY(halo_post<Real>(c, w, a.u0));  // restricted u: consumed by tau and by the first sweep of level L-1
     CUP_TRY(halo_wait(c, w));
     if (!w.par.empty()) {
       const int gridw = grid_for(c, (long long)w.par.size(), 12);
-      k_apply<Real, true><<<gridw, TPB, 0, c->stream>>>(view(w), w.d_par, (int)w.par.size(), a.u0, a.f, a.us,
-                                                         (Real)w.h, nullptr, (Real)0);
+      if (smooth_use_tma())
+        CUP_TRY(apply_tma_launch<Real>(c, view(w), w.d_par, (int)w.par.size(), a.u0, a.f, a.us, (Real)w.h, nullptr,
+                                       (Real)0, true));
+      else
+        k_apply<Real, true><<<gridw, TPB, 0, c->stream>>>(view(w), w.d_par, (int)w.par.size(), a.u0, a.f, a.us,
+                                                           (Real)w.h, nullptr, (Real)0);
       c->launches++;
     }
+    g_tr.mark(c, "L" + std::to_string(L) + " res+tau");
   }
   {
     Level &v = c->lv[0];
@@ -470,6 +633,17 @@ int vcycle_t(CupCtx *c, const Real *d_in, Real *d_out) {
     if (top == 0) {
       // single-level mesh: f is the caller's vector, u starts from zero
     }
+    if (v.gnact == 1 && c->bpd[0] == 1 && c->bpd[1] == 1 && c->bpd[2] == 1 && single_cta_bottom()) {
+      // the whole bottom solve in one CTA on the rank that owns the block
+      if (!v.act.empty()) {
+        k_bottom1<Real><<<1, TPB, 0, c->stream>>>(a.u0.at_host(v.act[0]), a.f.at_host(v.act[0]), (const Real *)c->d_W,
+                                                   (Real)v.h, (Real)(1.0 / v.h), (Real)0.8, MG_BOT, top == 0);
+        c->launches++;
+        CUP_TRY(halo_post<Real>(c, v, a.u0));
+      }
+      g_tr.mark(c, "L0 bottom");
+      goto bottom_done;
+    }
     CUP_CUDA(cudaMemsetAsync(q, 0, sizeof(double), c->stream));
     k_level_sum<Real><<<grid_for(c, (long long)v.act.size(), 4), 256, 0, c->stream>>>(
         view(v), a.f, q, 1.0 / (512.0 * (double)v.gnact));
@@ -477,7 +651,9 @@ int vcycle_t(CupCtx *c, const Real *d_in, Real *d_out) {
     CUP_TRY(comm_allreduce(c, 0, 1));
     fmean = q;
     CUP_TRY(smooth_level<Real>(c, v, MG_BOT, a, top == 0, fmean));
+    g_tr.mark(c, "L0 bottom");
   }
+bottom_done:
   for (int L = 1; L <= top; L++) {
     Level &v = c->lv[L];
     CUP_TRY(prolong_exchange<Real>(c, v, a.u0, a.us));
@@ -487,9 +663,12 @@ int vcycle_t(CupCtx *c, const Real *d_in, Real *d_out) {
       c->launches++;
     }
     CUP_TRY(halo_post<Real>(c, v, a.u0));
+    g_tr.mark(c, "L" + std::to_string(L) + " up");
     CUP_TRY(smooth_level<Real>(c, v, MG_POST, a, false, nullptr));
+    g_tr.mark(c, "L" + std::to_string(L) + " post");
   }
   CUP_CUDA(cudaGetLastError());
+  g_tr.report(c);
   return CUP_OK;
 }
 
@@ -549,8 +728,11 @@ int pois_op_t(CupCtx *c, const Real *d_in, Real *d_out) {
   SlotVec<Real> u{const_cast<Real *>(d_in), nullptr, nleaf}, o{d_out, nullptr, nleaf}, us{nullptr, nullptr, nleaf};
   CUP_TRY(halo_exchange<Real>(c, v, u));
   const Real h = (Real)v.h;
-  k_apply<Real, false><<<grid_for(c, c->nblk, 16), TPB, 0, c->stream>>>(view(v), nullptr, (int)v.act.size(), u, o,
-                                                                         us, h, shift, h * h * h);
+  if (smooth_use_tma())
+    CUP_TRY(apply_tma_launch<Real>(c, view(v), nullptr, (int)v.act.size(), u, o, us, h, shift, h * h * h, false));
+  else
+    k_apply<Real, false><<<grid_for(c, c->nblk, 16), TPB, 0, c->stream>>>(view(v), nullptr, (int)v.act.size(), u, o,
+                                                                           us, h, shift, h * h * h);
   c->launches++;
   if (mc == 1 || mc > 2) {
     const long long pin = c->pin_local;  // pois_pin: block (0,0,0), main.c:4888 (on its owner only)
@@ -678,7 +860,7 @@ int mg_vcycle_dev(CupCtx *c, const void *d_in, void *d_out) {
     set_error("mg_vcycle: no mesh uploaded");
     return CUP_ERR_STATE;
   }
-  if (!use_graphs())
+  if (!use_graphs() || getenv("CUP_TRACE"))
     return vcycle_eager(c, d_in, d_out);
   if (!c->graph_cache)
     c->graph_cache = new GraphCache;
@@ -767,7 +949,7 @@ int time_smooth(CupCtx *c, int level, int reps, float *ms) {
   cudaEvent_t e0, e1;
   CUP_CUDA(cudaEventCreate(&e0));
   CUP_CUDA(cudaEventCreate(&e1));
-  const int grid = grid_for(c, (long long)v.act.size(), smooth_use_tma() ? 12 : 16);
+  const int grid = grid_for(c, (long long)v.act.size(), smooth_use_tma() ? smooth_per_sm() : 16);
   // state[] vectors double as inputs: F_PRES as u, F_LHS as f, F_TMP as u'
   if (c->real_bytes == 8) {
     SlotVec<double> s{(double *)c->state[CUP_F_PRES], (double *)c->u0_x, nleaf};

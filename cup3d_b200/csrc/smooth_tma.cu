@@ -21,6 +21,7 @@
 #include "cup_internal.h"
 #include "mg_device.cuh"
 #include "smooth_tma.cuh"
+#include "stencil7_tma.cuh"
 #include "tma.cuh"
 
 namespace cup {
@@ -367,6 +368,18 @@ int get_map(CupCtx *c, const void *base, long long nblocks, int kind, CUtensorMa
 }
 
 }  // namespace
+
+int tma_face_maps(CupCtx *c, const void *leaf, const void *extra, CUtensorMap out[4]) {
+  const long long nleaf = c->nblk, nx = c->nslot - c->nblk + 1;
+  // a part that holds no blocks of this vector still needs a valid (unused) descriptor
+  const void *lb = leaf ? leaf : extra;
+  const void *eb = extra ? extra : leaf;
+  CUP_TRY(get_map(c, lb, leaf ? nleaf : 1, 0, &out[0]));
+  CUP_TRY(get_map(c, lb, leaf ? nleaf : 1, 1, &out[1]));
+  CUP_TRY(get_map(c, eb, extra ? nx : 1, 0, &out[2]));
+  CUP_TRY(get_map(c, eb, extra ? nx : 1, 1, &out[3]));
+  return CUP_OK;
+}
 
 void free_tma_cache(CupCtx *c) {
   delete (MapCache *)c->tma_cache;
