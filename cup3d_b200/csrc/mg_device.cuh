@@ -88,10 +88,62 @@ __device__ __forceinline__ void dst8(Real (&v)[8]) {
 // Bank-conflict-free shared-memory layout of one 8^3 block for the transposes
 // between the x, y and z passes.  With 64-bit words a half-warp must hit 16
 // distinct 8-byte bank pairs; bank pair = index mod 16 = 8*(row&1) + column.
-// Storing (x,y,z) at row (y ^ (z&1)), column (x+y)&7 makes all three access
+// Storing (x,y,z) at row (y ^ (z&1)), column x ^ y makes all three access
 // patterns (fixed x / fixed y / fixed z across a half-warp) conflict free
-// with no padding.
-__device__ __forceinline__ int sw(int x, int y, int z) { return (z << 6) + (((y ^ (z & 1))) << 3) + ((x + y) & 7); }
+// with no padding, and keeps the index a pure XOR of bit fields.
+__device__ __forceinline__ int sw(int x, int y, int z) { return (z << 6) + (((y ^ (z & 1))) << 3) + (x ^ y); }
+
+// The block-local exact inverse  v <- Lint^-1 v  (pre_blk, main.c:4368) on the CTA's 8^3 block:
+// every thread passes its z-line in and gets its z-line back.  Transform order z,y,x,(scale by
+// w = 1/(lam_i+lam_j+lam_k)),x,y,z through the shared buffer ex[512] in layout sw(); four
+// __syncthreads.  All shared addresses are one XOR with an immediate away from a per-thread base:
+//   z pass  idx = (zb ^ 8(k&1)) + 64k      zb = 8y + (x^y)
+//   y pass  idx = yb ^ 9k                  yb = 64 z2 + 8(z2&1) + x2
+//   x pass  idx = xb ^ k                   xb = 64 z3 + 8(y3 ^ (z3&1)) + y3
+template <typename Real>
+__device__ __forceinline__ void fdm_solve(Real (&v)[8], Real *ex, const Real (&w)[8], int t) {
+  const int a = t & 7, c = t >> 3;  // (x,y) in the z pass, (x2,z2) in the y pass, (y3,z3) in the x pass
+  const int zb0 = (c << 3) + (a ^ c), zb1 = zb0 ^ 8;
+  const int yb = (c << 6) + ((c & 1) << 3) + a;
+  const int xb = (c << 6) + ((a ^ (c & 1)) << 3) + a;
+  dst8<Real>(v);
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    ex[((k & 1) ? zb1 : zb0) + 64 * k] = v[k];
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    v[k] = ex[yb ^ (9 * k)];
+  dst8<Real>(v);
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    ex[yb ^ (9 * k)] = v[k];
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    v[k] = ex[xb ^ k];
+  dst8<Real>(v);
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    v[k] *= w[k];
+  dst8<Real>(v);
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    ex[xb ^ k] = v[k];
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    v[k] = ex[yb ^ (9 * k)];
+  dst8<Real>(v);
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    ex[yb ^ (9 * k)] = v[k];
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    v[k] = ex[((k & 1) ? zb1 : zb0) + 64 * k];
+  dst8<Real>(v);
+}
 
 // Load the six ghost faces of block `b` into halo[6][64] (shared).  Face f of a
 // regular neighbour is that neighbour's opposite boundary plane; at a domain

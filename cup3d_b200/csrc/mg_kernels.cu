@@ -76,57 +76,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_smooth(LevelView lv, SlotVec<Real
       for (int k = 0; k < 8; k++)
         v[k] = invh * (v[k] - q0);
     }
-    // forward z
-    dst8<Real>(v);
-#pragma unroll
-    for (int k = 0; k < 8; k++)
-      ex[sw(x, y, k)] = v[k];
-    __syncthreads();
-    // forward y : thread owns (x2, *, z2)
-    {
-      const int x2 = t & 7, z2 = t >> 3;
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        v[k] = ex[sw(x2, k, z2)];
-      dst8<Real>(v);
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        ex[sw(x2, k, z2)] = v[k];
-    }
-    __syncthreads();
-    // forward x, scale by 1/(lam_i+lam_j+lam_k), inverse x : thread owns (*, y3, z3)
-    {
-      const int y3 = t & 7, z3 = t >> 3;
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        v[k] = ex[sw(k, y3, z3)];
-      dst8<Real>(v);
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        v[k] *= w[k];
-      dst8<Real>(v);
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        ex[sw(k, y3, z3)] = v[k];
-    }
-    __syncthreads();
-    // inverse y
-    {
-      const int x2 = t & 7, z2 = t >> 3;
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        v[k] = ex[sw(x2, k, z2)];
-      dst8<Real>(v);
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        ex[sw(x2, k, z2)] = v[k];
-    }
-    __syncthreads();
-    // inverse z and update
-#pragma unroll
-    for (int k = 0; k < 8; k++)
-      v[k] = ex[sw(x, y, k)];
-    dst8<Real>(v);
+    fdm_solve<Real>(v, ex, w, t);
     Real *ob = udst.at(slot);
     if (MODE == 0) {
 #pragma unroll
@@ -330,52 +280,7 @@ __global__ void __launch_bounds__(TPB) k_bottom1(Real *__restrict__ u, const Rea
       const Real cnt = (Real)(cxy + (k == 0) + (k == 7));
       v[k] = invh * ((ff[k] - q0) - h * (cnt * uu[k]));
     }
-    dst8<Real>(v);
-#pragma unroll
-    for (int k = 0; k < 8; k++)
-      ex[sw(x, y, k)] = v[k];
-    __syncthreads();
-    {
-      const int x2 = t & 7, z2 = t >> 3;
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        v[k] = ex[sw(x2, k, z2)];
-      dst8<Real>(v);
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        ex[sw(x2, k, z2)] = v[k];
-    }
-    __syncthreads();
-    {
-      const int y3 = t & 7, z3 = t >> 3;
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        v[k] = ex[sw(k, y3, z3)];
-      dst8<Real>(v);
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        v[k] *= w[k];
-      dst8<Real>(v);
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        ex[sw(k, y3, z3)] = v[k];
-    }
-    __syncthreads();
-    {
-      const int x2 = t & 7, z2 = t >> 3;
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        v[k] = ex[sw(x2, k, z2)];
-      dst8<Real>(v);
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        ex[sw(x2, k, z2)] = v[k];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 8; k++)
-      v[k] = ex[sw(x, y, k)];
-    dst8<Real>(v);
+    fdm_solve<Real>(v, ex, w, t);
 #pragma unroll
     for (int k = 0; k < 8; k++)
       uu[k] = uu[k] + omega * (v[k] - uu[k]);

@@ -164,74 +164,41 @@ __global__ void __launch_bounds__(TPB, 12)
       const int cxm = (wall & 1) ? 0 : NCOL - 1, cxp = (wall & 2) ? NCOL - 1 : 0;
       const int stm = (wall & 0x100) ? 1 : NCOL, stp = (wall & 0x200) ? 1 : NCOL;
       const int om = (wall & 0x100) ? 0 : cxm, op = (wall & 0x200) ? 0 : cxp;
+      // ghost sums, branch per face class (uniform per thread, so the k loops stay straight-line)
+      Real g[8];
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        Real g = 0;
-        if (x == 0)
-          g += s_x[0][(k * 8 + y) * stm + om];
-        if (x == 7)
-          g += s_x[1][(k * 8 + y) * stp + op];
-        if (y == 0)
-          g += s_y[0][k * 8 + x];
-        if (y == 7)
-          g += s_y[1][k * 8 + x];
-        if (k == 0)
-          g += s_z[0][t];
-        if (k == 7)
-          g += s_z[1][t];
-        v[k] = invh * ((v[k] - q0) - h * g);
+      for (int k = 0; k < 8; k++)
+        g[k] = 0;
+      g[0] = s_z[0][t];
+      g[7] = s_z[1][t];
+      if (x == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          g[k] += s_x[0][(k * 8 + y) * stm + om];
       }
+      if (x == 7) {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          g[k] += s_x[1][(k * 8 + y) * stp + op];
+      }
+      if (y == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          g[k] += s_y[0][k * 8 + x];
+      }
+      if (y == 7) {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          g[k] += s_y[1][k * 8 + x];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        v[k] = invh * ((v[k] - q0) - h * g[k]);
     }
     __syncthreads();  // stage fully consumed
     if (t == 0 && more)
       issue(nslot, nnb);
-    // forward z
-    dst8<Real>(v);
-#pragma unroll
-    for (int k = 0; k < 8; k++)
-      ex[sw(x, y, k)] = v[k];
-    __syncthreads();
-    {
-      const int x2 = t & 7, z2 = t >> 3;
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        v[k] = ex[sw(x2, k, z2)];
-      dst8<Real>(v);
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        ex[sw(x2, k, z2)] = v[k];
-    }
-    __syncthreads();
-    {
-      const int y3 = t & 7, z3 = t >> 3;
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        v[k] = ex[sw(k, y3, z3)];
-      dst8<Real>(v);
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        v[k] *= w[k];
-      dst8<Real>(v);
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        ex[sw(k, y3, z3)] = v[k];
-    }
-    __syncthreads();
-    {
-      const int x2 = t & 7, z2 = t >> 3;
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        v[k] = ex[sw(x2, k, z2)];
-      dst8<Real>(v);
-#pragma unroll
-      for (int k = 0; k < 8; k++)
-        ex[sw(x2, k, z2)] = v[k];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 8; k++)
-      v[k] = ex[sw(x, y, k)];
-    dst8<Real>(v);
+    fdm_solve<Real>(v, ex, w, t);
     Real *ob = udst.at(slot);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
