@@ -69,7 +69,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -203,11 +203,13 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # clocks / throttle reasons are sampled from the warm-up to the end of the kernel timing so
+    # that even the sub-millisecond multi-GPU steps are covered by several samples
+    clk = ClockSampler(local_rank)
+    clk.start()
     for _ in range(args.warmup):
         ctx.mg_vcycle_dev(b, z)
     barrier()
-    clk = ClockSampler(local_rank)
-    clk.start()
     l0 = ctx.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -268,10 +270,11 @@ def run_ours(args, rank, world, local_rank):
                                "point-source pair" % (8 << L, L, L + 1),
                    "blocks": len(gib), "mg_levels": L + 1,
                    "l2_policy": "inputs larger than L2 (%.2f GB per vector per rank)" % (N * 8 / 1e9),
-                   "parallelism": "%d rank(s), one per GPU, contiguous Hilbert ranges of the block list; "
-                                  "face halos + restrict/prolong by NCCL send/recv, scalars by NCCL allreduce" % world},
+                   "parallelism": "%d rank(s), one per GPU, contiguous Hilbert ranges of the block list; ghost faces "
+                                  "pushed into peer windows over NVLink by the sweep kernels (NCCL for setup and "
+                                  "allreduce)" % world},
         "hbm_gbs_vcycle": cells * B_PER_CELL_VCYCLE * args.steps / (ms * 1e-3) / 1e9,
-        "roofline": {"bound": "hbm", "kernel": "k_smooth<double,0> (finest level)", "achieved": smooth_gbs,
+        "roofline": {"bound": "hbm", "kernel": "k_smooth_tma<double> (finest-level smoother)", "achieved": smooth_gbs,
                      "peak": peak, "unit": "GB/s", "frac": smooth_gbs / peak,
                      "traffic": traffic["bytes_per_launch"] if traffic else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": N * B_PER_CELL_SMOOTH, "ms_per_launch": sm_ms,

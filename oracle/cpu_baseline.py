@@ -36,9 +36,28 @@ def main():
         for p, v in ((0.25, 1.0), (0.75, -1.0)):
             i = int(np.nonzero(np.all((lo <= p) & (p < hi), axis=1))[0][0])
             b[i, 0] = v
+        # the reference's schedule(dynamic,1) loops collapse when the host is oversubscribed:
+        # pick the best OpenMP thread count with one cycle each, then time with it
+        import ctypes
+        gomp = ctypes.CDLL("libgomp.so.1")
+        ncpu = os.cpu_count() or 1
+        cand = sorted({t for t in (4, 8, 16, 24, 32, 48, 64, 96, 128, ncpu) if t <= ncpu})
+        if os.environ.get("OMP_NUM_THREADS"):
+            cand = [int(os.environ["OMP_NUM_THREADS"])]
+        best, best_t = None, None
+        for t in cand:
+            gomp.omp_set_num_threads(t)
+            R.time_vcycle(b, 0, 1)
+            s1 = R.time_vcycle(b, 0, 1)
+            if best is None or s1 < best:
+                best, best_t = s1, t
+            if s1 > 3 * best:
+                break
+        gomp.omp_set_num_threads(best_t)
         sec = R.time_vcycle(b, a.warmup, a.steps)
-        kind, threads = "reference", R.threads()
-        what = "unmodified reference main.c (oracle/_ref), gcc -O3 -fopenmp, %d OpenMP threads, 1 rank" % threads
+        kind, threads = "reference", best_t
+        what = ("unmodified reference main.c (oracle/_ref), gcc -O3 -fopenmp, %d OpenMP threads (best of %s on %d "
+                "logical CPUs), 1 rank" % (threads, cand, ncpu))
     else:
         from oracle import portbind as P
         sec, n, threads = P.time_vcycle_uniform(L, a.warmup, a.steps)
