@@ -30,11 +30,16 @@ CASES = {
     "b211": dict(bpdx=2, bpdy=1, bpdz=1, levelStart=1, levelMax=2),   # 32x16x16, non-cubic base
     "b222_l0": dict(bpdx=2, bpdy=2, bpdz=2, levelStart=0, levelMax=1),  # single level: V-cycle == mg_bottom
     "b321": dict(bpdx=3, bpdy=2, bpdz=1, levelStart=1, levelMax=2),   # irregular Hilbert base (sfc.is_regular=0)
+    # AMR: the reference's own mesh_adapt (main.c:4012) refines around a chi blob (k_gradchi tagging)
+    "amr2": dict(bpdx=2, bpdy=2, bpdz=2, levelStart=1, levelMax=4, Rtol=5, Ctol=-1),   # 2 levels, 148 blocks
+    "amr3": dict(bpdx=2, bpdy=2, bpdz=2, levelStart=1, levelMax=4, Rtol=5, Ctol=-1),   # 3 levels, 435 blocks
 }
+ADAPT = {"amr2": 1, "amr3": 2}  # mesh_adapt passes
 # what each case stores (fixtures must stay small): "full" = inputs and all outputs;
 # "mid" = outputs only (inputs are regenerated from the seed, their checksum is stored);
 # "big" = V-cycle / solve outputs only.
-TIER = {"u16": "full", "b211": "full", "b222_l0": "full", "b321": "mid", "u32": "big", "u64": "big"}
+TIER = {"u16": "full", "b211": "full", "b222_l0": "full", "b321": "mid", "u32": "big", "u64": "big",
+        "amr2": "mid", "amr3": "big"}
 
 
 def fields(ib, rb, seed):
@@ -79,6 +84,16 @@ def worker(case):
     from oracle import refbind as R
     R.init(**CASES[case])
     tier = TIER[case]
+    for _ in range(ADAPT.get(case, 0)):
+        # refine where 0 < chi < 0.9 (blob surface); velocity zero so vorticity does not tag
+        ib, rb = R.blocks()
+        from cup3d_b200 import mesh
+        X, Y, Z = mesh.cell_centers(ib, rb)
+        r = np.sqrt((X - 0.3) ** 2 + (Y - 0.35) ** 2 + (Z - 0.4) ** 2)
+        st = np.zeros((R.nblk(), 9, 512))
+        st[:, 0] = (1.0 / (1.0 + np.exp((r - 0.07) / 0.006))).reshape(-1, 512)
+        R.state_set(st)
+        R.mesh_adapt(5.0, -1.0)
     ib, rb = R.blocks()
     n = R.nblk()
     F = fields(ib, rb, seed=1234)
@@ -91,7 +106,7 @@ def worker(case):
         for k in F:
             g["in_" + k] = F[k]
     # --- mg_vcycle (main.c:4831) on two right-hand sides
-    for name in ("cosrhs", "rand"):
+    for name in (("cosrhs", "rand") if case not in ADAPT else ("cosrhs",)):
         g["vc_out_" + name] = R.mg_vcycle(F[name])
     # residual history of x += M(b - A x), constraint 2
     R.set_scalars(mean_constraint=2)
@@ -105,7 +120,7 @@ def worker(case):
         hist.append(np.sqrt(R.pois_dot(r, r)) / nb)
     g["vc_hist"] = np.array(hist)
     # --- pois_op (main.c:4282) for each mean-constraint mode
-    for mc in ((0, 1, 2, 3) if tier != "big" else (2,)):
+    for mc in ((0, 1, 2, 3) if tier != "big" and case not in ADAPT else ((0, 2) if tier != "big" else (2,))):
         R.set_scalars(mean_constraint=mc)
         g["op_out_mc%d" % mc] = R.pois_op(F["pres"])
     g["dot_ab"] = np.float64(R.pois_dot(F["pres"], F["rand"]))
@@ -121,13 +136,16 @@ def worker(case):
             R.state_set(st)
             R.stencil(name)
             g["st_" + name] = R.state_get()[:, f0:f0 + nc]
-        R.set_scalars(dt=dt, nu=nu, uinf=uinf, step=5, mean_constraint=2)
-        R.state_set(st)
-        R.advdiff()
-        g["advdiff"] = R.state_get()[:, R.F_VEL:R.F_VEL + 6]  # VEL, TMP
+        if case not in ADAPT:
+            R.set_scalars(dt=dt, nu=nu, uinf=uinf, step=5, mean_constraint=2)
+            R.state_set(st)
+            R.advdiff()
+            g["advdiff"] = R.state_get()[:, R.F_VEL:R.F_VEL + 6]  # VEL, TMP
     # --- pois_solve (main.c:4875): rhs = F_LHS with zero mean, guess F_PRES = 0
     if case != "b222_l0":
-        for mc in ((2, 1) if tier != "big" else (2,)):
+        for mc in ((2, 1) if tier != "big" and case not in ADAPT else (2,)):
+            if case == "amr3":
+                break
             R.set_scalars(dt=dt, nu=nu, uinf=uinf, step=5, mean_constraint=mc, ptol=1e-10, ptol_rel=1e-12)
             s = st.copy()
             s[:, R.F_LHS] = solve_rhs(F, rb)
@@ -137,7 +155,7 @@ def worker(case):
             g["solve_x_mc%d" % mc] = R.state_get()[:, R.F_PRES]
         # --- projection (main.c:5828), both branches of the incremental-pressure switch
         if tier != "big":
-            for step in (1, 5):
+            for step in ((1, 5) if case not in ADAPT else (5,)):
                 R.set_scalars(dt=dt, nu=nu, uinf=uinf, step=step, mean_constraint=2, ptol=1e-10, ptol_rel=1e-12)
                 R.state_set(st)
                 R.projection()

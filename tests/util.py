@@ -9,7 +9,8 @@ GOLD = os.path.join(HERE, "golden")
 sys.path.insert(0, GOLD)
 import make_golden as MG  # noqa: E402  (fields(), state0(), solve_rhs(): the input generators)
 
-ALL_CASES = list(MG.CASES)
+AMR_CASES = list(MG.ADAPT)                                  # multi-level meshes (coarse-fine interfaces)
+ALL_CASES = [c for c in MG.CASES if c not in AMR_CASES]     # single-level meshes
 FULL_CASES = [c for c in ALL_CASES if MG.TIER[c] == "full"]
 STENCIL_CASES = [c for c in ALL_CASES if MG.TIER[c] != "big"]
 SOLVE_CASES = [c for c in ALL_CASES if c != "b222_l0"]
