@@ -1,0 +1,300 @@
+// amr_kernels.cu -- the multigrid / Poisson kernels on levels with coarse-fine
+// interfaces (block-structured AMR).  Same decomposition as the uniform
+// kernels (one 8^3 block per 64 threads, z-line per thread); the ghost faces
+// additionally come from one coarser leaf (OP_FD interpolation) or from four
+// finer leaves (OP_AVG8), and the leaf-level operator applies the reference's
+// flux correction (fc_fill, main.c:3228) in the same pass.
+//
+// Reference: lab_load :3544, lab_exec :3401, gen_table.py (ss = 1, te = 0),
+// face_grad :4227, fc_prepare/fc_fill :3155-3293, mg_smooth/down/tau :4689-4770.
+#include "amr_kernels.cuh"
+#include "cup_internal.h"
+#include "mg_device.cuh"
+
+namespace cup {
+
+__constant__ double cFDp[9];
+__constant__ double cFDm[9];
+
+int amr_setup_constants() {
+  // d_coef_plus / d_coef_minus, main.c:3371-3374
+  const double p[9] = {-0.09375, 0.4375, 0.15625, 0.15625, -0.5625, 0.90625, -0.09375, 0.4375, 0.15625};
+  const double m[9] = {0.15625, -0.5625, 0.90625, -0.09375, 0.4375, 0.15625, 0.15625, 0.4375, -0.09375};
+  CUP_CUDA(cudaMemcpyToSymbol(cFDp, p, sizeof p));
+  CUP_CUDA(cudaMemcpyToSymbol(cFDm, m, sizeof m));
+  return CUP_OK;
+}
+
+// Ghost faces of block b into halo[6][64] for a level that may have coarser neighbours
+// (multigrid contexts) or coarser and finer ones (leaf context).  usame: vector holding the
+// same-level neighbours (the ping-pong source); ucan: canonical vector holding coarser / finer
+// leaves.  Two phases around one __syncthreads (the coarse patches are shared).
+template <typename Real>
+__device__ __forceinline__ void halo_amr_phase1(const SlotVec<Real> &usame, const SlotVec<Real> &ucan, const Real *own,
+                                                const int *nbr6, const int *ext24, int t, Real (*halo)[64],
+                                                Real (*patch)[16]) {
+  const int a = t & 7, c = t >> 3;
+#pragma unroll
+  for (int f = 0; f < 6; f++) {
+    const int nb = nbr6[f];
+    if (nb == kCoarse) {
+      coarse_patch_load<Real>(ucan.at(ext24[f * 4]), f, ext24[f * 4 + 1], t, patch[f]);
+    } else if (nb == kFine) {
+      Real lay[2][2][2];
+      halo[f][t] = fine_avg<Real>(ucan, ext24 + f * 4, f, a, c, lay);
+    } else {
+      const Real *src = nb >= 0 ? usame.at(nb) : own;
+      const int p = (nb >= 0) ? ((f & 1) ? 0 : 7) : ((f & 1) ? 7 : 0);
+      halo[f][t] = src[face_idx(f, p, a, c)];
+    }
+  }
+}
+
+template <typename Real>
+__device__ __forceinline__ void halo_amr_phase2(const Real *own, const int *nbr6, int t, Real (*halo)[64],
+                                                const Real (*patch)[16]) {
+  const int a = t & 7, c = t >> 3;
+#pragma unroll
+  for (int f = 0; f < 6; f++)
+    if (nbr6[f] == kCoarse) {
+      const Real bb = own[face_idx(f, (f & 1) ? 7 : 0, a, c)], cq = own[face_idx(f, (f & 1) ? 6 : 1, a, c)];
+      halo[f][t] = fd_ghost<Real>(patch[f], a, c, bb, cq);
+    }
+}
+
+// mg_smooth on a level with coarser neighbours.  Same algebraic form as k_smooth (the ghost of
+// a coarse face depends on the block's own OLD values through the blend, which is exactly what
+// A u_old contains).
+template <typename Real>
+__global__ void __launch_bounds__(TPB) k_smooth_amr(LevelView lv, SlotVec<Real> usrc, SlotVec<Real> ucan,
+                                                    SlotVec<Real> udst, SlotVec<Real> fvec,
+                                                    const Real *__restrict__ Wl, Real h, Real invh, Real omega,
+                                                    const double *__restrict__ fmean, int zero_src) {
+  __shared__ Real ex[512];
+  __shared__ Real halo[6][64];
+  __shared__ Real patch[6][16];
+  const int t = threadIdx.x, x = t & 7, y = t >> 3;
+  Real w[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    w[k] = Wl[k * 64 + t];
+  const Real q0 = fmean ? (Real)(*fmean) : (Real)0;
+  for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
+    const int slot = lv.act[b];
+    const Real *fb = fvec.at(slot);
+    Real uu[8], v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      v[k] = fb[k * 64 + t];
+    if (!zero_src) {
+      const Real *ub = usrc.at(slot);
+      const int *nbr6 = lv.nbr + (size_t)b * 6;
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        uu[k] = ub[k * 64 + t];
+      halo_amr_phase1<Real>(usrc, ucan, ub, nbr6, lv.ext + (size_t)b * 24, t, halo, patch);
+      __syncthreads();
+      halo_amr_phase2<Real>(ub, nbr6, t, halo, patch);
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        v[k] = invh * ((v[k] - q0) - h * ghost_sum<Real>(halo, x, y, k));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        uu[k] = 0;
+        v[k] = invh * (v[k] - q0);
+      }
+    }
+    fdm_solve<Real>(v, ex, w, t);
+    Real *ob = udst.at(slot);
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      ob[k * 64 + t] = uu[k] + omega * (v[k] - uu[k]);
+    __syncthreads();
+  }
+}
+
+// mg_down on a level with coarser neighbours
+template <typename Real>
+__global__ void __launch_bounds__(TPB) k_down_amr(LevelView lv, const int *__restrict__ pslot,
+                                                  const int *__restrict__ oct, SlotVec<Real> u, SlotVec<Real> f,
+                                                  Real h) {
+  __shared__ Real tu[512];
+  __shared__ Real tr[512];
+  __shared__ Real halo[6][64];
+  __shared__ Real patch[6][16];
+  const int t = threadIdx.x, x = t & 7, y = t >> 3;
+  for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
+    const int slot = lv.act[b];
+    const Real *ub = u.at(slot);
+    const Real *fb = f.at(slot);
+    const int *nbr6 = lv.nbr + (size_t)b * 6;
+    Real uu[8], ff[8], tt[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      uu[k] = ub[k * 64 + t];
+      ff[k] = fb[k * 64 + t];
+      tu[k * 64 + t] = uu[k];
+    }
+    halo_amr_phase1<Real>(u, u, ub, nbr6, lv.ext + (size_t)b * 24, t, halo, patch);
+    __syncthreads();
+    halo_amr_phase2<Real>(ub, nbr6, t, halo, patch);
+    __syncthreads();
+    lap_line<Real>(tu, halo, uu, x, y, t, h, tt);
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      tr[k * 64 + t] = ff[k] - tt[k];
+    __syncthreads();
+    {
+      const int cx = t & 3, cy = (t >> 2) & 3, cz = t >> 4;
+      const int base = ((2 * cz) << 6) + ((2 * cy) << 3) + 2 * cx;
+      const Real sr = ((((((tr[base] + tr[base + 1]) + tr[base + 8]) + tr[base + 9]) + tr[base + 64]) +
+                         tr[base + 65]) + tr[base + 72]) + tr[base + 73];
+      const Real su = ((((((tu[base] + tu[base + 1]) + tu[base + 8]) + tu[base + 9]) + tu[base + 64]) +
+                         tu[base + 65]) + tu[base + 72]) + tu[base + 73];
+      const int o = oct[b], ps = pslot[b];
+      const int pidx = ((4 * (o >> 2) + cz) << 6) + ((4 * ((o >> 1) & 1) + cy) << 3) + 4 * (o & 1) + cx;
+      f.at(ps)[pidx] = sr;
+      u.at(ps)[pidx] = (Real)0.125 * su;
+    }
+    __syncthreads();
+  }
+}
+
+// out = A u on blocks sub[] of a level / of the leaf context.
+//   TAU : out += A u, us = u                      (mg_tau)
+//   FC  : leaf operator with flux correction      (k_lhs + fc_fill: coarse cells facing finer
+//         blocks get  + h_c (u_c - ghost) + sum of the 2x2 fine fluxes h_f (u_f - ghost_f) )
+//   per-block h from lv-level hblk when given (leaf context), else the level's h
+template <typename Real, bool TAU, bool FC>
+__global__ void __launch_bounds__(TPB) k_apply_amr(LevelView lv, const int *__restrict__ sub, int nsub,
+                                                   SlotVec<Real> u, SlotVec<Real> out, SlotVec<Real> us, Real hlev,
+                                                   const Real *__restrict__ hblk, const double *__restrict__ shift) {
+  __shared__ Real tu[512];
+  __shared__ Real halo[6][64];
+  __shared__ Real patch[6][16];
+  const int t = threadIdx.x, x = t & 7, y = t >> 3;
+  const int a = t & 7, c = t >> 3;
+  for (int i = blockIdx.x; i < nsub; i += gridDim.x) {
+    const int b = sub ? sub[i] : i;
+    const int slot = lv.act[b];
+    const Real *ub = u.at(slot);
+    const int *nbr6 = lv.nbr + (size_t)b * 6;
+    const int *ext24 = lv.ext + (size_t)b * 24;
+    const Real h = hblk ? hblk[b] : hlev;
+    Real uu[8], tt[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      uu[k] = ub[k * 64 + t];
+      tu[k * 64 + t] = uu[k];
+    }
+    halo_amr_phase1<Real>(u, u, ub, nbr6, ext24, t, halo, patch);
+    __syncthreads();
+    halo_amr_phase2<Real>(ub, nbr6, t, halo, patch);
+    __syncthreads();
+    lap_line<Real>(tu, halo, uu, x, y, t, h, tt);
+    Real *ob = out.at(slot);
+    if (TAU) {
+      Real *sb = us.at(slot);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        ob[k * 64 + t] += tt[k];
+        sb[k * 64 + t] = uu[k];
+      }
+    } else {
+      const Real add = shift ? (Real)(*shift) * (h * h * h) : (Real)0;
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        ob[k * 64 + t] = tt[k] + add;
+    }
+    if (FC) {
+      // flux correction at faces with finer neighbours; face order 0..5 == the reference's
+      // d = 0,1,2 loop, so a cell on an edge receives its additions in the same order
+      __syncthreads();  // ob of this block is complete (other threads' cells are updated below)
+#pragma unroll
+      for (int f = 0; f < 6; f++) {
+        if (nbr6[f] != kFine)
+          continue;
+        // this thread's face cell (a, c): own flux h (u_c - ghost)
+        const int nI = (f & 1) ? 7 : 0;
+        const int cell = face_idx(f, nI, a, c);
+        const Real Fown = h * (tu[cell] - halo[f][t]);
+        // the finer blocks' fluxes on the 2x2 fine cells facing this cell
+        Real lay[2][2][2];
+        (void)fine_avg<Real>(u, ext24 + f * 4, f, a, c, lay);
+        // their ghosts: OP_FD from MY 4x4 cells of the quadrant (a>>2, c>>2)
+        Real mine[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++)
+          mine[q] = tu[face_idx(f, nI, 4 * (a >> 2) + (q & 3), 4 * (c >> 2) + (q >> 2))];
+        const Real hf = (Real)0.5 * h;
+        Real Ff[2][2];
+#pragma unroll
+        for (int j2 = 0; j2 < 2; j2++)
+#pragma unroll
+          for (int j1 = 0; j1 < 2; j1++) {
+            const int g1 = 2 * (a & 3) + j1, g2 = 2 * (c & 3) + j2;
+            const Real gh = fd_ghost<Real>(mine, g1, g2, lay[0][j2][j1], lay[1][j2][j1]);
+            Ff[j2][j1] = hf * (lay[0][j2][j1] - gh);
+          }
+        const Real fsum = (Ff[0][0] + Ff[0][1]) + (Ff[1][0] + Ff[1][1]);  // fc_fill :3245-3246
+        ob[cell] += Fown + fsum;
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+static inline int agrid(const CupCtx *c, long long n) {
+  long long g = (long long)c->num_sms * 8;
+  return (int)(g < n ? g : (n < 1 ? 1 : n));
+}
+
+template <typename Real>
+int smooth_amr_launch(CupCtx *c, LevelView lv, SlotVec<Real> src, SlotVec<Real> can, SlotVec<Real> dst,
+                      SlotVec<Real> f, Real h, const double *fmean, bool zero_src) {
+  k_smooth_amr<Real><<<agrid(c, lv.nact), TPB, 0, c->stream>>>(lv, src, can, dst, f, (const Real *)c->d_W, h,
+                                                               (Real)(1.0 / (double)h), (Real)0.8, fmean,
+                                                               zero_src ? 1 : 0);
+  return CUP_OK;
+}
+
+template <typename Real>
+int down_amr_launch(CupCtx *c, LevelView lv, const int *pslot, const int *oct, SlotVec<Real> u, SlotVec<Real> f,
+                    Real h) {
+  k_down_amr<Real><<<agrid(c, lv.nact), TPB, 0, c->stream>>>(lv, pslot, oct, u, f, h);
+  return CUP_OK;
+}
+
+template <typename Real>
+int apply_amr_launch(CupCtx *c, LevelView lv, const int *sub, int nsub, SlotVec<Real> u, SlotVec<Real> out,
+                     SlotVec<Real> us, Real h, const void *hblk, const double *shift, int mode) {
+  if (mode == 1)
+    k_apply_amr<Real, true, false><<<agrid(c, nsub), TPB, 0, c->stream>>>(lv, sub, nsub, u, out, us, h,
+                                                                         (const Real *)hblk, shift);
+  else if (mode == 2)
+    k_apply_amr<Real, false, true><<<agrid(c, nsub), TPB, 0, c->stream>>>(lv, sub, nsub, u, out, us, h,
+                                                                         (const Real *)hblk, shift);
+  else
+    k_apply_amr<Real, false, false><<<agrid(c, nsub), TPB, 0, c->stream>>>(lv, sub, nsub, u, out, us, h,
+                                                                          (const Real *)hblk, shift);
+  return CUP_OK;
+}
+
+template int smooth_amr_launch<double>(CupCtx *, LevelView, SlotVec<double>, SlotVec<double>, SlotVec<double>,
+                                       SlotVec<double>, double, const double *, bool);
+template int smooth_amr_launch<float>(CupCtx *, LevelView, SlotVec<float>, SlotVec<float>, SlotVec<float>,
+                                      SlotVec<float>, float, const double *, bool);
+template int down_amr_launch<double>(CupCtx *, LevelView, const int *, const int *, SlotVec<double>, SlotVec<double>,
+                                     double);
+template int down_amr_launch<float>(CupCtx *, LevelView, const int *, const int *, SlotVec<float>, SlotVec<float>,
+                                    float);
+template int apply_amr_launch<double>(CupCtx *, LevelView, const int *, int, SlotVec<double>, SlotVec<double>,
+                                      SlotVec<double>, double, const void *, const double *, int);
+template int apply_amr_launch<float>(CupCtx *, LevelView, const int *, int, SlotVec<float>, SlotVec<float>,
+                                     SlotVec<float>, float, const void *, const double *, int);
+
+}  // namespace cup

@@ -32,7 +32,7 @@ void set_error(const char *fmt, ...);
 
 // neighbour codes: >= 0 local slot; NBR_WALL; NBR_COARSE (AMR); <= NBR_REMOTE0: face
 // number (NBR_REMOTE0 - code) of the level's received-face buffer (owned by another rank)
-enum { NBR_WALL = -1, NBR_COARSE = -2, NBR_REMOTE0 = -3 };
+enum { NBR_WALL = -1, NBR_COARSE = -2, NBR_REMOTE0 = -3, NBR_FINE = -2147483647 - 1 };
 
 // One multigrid level == one AMR level (reference: struct Lvl, main.c:4443).
 // "active" blocks are those whose level == L in that level's context: leaves
@@ -44,11 +44,15 @@ struct Level {
   double h = 0;
   std::vector<int> act;    // [nact] slot of each active block
   std::vector<int> ijk;    // [nact][3] block index at this level (host only)
-  std::vector<int> nbr;    // [nact][6] slot of -x,+x,-y,+y,-z,+z neighbour, NBR_WALL / NBR_COARSE
+  std::vector<int> nbr;    // [nact][6] slot of -x,+x,-y,+y,-z,+z neighbour, NBR_WALL / NBR_COARSE / NBR_FINE
+  std::vector<int> ext;    // [nact][6][4] coarse-fine faces: {coarse slot, quadrant} or the 4 finer slots
+  std::vector<double> hblk;  // [nact] cell size per block (leaf context only; MG levels share v.h)
   std::vector<int> pslot;  // [nact] slot of the parent (level L-1), L >= 1
   std::vector<int> oct;    // [nact] octant inside the parent, (ix&1)+2(iy&1)+4(iz&1)
   std::vector<int> par;    // [npar] indices into act[] of blocks that are synthesised parents
   int *d_act = nullptr, *d_nbr = nullptr, *d_pslot = nullptr, *d_oct = nullptr, *d_par = nullptr;
+  int *d_ext = nullptr;
+  void *d_hblk = nullptr;  // Real [nact]
   bool uniform = true;     // no NBR_COARSE entries
   long long gnact = 0;     // active blocks of this level over all ranks
   // ---- multi-rank plans (empty on one rank) ----
@@ -95,6 +99,7 @@ struct HostMesh {
   bool leaf_uniform = true;
   std::vector<CupBlk> blk;
   std::vector<Level> lv;
+  Level leafv;  // ALL local leaves (every level) with their neighbours: context of pois_op and the stencil sweeps
 };
 
 struct Krylov;
@@ -122,6 +127,7 @@ struct CupCtx {
   int level_max = 1;
   std::vector<CupBlk> blk;
   std::vector<cup::Level> lv;   // index = level
+  cup::Level leafv;             // all leaves (multi-level meshes); on single-level meshes == lv[finest]
   bool leaf_uniform = true;     // all leaves on one level (fast stencil path)
   // device state: 9 components, each [nblk][512] Real
   void *state[CUP_F_N] = {nullptr};
@@ -140,6 +146,7 @@ struct CupCtx {
   void *p_old = nullptr;        // projection(): previous pressure
   void *graph_cache = nullptr;  // captured V-cycles keyed by (in, out) (mg_kernels.cu)
   void *tma_cache = nullptr;    // tensor-map cache (smooth_tma.cu)
+  bool no_flux_correction = false;  // st_mg on the leaves (stencil_apply(CUP_ST_MG)): k_mg has no flux faces
   bool keep_tmp_udef = false;   // projection(): F_TMP already holds fish_tmpv()'s udef
 };
 

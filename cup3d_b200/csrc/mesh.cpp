@@ -129,10 +129,90 @@ int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner_
   m->nblk = (long long)m->blk.size();
   long long lnslot = m->nblk;
 
+  // ---- leaf context: every local leaf with its six face neighbours (same level, wall,
+  // one coarser leaf, or four finer leaves).  Context of pois_op and the stencil sweeps on
+  // multi-level meshes (the reference's top-level mesh: lab_load :3579-3602).
+  {
+    Level &lf = m->leafv;
+    lf = Level();
+    lf.L = lmax;
+    lf.h = 0;
+    lf.gnact = G;
+    if (!m->leaf_uniform) {
+      std::unordered_map<uint64_t, int> map;
+      map.reserve((size_t)G * 2);
+      for (long long i = 0; i < G; i++)
+        map.emplace(key_of(gblk[i].level, gblk[i].ix, gblk[i].iy, gblk[i].iz), (int)i);
+      for (long long i = 0; i < G; i++) {
+        if (owner[i] != rank)
+          continue;
+        const CupBlk &b = gblk[i];
+        const int L = b.level;
+        const int dim[3] = {bpd[0] << L, bpd[1] << L, bpd[2] << L};
+        const int idx[3] = {b.ix, b.iy, b.iz};
+        lf.act.push_back(g2l[i]);
+        lf.hblk.push_back(b.h);
+        for (int f = 0; f < 6; f++) {
+          const int d = f / 2, s = (f & 1) ? 1 : -1, t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
+          int q[3] = {idx[0], idx[1], idx[2]};
+          q[d] += s;
+          int code = NBR_WALL, e4[4] = {-1, -1, -1, -1};
+          if (q[d] >= 0 && q[d] < dim[d]) {
+            auto it = map.find(key_of(L, q[0], q[1], q[2]));
+            if (it != map.end()) {
+              code = it->second;
+            } else if (L > 0 && (it = map.find(key_of(L - 1, q[0] / 2, q[1] / 2, q[2] / 2))) != map.end()) {
+              code = NBR_COARSE;
+              e4[0] = it->second;
+              e4[1] = (idx[t1] & 1) + 2 * (idx[t2] & 1);
+            } else {
+              code = NBR_FINE;
+              for (int qd = 0; qd < 4; qd++) {
+                int cc[3];
+                cc[d] = 2 * q[d] + (s > 0 ? 0 : 1);
+                cc[t1] = 2 * q[t1] + (qd & 1);
+                cc[t2] = 2 * q[t2] + (qd >> 1);
+                auto jf = map.find(key_of(L + 1, cc[0], cc[1], cc[2]));
+                if (jf == map.end()) {
+                  set_error("leaf level %d (%d,%d,%d): face %d has no neighbour at levels %d..%d (2:1 balance broken)",
+                            L, b.ix, b.iy, b.iz, f, L - 1, L + 1);
+                  return CUP_ERR_MESH;
+                }
+                e4[qd] = jf->second;
+              }
+            }
+          }
+          if (code >= 0 || code == NBR_COARSE || code == NBR_FINE) {
+            // global -> local slots (multi-level meshes are single-rank for now)
+            int *pp[5] = {&code, &e4[0], &e4[1], &e4[2], &e4[3]};
+            for (int z = 0; z < 5; z++) {
+              if (z == 0 && code < 0)
+                continue;
+              if (z == 2 && code == NBR_COARSE)
+                continue;  // quadrant, not a slot
+              if (*pp[z] < 0)
+                continue;
+              if (owner[*pp[z]] != rank) {
+                set_error("multi-level meshes are single-rank in this build");
+                return CUP_ERR_UNSUPPORTED;
+              }
+              *pp[z] = g2l[*pp[z]];
+            }
+          }
+          lf.nbr.push_back(code);
+          for (int z = 0; z < 4; z++)
+            lf.ext.push_back(e4[z]);
+        }
+      }
+      lf.uniform = false;
+    }
+  }
+
   // ---- global hierarchy, finest to coarsest ------------------------------
   struct GLevel {
     std::vector<Ent> act;          // global active list (global order)
-    std::vector<int> nbr;          // [n][6] global slot / NBR_WALL / NBR_COARSE
+    std::vector<int> nbr;          // [n][6] global slot / NBR_WALL / NBR_COARSE / NBR_FINE
+    std::vector<int> ext;          // [n][6][4] global slots of the coarse / 4 fine neighbours
     std::vector<int> pg;           // parent global slot
   };
   std::vector<GLevel> gl(m->top + 1);
@@ -150,6 +230,7 @@ int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner_
         g.act.push_back(e);
     const size_t na = g.act.size();
     g.nbr.assign(na * 6, NBR_WALL);
+    g.ext.assign(na * 24, -1);
     const int dim[3] = {bpd[0] << L, bpd[1] << L, bpd[2] << L};
     for (size_t k = 0; k < na; k++) {
       const Ent &e = g.act[k];
@@ -165,11 +246,17 @@ int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner_
           g.nbr[k * 6 + f] = it->second;
         } else {
           // must be covered by a coarser leaf (2:1 balance): check its presence
-          if (L == 0 || map.find(key_of(L - 1, q[0] / 2, q[1] / 2, q[2] / 2)) == map.end()) {
+          auto ic = L == 0 ? map.end() : map.find(key_of(L - 1, q[0] / 2, q[1] / 2, q[2] / 2));
+          if (ic == map.end()) {
             set_error("level %d block (%d,%d,%d): face %d neighbour missing", L, e.ix, e.iy, e.iz, f);
             return CUP_ERR_MESH;
           }
           g.nbr[k * 6 + f] = NBR_COARSE;
+          // which quadrant of the coarse block's face this block touches: parity of its own
+          // index in the two tangential directions (lower dimension first)
+          const int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
+          g.ext[(k * 6 + f) * 4 + 0] = ic->second;
+          g.ext[(k * 6 + f) * 4 + 1] = (idx[t1] & 1) + 2 * (idx[t2] & 1);
         }
       }
     }
@@ -267,8 +354,18 @@ int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner_
         int code;
         if (gn == NBR_WALL || gn == NBR_COARSE) {
           code = gn;
-          if (gn == NBR_COARSE)
+          if (gn == NBR_COARSE) {
             v.uniform = false;
+            const int gc = g.ext[(k * 6 + f) * 4];
+            if (owner[gc] != rank) {
+              set_error("coarse-fine interface across ranks (level %d): multi-level meshes are single-rank in this build", L);
+              return CUP_ERR_UNSUPPORTED;
+            }
+            if (v.ext.size() < v.nbr.size() * 4 + 4)
+              v.ext.resize((size_t)(v.nbr.size() + 1) * 4, -1);
+            v.ext[v.nbr.size() * 4 + 0] = g2l[gc];
+            v.ext[v.nbr.size() * 4 + 1] = g.ext[(k * 6 + f) * 4 + 1];
+          }
         } else if (owner[gn] == rank) {
           code = g2l[gn];
         } else {
@@ -374,6 +471,8 @@ int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner_
       v.res_scnt.assign(nranks, 0);
       v.res_rcnt.assign(nranks, 0);
     }
+    if (!v.uniform)
+      v.ext.resize(v.nbr.size() * 4, -1);
     // par[]: indices (into act[]) of synthesised parents, i.e. local slot >= nblk
     for (size_t k = 0; k < v.act.size(); k++)
       if (v.act[k] >= m->nblk)
@@ -435,6 +534,8 @@ void free_mesh(CupCtx *c) {
     cudaFree(v.d_pslot);
     cudaFree(v.d_oct);
     cudaFree(v.d_par);
+    cudaFree(v.d_ext);
+    cudaFree(v.d_hblk);
     cudaFree(v.d_inner);
     cudaFree(v.d_bnd);
     cudaFree(v.d_face_sslot);
@@ -443,6 +544,14 @@ void free_mesh(CupCtx *c) {
     cudaFree(v.d_res_roct);
   }
   c->lv.clear();
+  {
+    Level &v = c->leafv;
+    cudaFree(v.d_act);
+    cudaFree(v.d_nbr);
+    cudaFree(v.d_ext);
+    cudaFree(v.d_hblk);
+    v = Level();
+  }
   c->blk.clear();
   c->nblk = c->nslot = 0;
   c->top = -1;
@@ -458,6 +567,7 @@ int build_mesh(CupCtx *c, const CupBlk *gblk, long long G, const int *owner, con
   }
   c->blk.swap(m.blk);
   c->lv.swap(m.lv);
+  c->leafv = m.leafv;
   c->win_reals.swap(m.win_reals);
   c->nblk = m.nblk;
   c->nslot = m.nslot;
@@ -475,12 +585,27 @@ int build_mesh(CupCtx *c, const CupBlk *gblk, long long G, const int *owner, con
     CUP_TRY(upload(&v.d_pslot, v.pslot));
     CUP_TRY(upload(&v.d_oct, v.oct));
     CUP_TRY(upload(&v.d_par, v.par));
+    CUP_TRY(upload(&v.d_ext, v.ext));
     CUP_TRY(upload(&v.d_inner, v.inner));
     CUP_TRY(upload(&v.d_bnd, v.bnd));
     CUP_TRY(upload(&v.d_face_sslot, v.face_sslot));
     CUP_TRY(upload(&v.d_face_splane, v.face_splane));
     CUP_TRY(upload(&v.d_res_rslot, v.res_rslot));
     CUP_TRY(upload(&v.d_res_roct, v.res_roct));
+  }
+  {
+    Level &v = c->leafv;
+    CUP_TRY(upload(&v.d_act, v.act));
+    CUP_TRY(upload(&v.d_nbr, v.nbr));
+    CUP_TRY(upload(&v.d_ext, v.ext));
+    if (!v.hblk.empty()) {
+      if (c->real_bytes == 8) {
+        CUP_TRY(upload((double **)&v.d_hblk, v.hblk));
+      } else {
+        std::vector<float> hf(v.hblk.begin(), v.hblk.end());
+        CUP_TRY(upload((float **)&v.d_hblk, hf));
+      }
+    }
   }
   return CUP_OK;
 }

@@ -15,7 +15,7 @@ namespace cup {
 
 enum { TPB = 64 };  // threads per 8^3 block
 // neighbour codes (cup_internal.h): >= 0 local slot, -1 wall, <= kRemote0 received face number
-enum { kWall = -1, kCoarse = -2, kRemote0 = -3 };
+enum { kWall = -1, kCoarse = -2, kRemote0 = -3, kFine = -2147483647 - 1 };
 
 // slot -> pointer.  Slots below nleaf are leaves and live in the caller's flat
 // vector (block-index order); the rest are synthesised multigrid parents and
@@ -44,6 +44,9 @@ struct LevelView {
   // exchange counter (device memory, so a captured CUDA graph stays valid on replay)
   const unsigned long long *seq;
   long long rface_stride;  // Reals between the two copies
+  // coarse-fine interfaces (AMR): ext[k][6][4] -- kCoarse: {coarse slot, quadrant of its face};
+  // kFine: the four finer blocks across the face, quadrant-major (a/4 + 2*(c/4))
+  const int *ext;
 };
 
 template <typename Real>
@@ -174,6 +177,121 @@ __device__ __forceinline__ void load_halo(const SlotVec<Real> &u, const Real *ow
       idx = (p << 6) + t;
     halo[f][t] = src[idx];
   }
+}
+
+// ---------------------------------------------------------------------------
+// Coarse-fine ghost faces (reference: lab_load :3544 + lab_exec :3401 with the
+// tables of gen_table.py for ss = 1, non-tensorial stencils, where only the six
+// faces matter).
+//
+//  * finer neighbours: ghost = 0.125 * sum of the 2x2x2 fine cells (OP_AVG8, fine())
+//  * coarser neighbour: OP_FD -- one-sided / centred quadratic interpolation in the two
+//    tangential directions on the 4x4 coarse cells facing this block, plus a mixed term,
+//    blended with the block's own first two interior cells: (8 v + 10 b - 3 c) / 15.
+// Plane element (a, c) and plane order as in load_halo.
+// ---------------------------------------------------------------------------
+extern __constant__ double cFDp[9], cFDm[9];  // d_coef_plus / d_coef_minus, main.c:3371-3374
+
+// index inside a block of the cell with normal coordinate n (direction d = f/2) and tangential (a, c)
+__device__ __forceinline__ int face_idx(int f, int n, int a, int c) {
+  return f < 2 ? (c << 6) + (a << 3) + n : (f < 4 ? (c << 6) + (n << 3) + a : (n << 6) + (c << 3) + a);
+}
+
+// phase 1 (before a __syncthreads): threads 0..15 fetch the 4x4 coarse cells facing this block
+template <typename Real>
+__device__ __forceinline__ void coarse_patch_load(const Real *cblk, int f, int quad, int t, Real *patch16) {
+  if (t < 16) {
+    const int q1 = (t & 3) + 4 * (quad & 1), q2 = (t >> 2) + 4 * (quad >> 1);
+    patch16[t] = cblk[face_idx(f, (f & 1) ? 0 : 7, q1, q2)];
+  }
+}
+
+// OP_FD (main.c:3465-3521) for fine plane element (a, c); bb / cq = the fine block's first and
+// second interior cell behind that element; patch = 4x4 coarse cells, index C1 + 4*C2
+template <typename Real>
+__device__ __forceinline__ Real fd_ghost(const Real *patch, int a, int c, Real bb, Real cq) {
+  const int C1 = a >> 1, C2 = c >> 1;
+  const double d1 = 0.25 * (2 * (a & 1) - 1), d2 = 0.25 * (2 * (c & 1) - 1);
+  const double *c1 = d1 > 0 ? cFDp : cFDm, *c2 = d2 > 0 ? cFDp : cFDm;
+  const Real *p0 = patch + C1 + 4 * C2;
+  double mixed_coef = 1.0;
+  int P1, M1, P2, M2;
+  Real x1, x2;
+  if (C1 != 0 && C1 != 3) {
+    x1 = (c1[6] * p0[-1] + c1[8] * p0[1]) + c1[7] * p0[0];
+    P1 = 1;
+    M1 = -1;
+    mixed_coef *= 0.5;
+  } else if (C1 == 0) {
+    x1 = (c1[0] * p0[2] + c1[1] * p0[1]) + c1[2] * p0[0];
+    P1 = 1;
+    M1 = 0;
+  } else {
+    x1 = (c1[3] * p0[-2] + c1[4] * p0[-1]) + c1[5] * p0[0];
+    P1 = 0;
+    M1 = -1;
+  }
+  if (C2 != 0 && C2 != 3) {
+    x2 = (c2[6] * p0[-4] + c2[8] * p0[4]) + c2[7] * p0[0];
+    P2 = 4;
+    M2 = -4;
+    mixed_coef *= 0.5;
+  } else if (C2 == 0) {
+    x2 = (c2[0] * p0[8] + c2[1] * p0[4]) + c2[2] * p0[0];
+    P2 = 4;
+    M2 = 0;
+  } else {
+    x2 = (c2[3] * p0[-8] + c2[4] * p0[-4]) + c2[5] * p0[0];
+    P2 = 0;
+    M2 = -4;
+  }
+  const Real mixed = mixed_coef * d1 * d2 * ((p0[M1 + M2] + p0[P1 + P2]) - (p0[P1 + M2] + p0[M1 + P2]));
+  const Real v = (x1 + x2) + mixed;
+  return (Real)(1.0 / 15.0) * ((Real)8.0 * v + ((Real)10.0 * bb - (Real)3.0 * cq));
+}
+
+// OP_AVG8 ghost of plane element (a, c) from the four finer blocks across face f.  The 2x2x2
+// cluster is summed in the table's order (x outermost, z innermost; gen_table.py fine()).
+// Also returns the cluster's two layers: lay[0] = cells touching the face, lay[1] = one behind,
+// each [j2][j1] over the 2x2 fine tangential cells (needed by the flux correction).
+template <typename Real>
+__device__ __forceinline__ Real fine_avg(const SlotVec<Real> &u, const int *ext4, int f, int a, int c,
+                                         Real (&lay)[2][2][2]) {
+  const Real *fb = u.at(ext4[(a >> 2) + 2 * (c >> 2)]);
+  const int g1 = 2 * (a & 3), g2 = 2 * (c & 3);
+  const int n0 = (f & 1) ? 0 : 7, n1 = (f & 1) ? 1 : 6;
+#pragma unroll
+  for (int j2 = 0; j2 < 2; j2++)
+#pragma unroll
+    for (int j1 = 0; j1 < 2; j1++) {
+      lay[0][j2][j1] = fb[face_idx(f, n0, g1 + j1, g2 + j2)];
+      lay[1][j2][j1] = fb[face_idx(f, n1, g1 + j1, g2 + j2)];
+    }
+  // cluster cell (dx,dy,dz) relative to its lowest corner, in block coordinates
+  Real s = 0;
+  bool first = true;
+#pragma unroll
+  for (int dx = 0; dx < 2; dx++)
+#pragma unroll
+    for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+      for (int dz = 0; dz < 2; dz++) {
+        // normal offset dn (0 = lower coordinate) and tangential offsets of this cluster cell
+        int dn, j1, j2;
+        if (f < 2) {
+          dn = dx; j1 = dy; j2 = dz;
+        } else if (f < 4) {
+          dn = dy; j1 = dx; j2 = dz;
+        } else {
+          dn = dz; j1 = dx; j2 = dy;
+        }
+        // lower normal coordinate is the second layer for a -dir neighbour (cells 6,7), the first for +dir (0,1)
+        const int layer = (f & 1) ? dn : 1 - dn;
+        const Real val = lay[layer][j2][j1];
+        s = first ? val : s + val;
+        first = false;
+      }
+  return (Real)0.125 * s;
 }
 
 // Sum of the ghost values adjacent to cell (x, y, k) (zero for interior cells).

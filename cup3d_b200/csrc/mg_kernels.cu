@@ -17,6 +17,7 @@
 #include "mg_device.cuh"
 #include "smooth_tma.cuh"
 #include "stencil7_tma.cuh"
+#include "amr_kernels.cuh"
 #include "comm.cuh"
 
 namespace cup {
@@ -304,7 +305,7 @@ struct Arr {
 
 inline LevelView view(const Level &v) {
   return LevelView{v.d_act, v.d_nbr, (int)v.act.size(), v.d_frecv, (const unsigned long long *)v.d_seq,
-                   v.rface_stride};
+                   v.rface_stride, v.d_ext};
 }
 
 inline int grid_for(const CupCtx *c, long long nwork, int per_sm) {
@@ -388,8 +389,19 @@ int smooth_level(CupCtx *c, Level &v, int n, Arr<Real> &a, bool first_is_zero, c
   if (n == 0 || (v.act.empty() && v.gnact == 0))
     return CUP_OK;
   if (!v.uniform) {
-    set_error("multigrid level %d has coarse-fine interfaces: AMR smoother not available in this build", v.L);
-    return CUP_ERR_UNSUPPORTED;
+    // level with coarser neighbours (AMR): generic ghost fill; coarser leaves are read from U0
+    if (n & 1) {
+      set_error("odd smoothing count %d not supported (ping-pong)", n);
+      return CUP_ERR_UNSUPPORTED;
+    }
+    for (int it = 0; it < n; it++) {
+      SlotVec<Real> &src = (it & 1) ? a.u1 : a.u0;
+      SlotVec<Real> &dst = (it & 1) ? a.u0 : a.u1;
+      CUP_TRY(smooth_amr_launch<Real>(c, view(v), src, a.u0, dst, a.f, (Real)v.h, fmean, it == 0 && first_is_zero));
+      c->launches++;
+    }
+    CUP_CUDA(cudaGetLastError());
+    return CUP_OK;
   }
   const int grid = grid_for(c, (long long)v.act.size(), smooth_use_tma() ? smooth_per_sm() : 16);
   const Real h = (Real)v.h, invh = (Real)(1.0 / v.h), om = (Real)0.8;  // mg_omega, main.c:4434
@@ -495,8 +507,8 @@ int vcycle_t(CupCtx *c, const Real *d_in, Real *d_out) {
   while (top > 0 && c->lv[top].gnact == 0)
     top--;
   if (!c->leaf_uniform) {
-    set_error("mg_vcycle on a multi-level mesh is not available in this build");
-    return CUP_ERR_UNSUPPORTED;
+    // coarser leaves are read as neighbours before their own level is visited: u = 0 (vec_zero, :4834)
+    CUP_CUDA(cudaMemsetAsync(d_out, 0, (size_t)c->nblk * 512 * sizeof(Real), c->stream));
   }
   for (int L = top; L >= 1; L--) {
     Level &v = c->lv[L];
@@ -507,7 +519,9 @@ int vcycle_t(CupCtx *c, const Real *d_in, Real *d_out) {
     CUP_TRY(halo_wait(c, v));  // faces of u0 were posted by the last sweep
     if (!v.act.empty()) {
       const int grid = grid_for(c, (long long)v.act.size(), 12);
-      if (smooth_use_tma())
+      if (!v.uniform)
+        CUP_TRY(down_amr_launch<Real>(c, view(v), v.d_pslot, v.d_oct, a.u0, a.f, (Real)v.h));
+      else if (smooth_use_tma())
         CUP_TRY(down_tma_launch<Real>(c, view(v), v.d_pslot, v.d_oct, a.u0, a.f, (Real)v.h, v.d_rptr));
       else
         k_down<Real><<<grid, TPB, 0, c->stream>>>(view(v), v.d_pslot, v.d_oct, a.u0, a.f, (Real)v.h,
@@ -521,7 +535,10 @@ int vcycle_t(CupCtx *c, const Real *d_in, Real *d_out) {
     CUP_TRY(halo_wait(c, w));
     if (!w.par.empty()) {
       const int gridw = grid_for(c, (long long)w.par.size(), 12);
-      if (smooth_use_tma())
+      if (!w.uniform)
+        CUP_TRY(apply_amr_launch<Real>(c, view(w), w.d_par, (int)w.par.size(), a.u0, a.f, a.us, (Real)w.h, nullptr,
+                                       nullptr, 1));
+      else if (smooth_use_tma())
         CUP_TRY(apply_tma_launch<Real>(c, view(w), w.d_par, (int)w.par.size(), a.u0, a.f, a.us, (Real)w.h, nullptr,
                                        (Real)0, true));
       else
@@ -610,14 +627,10 @@ __global__ void k_pin(const Real *in, Real *out, long long off, const double *av
 
 template <typename Real>
 int pois_op_t(CupCtx *c, const Real *d_in, Real *d_out) {
-  if (!c->leaf_uniform) {
-    set_error("pois_op on a multi-level mesh is not available in this build");
-    return CUP_ERR_UNSUPPORTED;
-  }
   int top = c->top;
   while (top > 0 && c->lv[top].gnact == 0)
     top--;
-  Level &v = c->lv[top];
+  Level &v = c->leaf_uniform ? c->lv[top] : c->leafv;
   const int mc = c->prm.mean_constraint;
   const double *shift = nullptr;
   double *q = c->d_scal + 1;
@@ -633,7 +646,10 @@ int pois_op_t(CupCtx *c, const Real *d_in, Real *d_out) {
   SlotVec<Real> u{const_cast<Real *>(d_in), nullptr, nleaf}, o{d_out, nullptr, nleaf}, us{nullptr, nullptr, nleaf};
   CUP_TRY(halo_exchange<Real>(c, v, u));
   const Real h = (Real)v.h;
-  if (smooth_use_tma())
+  if (!c->leaf_uniform)  // k_lhs + fc_fill on all leaves, per-block h
+    CUP_TRY(apply_amr_launch<Real>(c, view(v), nullptr, (int)v.act.size(), u, o, us, h, v.d_hblk, shift,
+                                   c->no_flux_correction ? 0 : 2));
+  else if (smooth_use_tma())
     CUP_TRY(apply_tma_launch<Real>(c, view(v), nullptr, (int)v.act.size(), u, o, us, h, shift, h * h * h, false));
   else
     k_apply<Real, false><<<grid_for(c, c->nblk, 16), TPB, 0, c->stream>>>(view(v), nullptr, (int)v.act.size(), u, o,
@@ -653,6 +669,7 @@ int pois_op_t(CupCtx *c, const Real *d_in, Real *d_out) {
 }  // namespace
 
 int mg_setup(CupCtx *c) {
+  CUP_TRY(amr_setup_constants());
   // FDM constants exactly as pois_init computes them (main.c:4322-4334)
   const int BS = 8;
   double lam[8], S[8][8];

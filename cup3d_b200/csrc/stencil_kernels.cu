@@ -340,7 +340,7 @@ int need_uniform(CupCtx *c, const char *what) {
 template <typename Real>
 int stencil_t(CupCtx *c, CupStencilId id, const int *d_sub, long long nsub) {
   const Level &v = *leaf_level(c);
-  LevelView lv{v.d_act, v.d_nbr, (int)v.act.size(), v.d_frecv, (const unsigned long long *)v.d_seq, v.rface_stride};
+  LevelView lv{v.d_act, v.d_nbr, (int)v.act.size(), v.d_frecv, (const unsigned long long *)v.d_seq, v.rface_stride, v.d_ext};
   if (c->nranks > 1 && id != CUP_ST_LHS && id != CUP_ST_MG) {
     set_error("stencil sweeps other than LHS/MG are single-rank in this build");
     return CUP_ERR_UNSUPPORTED;
@@ -382,10 +382,13 @@ int stencil_t(CupCtx *c, CupStencilId id, const int *d_sub, long long nsub) {
   }
   case CUP_ST_LHS:
   case CUP_ST_MG: {
-    // k_lhs / k_mg on the state: F_PRES -> F_LHS, no mean term (that is pois_op's)
+    // k_lhs / k_mg on the state: F_PRES -> F_LHS, no mean term (that is pois_op's); st_mg has no
+    // flux faces (outc = 0, main.c:4280)
     const int mc = c->prm.mean_constraint;
     c->prm.mean_constraint = 0;
+    c->no_flux_correction = (id == CUP_ST_MG);
     int rc = pois_op_dev(c, S[CUP_F_PRES], S[CUP_F_LHS]);
+    c->no_flux_correction = false;
     c->prm.mean_constraint = mc;
     return rc;
   }
@@ -469,7 +472,12 @@ int projection_t(CupCtx *c, CupSolveInfo *info) {
 }  // namespace
 
 int stencil_run(CupCtx *c, CupStencilId id, const long long *list, long long n) {
-  CUP_TRY(need_uniform(c, "stencil_run"));
+  if (id != CUP_ST_LHS && id != CUP_ST_MG)
+    CUP_TRY(need_uniform(c, "stencil_run (sweeps other than LHS/MG)"));
+  if (c->nblk == 0) {
+    set_error("stencil_run: no mesh uploaded");
+    return CUP_ERR_STATE;
+  }
   if (list != nullptr && n != c->nblk) {
     set_error("stencil_run: block sub-lists are not supported yet (n=%lld of %lld)", n, c->nblk);
     return CUP_ERR_UNSUPPORTED;

@@ -1,0 +1,87 @@
+"""GPU parity on MULTI-LEVEL (AMR) meshes produced by the reference's own
+mesh_adapt: ghost faces from coarser leaves (OP_FD interpolation), from finer
+leaves (OP_AVG8) and the flux correction at coarse-fine faces (fc_fill), inside
+pois_op, k_lhs, the V-cycle (levels with pass-through leaves) and the full
+solve.  Goldens: tests/golden/amr2.npz (2 levels), amr3.npz (3 levels)."""
+import numpy as np
+import pytest
+
+from util import AMR_CASES, case, relerr
+from cup3d_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+
+def make_ctx(c, **params):
+    import cup3d_b200
+    ctx = cup3d_b200.Context(0, 8)
+    ctx.mesh_upload(c.ib, c.rb, c.bpd, c.level_max)
+    ctx.set_params(dt=c.dt, nu=c.nu, uinf=c.uinf, step=5, mean_constraint=2, **params)
+    return ctx
+
+
+@pytest.mark.parametrize("name", AMR_CASES)
+def test_amr_levels(built, name):
+    c = case(name)
+    ctx = make_ctx(c)
+    counts = np.bincount(c.ib[:, 0], minlength=c.level_max)
+    finest = int(np.max(c.ib[:, 0]))
+    assert ctx.mg_nact(finest) == counts[finest]
+    # every coarser level = its own leaves + one parent per 8 blocks of the level above
+    n_above = counts[finest]
+    for L in range(finest - 1, -1, -1):
+        assert ctx.mg_nact(L) == counts[L] + n_above // 8
+        n_above = ctx.mg_nact(L)
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", AMR_CASES)
+def test_amr_pois_op(built, name):
+    c = case(name)
+    for mc in (0, 2):
+        key = "op_out_mc%d" % mc
+        if key not in c.g:
+            continue
+        ctx = make_ctx(c)
+        ctx.set_params(mean_constraint=mc)
+        out = ctx.pois_op(np.ascontiguousarray(c.F["pres"]))
+        e = relerr(out, c.g[key])
+        assert e < 1e-12, (mc, e)
+        ctx.close()
+
+
+def test_amr_k_lhs_with_flux_correction(built):
+    c = case("amr2")
+    ctx = make_ctx(c)
+    s0 = c.state0()
+    ctx.state_h2d(s0)
+    ctx.stencil_apply(capi.ST_LHS)
+    out = np.zeros_like(s0)
+    ctx.state_d2h(out)
+    assert relerr(out[:, 8:9], c.g["st_lhs"]) < 1e-12
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", AMR_CASES)
+def test_amr_vcycle(built, name):
+    c = case(name)
+    ctx = make_ctx(c)
+    out = ctx.mg_vcycle(np.ascontiguousarray(c.F["cosrhs"]))
+    e = relerr(out, c.g["vc_out_cosrhs"])
+    assert e < 1e-11, e
+    ctx.close()
+
+
+def test_amr_pois_solve(built):
+    c = case("amr2")
+    ctx = make_ctx(c, ptol=1e-10, ptol_rel=1e-12)
+    st = c.state0()
+    st[:, 8] = c.solve_rhs()
+    st[:, 1] = 0
+    ctx.state_h2d(st)
+    info = ctx.pois_solve()
+    out = np.zeros_like(st)
+    ctx.state_d2h(out, 1, 1)
+    assert info.residual < max(1e-10, 1e-12 * info.rhs_norm)
+    assert relerr(out[:, 1], c.g["solve_x_mc2"]) < 1e-8
+    ctx.close()
