@@ -248,6 +248,220 @@ __global__ void __launch_bounds__(TPB) k_apply_amr(LevelView lv, const int *__re
 }
 
 // ---------------------------------------------------------------------------
+// Pressure sweeps on the leaves of a multi-level mesh: k_divp (:5700) and k_gradp (:5715)
+// with their flux correction (face_grad :4227 / face_sum :4241 + fc_fill).
+//   WHAT 0: o0 = h (sum of 6 neighbours - 6 p)             [k_divp summation order]
+//   WHAT 1: o_a = fac (p(+a) - p(-a)), fac = facs * h^2     [facs = -dt/2]
+template <typename Real, int WHAT>
+__global__ void __launch_bounds__(TPB) k_pres_amr(LevelView lv, const Real *__restrict__ hblk,
+                                                  const Real *__restrict__ p, Real *__restrict__ o0,
+                                                  Real *__restrict__ o1, Real *__restrict__ o2, Real facs) {
+  __shared__ Real tu[512];
+  __shared__ Real halo[6][64];
+  __shared__ Real patch[6][16];
+  const int t = threadIdx.x, x = t & 7, y = t >> 3, a = t & 7, c = t >> 3;
+  SlotVec<Real> pv{const_cast<Real *>(p), nullptr, 0x7fffffff};
+  Real *outs[3] = {o0, o1, o2};
+  for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
+    const size_t own = (size_t)lv.act[b] * 512;
+    const int *nbr6 = lv.nbr + (size_t)b * 6;
+    const int *ext24 = lv.ext + (size_t)b * 24;
+    const Real h = hblk[b];
+    const Real fac = WHAT == 0 ? h : facs * h * h;
+    Real uu[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      uu[k] = p[own + k * 64 + t];
+      tu[k * 64 + t] = uu[k];
+    }
+    halo_amr_phase1<Real>(pv, pv, p + own, nbr6, ext24, t, halo, patch);
+    __syncthreads();
+    halo_amr_phase2<Real>(p + own, nbr6, t, halo, patch);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int i = k * 64 + t;
+      const Real xm = x > 0 ? tu[i - 1] : halo[0][y + 8 * k];
+      const Real xp = x < 7 ? tu[i + 1] : halo[1][y + 8 * k];
+      const Real ym = y > 0 ? tu[i - 8] : halo[2][x + 8 * k];
+      const Real yp = y < 7 ? tu[i + 8] : halo[3][x + 8 * k];
+      const Real zm = k > 0 ? uu[k > 0 ? k - 1 : 0] : halo[4][t];
+      const Real zp = k < 7 ? uu[k < 7 ? k + 1 : 7] : halo[5][t];
+      if (WHAT == 0) {
+        o0[own + i] = fac * ((((((xp + xm) + yp) + ym) + zp) + zm) - (Real)6.0 * uu[k]);
+      } else {
+        o0[own + i] = fac * (xp - xm);
+        o1[own + i] = fac * (yp - ym);
+        o2[own + i] = fac * (zp - zm);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int f = 0; f < 6; f++) {
+      if (nbr6[f] != kFine)
+        continue;
+      const int nI = (f & 1) ? 7 : 0;
+      const int cell = face_idx(f, nI, a, c);
+      Real lay[2][2][2], mine[16];
+      (void)fine_avg<Real>(pv, ext24 + f * 4, f, a, c, lay);
+#pragma unroll
+      for (int q = 0; q < 16; q++)
+        mine[q] = tu[face_idx(f, nI, 4 * (a >> 2) + (q & 3), 4 * (c >> 2) + (q >> 2))];
+      const Real hf = (Real)0.5 * h;
+      Real Fown, Ff[2][2];
+      if (WHAT == 0) {
+        Fown = fac * (tu[cell] - halo[f][t]);  // face_grad: coef (c - n)
+      } else {
+        const Real sgn = (f & 1) ? -fac : fac;  // face_sum: s (n + c)
+        Fown = sgn * (halo[f][t] + tu[cell]);
+      }
+#pragma unroll
+      for (int j2 = 0; j2 < 2; j2++)
+#pragma unroll
+        for (int j1 = 0; j1 < 2; j1++) {
+          const Real gh = fd_ghost<Real>(mine, 2 * (a & 3) + j1, 2 * (c & 3) + j2, lay[0][j2][j1], lay[1][j2][j1]);
+          if (WHAT == 0) {
+            Ff[j2][j1] = hf * (lay[0][j2][j1] - gh);
+          } else {
+            const Real facf = facs * hf * hf;
+            const Real sf = ((f ^ 1) & 1) ? -facf : facf;  // the fine block's face is f^1
+            Ff[j2][j1] = sf * (gh + lay[0][j2][j1]);
+          }
+        }
+      const Real fsum = (Ff[0][0] + Ff[0][1]) + (Ff[1][0] + Ff[1][1]);
+      Real *o = WHAT == 0 ? o0 : outs[f >> 1];
+      o[own + cell] += Fown + fsum;
+      __syncthreads();
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// k_prhs (:5663) on the leaves of a multi-level mesh, with flux correction.
+// Only the face-normal components are needed on each face (u, udef_x on x faces, ...).
+template <typename Real>
+__global__ void __launch_bounds__(TPB) k_prhs_amr(LevelView lv, const Real *__restrict__ hblk,
+                                                  const Real *__restrict__ v0, const Real *__restrict__ v1,
+                                                  const Real *__restrict__ v2, const Real *__restrict__ d0,
+                                                  const Real *__restrict__ d1, const Real *__restrict__ d2,
+                                                  const Real *__restrict__ chi, Real *__restrict__ lhs, Real idt2) {
+  __shared__ Real tl[6][512];     // u v w udef_x udef_y udef_z cores
+  __shared__ Real hl[2][6][64];   // [vel / udef][face]: ghost plane of the face-normal component
+  __shared__ Real patch[2][6][16];
+  const int t = threadIdx.x, x = t & 7, y = t >> 3, a = t & 7, c = t >> 3;
+  const Real *comp[6] = {v0, v1, v2, d0, d1, d2};
+  for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
+    const size_t own = (size_t)lv.act[b] * 512;
+    const int *nbr6 = lv.nbr + (size_t)b * 6;
+    const int *ext24 = lv.ext + (size_t)b * 24;
+    const Real h = hblk[b];
+    const Real fac = (Real)0.5 * h * h * idt2;  // 0.5 h^2 / dt
+#pragma unroll
+    for (int q = 0; q < 6; q++)
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        tl[q][k * 64 + t] = comp[q][own + k * 64 + t];
+    // phase 1: ghost planes of component (f/2) and (3 + f/2) on face f
+#pragma unroll
+    for (int g = 0; g < 2; g++)
+#pragma unroll
+      for (int f = 0; f < 6; f++) {
+        const Real *cp = comp[3 * g + (f >> 1)];
+        SlotVec<Real> cv{const_cast<Real *>(cp), nullptr, 0x7fffffff};
+        const int nb = nbr6[f];
+        if (nb == kCoarse) {
+          coarse_patch_load<Real>(cv.at(ext24[f * 4]), f, ext24[f * 4 + 1], t, patch[g][f]);
+        } else if (nb == kFine) {
+          Real lay[2][2][2];
+          hl[g][f][t] = fine_avg<Real>(cv, ext24 + f * 4, f, a, c, lay);
+        } else if (nb >= 0) {
+          hl[g][f][t] = cp[(size_t)nb * 512 + face_idx(f, (f & 1) ? 0 : 7, a, c)];
+        } else {  // wall: nearest interior cell, normal component negated (OP_BC, vflip)
+          hl[g][f][t] = -cp[own + face_idx(f, (f & 1) ? 7 : 0, a, c)];
+        }
+      }
+    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < 2; g++)
+#pragma unroll
+      for (int f = 0; f < 6; f++)
+        if (nbr6[f] == kCoarse) {
+          const Real *tc = tl[3 * g + (f >> 1)];
+          hl[g][f][t] = fd_ghost<Real>(patch[g][f], a, c, tc[face_idx(f, (f & 1) ? 7 : 0, a, c)],
+                                       tc[face_idx(f, (f & 1) ? 6 : 1, a, c)]);
+        }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int i = k * 64 + t;
+      Real dv[2];
+#pragma unroll
+      for (int g = 0; g < 2; g++) {
+        const Real *U = tl[3 * g], *V = tl[3 * g + 1], *W = tl[3 * g + 2];
+        const Real uxp = x < 7 ? U[i + 1] : hl[g][1][y + 8 * k];
+        const Real uxm = x > 0 ? U[i - 1] : hl[g][0][y + 8 * k];
+        const Real vyp = y < 7 ? V[i + 8] : hl[g][3][x + 8 * k];
+        const Real vym = y > 0 ? V[i - 8] : hl[g][2][x + 8 * k];
+        const Real wzp = k < 7 ? W[i + 64] : hl[g][5][t];
+        const Real wzm = k > 0 ? W[i - 64] : hl[g][4][t];
+        dv[g] = ((((uxp - uxm) + vyp) - vym) + wzp) - wzm;
+      }
+      Real pp = fac * dv[0];
+      pp += -chi[own + i] * fac * dv[1];
+      lhs[own + i] = pp;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int f = 0; f < 6; f++) {
+      if (nbr6[f] != kFine)
+        continue;
+      const int d = f >> 1, nI = (f & 1) ? 7 : 0;
+      const int cell = face_idx(f, nI, a, c);
+      const Real s = (f & 1) ? (Real)-1.0 : (Real)1.0;
+      // own flux (k_prhs :5694): s (fac (n_d + c_d) - chi fac (n_{3+d} + c_{3+d}))
+      const Real Fown = s * (fac * (hl[0][f][t] + tl[d][cell]) - chi[own + cell] * fac * (hl[1][f][t] + tl[3 + d][cell]));
+      // the four fine cells facing this cell
+      const Real hf = (Real)0.5 * h, facf = (Real)0.5 * hf * hf * idt2;
+      const Real sf = ((f ^ 1) & 1) ? (Real)-1.0 : (Real)1.0;
+      Real gh[2][2][2], bnd[2][2][2];  // [vel/udef][j2][j1]
+#pragma unroll
+      for (int g = 0; g < 2; g++) {
+        const Real *cp = comp[3 * g + d];
+        SlotVec<Real> cv{const_cast<Real *>(cp), nullptr, 0x7fffffff};
+        Real lay[2][2][2], mine[16];
+        (void)fine_avg<Real>(cv, ext24 + f * 4, f, a, c, lay);
+#pragma unroll
+        for (int q = 0; q < 16; q++)
+          mine[q] = tl[3 * g + d][face_idx(f, nI, 4 * (a >> 2) + (q & 3), 4 * (c >> 2) + (q >> 2))];
+#pragma unroll
+        for (int j2 = 0; j2 < 2; j2++)
+#pragma unroll
+          for (int j1 = 0; j1 < 2; j1++) {
+            gh[g][j2][j1] = fd_ghost<Real>(mine, 2 * (a & 3) + j1, 2 * (c & 3) + j2, lay[0][j2][j1], lay[1][j2][j1]);
+            bnd[g][j2][j1] = lay[0][j2][j1];
+          }
+      }
+      // chi of the fine boundary cells
+      const Real *fchi = chi + (size_t)ext24[f * 4 + (a >> 2) + 2 * (c >> 2)] * 512;
+      const int nF = (f & 1) ? 0 : 7;
+      Real Ff[2][2];
+#pragma unroll
+      for (int j2 = 0; j2 < 2; j2++)
+#pragma unroll
+        for (int j1 = 0; j1 < 2; j1++) {
+          const Real cf = fchi[face_idx(f, nF, 2 * (a & 3) + j1, 2 * (c & 3) + j2)];
+          Ff[j2][j1] = sf * (facf * (gh[0][j2][j1] + bnd[0][j2][j1]) - cf * facf * (gh[1][j2][j1] + bnd[1][j2][j1]));
+        }
+      const Real fsum = (Ff[0][0] + Ff[0][1]) + (Ff[1][0] + Ff[1][1]);
+      lhs[own + cell] += Fown + fsum;
+      __syncthreads();
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
 static inline int agrid(const CupCtx *c, long long n) {
   long long g = (long long)c->num_sms * 8;
   return (int)(g < n ? g : (n < 1 ? 1 : n));
@@ -283,6 +497,31 @@ int apply_amr_launch(CupCtx *c, LevelView lv, const int *sub, int nsub, SlotVec<
                                                                           (const Real *)hblk, shift);
   return CUP_OK;
 }
+
+template <typename Real>
+int pres_amr_launch(CupCtx *c, LevelView lv, const void *hblk, const Real *p, Real *o0, Real *o1, Real *o2, Real facs,
+                    int what) {
+  if (what == 0)
+    k_pres_amr<Real, 0><<<agrid(c, lv.nact), TPB, 0, c->stream>>>(lv, (const Real *)hblk, p, o0, o1, o2, facs);
+  else
+    k_pres_amr<Real, 1><<<agrid(c, lv.nact), TPB, 0, c->stream>>>(lv, (const Real *)hblk, p, o0, o1, o2, facs);
+  return CUP_OK;
+}
+
+template <typename Real>
+int prhs_amr_launch(CupCtx *c, LevelView lv, const void *hblk, Real *const *S, Real idt2) {
+  k_prhs_amr<Real><<<agrid(c, lv.nact), TPB, 0, c->stream>>>(lv, (const Real *)hblk, S[CUP_F_VEL], S[CUP_F_VEL + 1],
+                                                             S[CUP_F_VEL + 2], S[CUP_F_TMP], S[CUP_F_TMP + 1],
+                                                             S[CUP_F_TMP + 2], S[CUP_F_CHI], S[CUP_F_LHS], idt2);
+  return CUP_OK;
+}
+
+template int pres_amr_launch<double>(CupCtx *, LevelView, const void *, const double *, double *, double *, double *,
+                                     double, int);
+template int pres_amr_launch<float>(CupCtx *, LevelView, const void *, const float *, float *, float *, float *, float,
+                                    int);
+template int prhs_amr_launch<double>(CupCtx *, LevelView, const void *, double *const *, double);
+template int prhs_amr_launch<float>(CupCtx *, LevelView, const void *, float *const *, float);
 
 template int smooth_amr_launch<double>(CupCtx *, LevelView, SlotVec<double>, SlotVec<double>, SlotVec<double>,
                                        SlotVec<double>, double, const double *, bool);

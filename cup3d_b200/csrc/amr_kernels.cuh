@@ -15,4 +15,11 @@ int down_amr_launch(CupCtx *c, LevelView lv, const int *pslot, const int *oct, S
 template <typename Real>
 int apply_amr_launch(CupCtx *c, LevelView lv, const int *sub, int nsub, SlotVec<Real> u, SlotVec<Real> out,
                      SlotVec<Real> us, Real h, const void *hblk, const double *shift, int mode);
+// leaf sweeps with flux correction: what 0 = k_divp (facs unused), 1 = k_gradp (facs = -dt/2)
+template <typename Real>
+int pres_amr_launch(CupCtx *c, LevelView lv, const void *hblk, const Real *p, Real *o0, Real *o1, Real *o2, Real facs,
+                    int what);
+// k_prhs; S = the nine state components, idt2 = 1/dt
+template <typename Real>
+int prhs_amr_launch(CupCtx *c, LevelView lv, const void *hblk, Real *const *S, Real idt2);
 }  // namespace cup

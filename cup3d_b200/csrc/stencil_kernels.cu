@@ -14,6 +14,7 @@
 #include "blas_kernels.cuh"
 #include "cup_internal.h"
 #include "comm.cuh"
+#include "amr_kernels.cuh"
 #include "mg_device.cuh"
 
 namespace cup {
@@ -337,8 +338,47 @@ int need_uniform(CupCtx *c, const char *what) {
   return CUP_OK;
 }
 
+// v += g / h^3 per block (projection's velocity update on multi-level meshes, :5907-5916)
+template <typename Real>
+__global__ void __launch_bounds__(256) k_vel_add_blk(Real *__restrict__ v, const Real *__restrict__ g,
+                                                     const Real *__restrict__ h3, long long nblk) {
+  for (long long b = blockIdx.x; b < nblk; b += gridDim.x) {
+    const Real fac = (Real)1.0 / h3[b];
+    for (int j = threadIdx.x; j < 512; j += blockDim.x)
+      v[b * 512 + j] += fac * g[b * 512 + j];
+  }
+}
+
+template <typename Real>
+int stencil_amr_t(CupCtx *c, CupStencilId id) {
+  const Level &v = c->leafv;
+  LevelView lv{v.d_act, v.d_nbr, (int)v.act.size(), nullptr, nullptr, 0, v.d_ext};
+  Real **S = (Real **)c->state;
+  const double dt = c->prm.dt;
+  switch (id) {
+  case CUP_ST_PRHS:
+    CUP_TRY(prhs_amr_launch<Real>(c, lv, v.d_hblk, S, (Real)(1.0 / dt)));
+    break;
+  case CUP_ST_DIVP:
+    CUP_TRY(pres_amr_launch<Real>(c, lv, v.d_hblk, S[CUP_F_PRES], S[CUP_F_TMP], nullptr, nullptr, (Real)0, 0));
+    break;
+  case CUP_ST_GRADP:
+    CUP_TRY(pres_amr_launch<Real>(c, lv, v.d_hblk, S[CUP_F_PRES], S[CUP_F_TMP], S[CUP_F_TMP + 1], S[CUP_F_TMP + 2],
+                                  (Real)(-0.5 * dt), 1));
+    break;
+  default:
+    set_error("stencil %d on a multi-level mesh is not available in this build", (int)id);
+    return CUP_ERR_UNSUPPORTED;
+  }
+  c->launches++;
+  CUP_CUDA(cudaGetLastError());
+  return CUP_OK;
+}
+
 template <typename Real>
 int stencil_t(CupCtx *c, CupStencilId id, const int *d_sub, long long nsub) {
+  if (!c->leaf_uniform && id != CUP_ST_LHS && id != CUP_ST_MG)
+    return stencil_amr_t<Real>(c, id);
   const Level &v = *leaf_level(c);
   LevelView lv{v.d_act, v.d_nbr, (int)v.act.size(), v.d_frecv, (const unsigned long long *)v.d_seq, v.rface_stride, v.d_ext};
   if (c->nranks > 1 && id != CUP_ST_LHS && id != CUP_ST_MG) {
@@ -461,7 +501,11 @@ int projection_t(CupCtx *c, CupSolveInfo *info) {
   CUP_TRY(stencil_t<Real>(c, CUP_ST_GRADP, nullptr, 0));
   const double fac = 1.0 / (v.h * v.h * v.h);
   for (int a = 0; a < 3; a++) {
-    k_vel_add<Real><<<sgrid(c, N), 256, 0, c->stream>>>(S[CUP_F_VEL + a], S[CUP_F_TMP + a], N, (Real)fac);
+    if (c->leaf_uniform)
+      k_vel_add<Real><<<sgrid(c, N), 256, 0, c->stream>>>(S[CUP_F_VEL + a], S[CUP_F_TMP + a], N, (Real)fac);
+    else
+      k_vel_add_blk<Real><<<bgrid(c, c->nblk, 8), 256, 0, c->stream>>>(S[CUP_F_VEL + a], S[CUP_F_TMP + a],
+                                                                      (const Real *)c->d_hw, c->nblk);
     c->launches++;
   }
   CUP_CUDA(cudaGetLastError());
@@ -472,8 +516,8 @@ int projection_t(CupCtx *c, CupSolveInfo *info) {
 }  // namespace
 
 int stencil_run(CupCtx *c, CupStencilId id, const long long *list, long long n) {
-  if (id != CUP_ST_LHS && id != CUP_ST_MG)
-    CUP_TRY(need_uniform(c, "stencil_run (sweeps other than LHS/MG)"));
+  if (id == CUP_ST_ADVDIFF)
+    CUP_TRY(need_uniform(c, "stencil_run(advdiff)"));
   if (c->nblk == 0) {
     set_error("stencil_run: no mesh uploaded");
     return CUP_ERR_STATE;
@@ -491,7 +535,10 @@ int advdiff(CupCtx *c) {
 }
 
 int projection(CupCtx *c, CupSolveInfo *info) {
-  CUP_TRY(need_uniform(c, "projection"));
+  if (c->nblk == 0) {
+    set_error("projection: no mesh uploaded");
+    return CUP_ERR_STATE;
+  }
   return c->real_bytes == 8 ? projection_t<double>(c, info) : projection_t<float>(c, info);
 }
 

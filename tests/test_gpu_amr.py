@@ -85,3 +85,33 @@ def test_amr_pois_solve(built):
     assert info.residual < max(1e-10, 1e-12 * info.rhs_norm)
     assert relerr(out[:, 1], c.g["solve_x_mc2"]) < 1e-8
     ctx.close()
+
+
+@pytest.mark.parametrize("st,sid,f0,nc", [("prhs", capi.ST_PRHS, 8, 1), ("divp", capi.ST_DIVP, 5, 1),
+                                          ("gradp", capi.ST_GRADP, 5, 3)])
+def test_amr_projection_sweeps(built, st, sid, f0, nc):
+    """k_prhs / k_divp / k_gradp with their flux correction on a 2-level mesh"""
+    c = case("amr2")
+    ctx = make_ctx(c)
+    s0 = c.state0()
+    ctx.state_h2d(s0)
+    ctx.stencil_apply(sid)
+    out = np.zeros_like(s0)
+    ctx.state_d2h(out)
+    assert relerr(out[:, f0:f0 + nc], c.g["st_" + st]) < 1e-12, st
+    ctx.close()
+
+
+def test_amr_projection(built):
+    c = case("amr2")
+    ctx = make_ctx(c, ptol=1e-10, ptol_rel=1e-12)
+    s0 = c.state0()
+    ctx.state_h2d(s0)
+    info = ctx.projection()
+    out = np.zeros_like(s0)
+    ctx.state_d2h(out)
+    ref = c.g["proj_step5"]
+    assert info.residual < max(1e-10, 1e-12 * info.rhs_norm)
+    assert relerr(out[:, 1], ref[:, 0]) < 1e-7
+    assert relerr(out[:, 2:5], ref[:, 1:4]) < 1e-9
+    ctx.close()
