@@ -263,6 +263,27 @@ __global__ void __launch_bounds__(64) k_pack_faces(const int *__restrict__ sslot
   }
 }
 
+// ghost slabs of the stencil sweeps: for each face entry, `ncomp` components x `nlayer` planes
+// counted inward from the face; entry layout [(comp*nlayer + layer)*64 + t], SLAB_PLANES*64 apart
+template <typename Real>
+__global__ void __launch_bounds__(64) k_pack_slabs(const int *__restrict__ sslot, const int *__restrict__ splane,
+                                                   int n, SlabSrc<Real> src, int ncomp, int nlayer,
+                                                   Real *const *__restrict__ dst0, Real *const *__restrict__ dst1,
+                                                   const unsigned long long *__restrict__ seq) {
+  const int t = threadIdx.x, a = t & 7, cc = t >> 3;
+  const bool odd = seq ? ((*seq + 1) & 1) : false;
+  for (int e = blockIdx.x; e < n; e += gridDim.x) {
+    const size_t base = (size_t)sslot[e] * 512;
+    const int p = splane[e];
+    Real *d = (odd ? dst1 : dst0)[e];
+    for (int q = 0; q < ncomp; q++)
+      for (int l = 0; l < nlayer; l++) {
+        const int n0 = (p & 1) ? 7 - l : l;
+        d[(q * nlayer + l) * 64 + t] = src.c[q][base + face_idx(p, n0, a, cc)];
+      }
+  }
+}
+
 // mg_put (main.c:4722): received 64 r + 64 u of a remote child -> the parent's octant
 template <typename Real>
 __global__ void __launch_bounds__(64) k_put(const int *__restrict__ rslot, const int *__restrict__ roct, int n,
@@ -370,13 +391,19 @@ void comm_free_level_buffers(CupCtx *c) {
     cm->d_seq = nullptr;
     cm->p2p = false;
     for (auto &v : c->lv)
-      v.d_frecv = v.d_rrecv = v.d_precv = nullptr;  // lived inside the window
+      v.d_frecv = v.d_rrecv = v.d_precv = v.d_srecv = nullptr;  // lived inside the window
   }
   for (auto &v : c->lv) {
     cudaFree(v.d_fsend);
     cudaFree(v.d_frecv);
     cudaFree(v.d_rsend);
     cudaFree(v.d_rrecv);
+    cudaFree(v.d_ssend);
+    cudaFree(v.d_srecv);
+    cudaFree(v.d_sptr0);
+    cudaFree(v.d_sptr1);
+    v.d_ssend = v.d_srecv = nullptr;
+    v.d_sptr0 = v.d_sptr1 = nullptr;
     cudaFree(v.d_order);
     cudaFree(v.d_bsend);
     cudaFree(v.d_counters);
@@ -522,6 +549,30 @@ int comm_alloc_level_buffers(CupCtx *c) {
       for (size_t e = 0; e < cr; e++)
         pp[e] = (char *)v.d_rrecv + e * 64 * rb;
     }
+    // ghost slabs (stencil sweeps): same entries, SLAB_PLANES planes each
+    if (v.win_slab.size() == (size_t)c->nranks && v.win_slab[me] >= 0 && (ns || nr)) {
+      std::vector<char *> s0(ns), s1(ns);
+      const size_t eb = 64 * SLAB_PLANES * rb;
+      if (p2p) {
+        v.d_srecv = cm->win + cm->flag_bytes + (size_t)v.win_slab[me] * rb;
+        v.slab_stride = (long long)nr * 64 * SLAB_PLANES;
+        for (size_t e = 0; e < ns; e++) {
+          const int p = v.face_speer[e];
+          s0[e] = cm->peer_win[p] + cm->flag_bytes + (size_t)v.win_slab[p] * rb + (size_t)v.face_sidx[e] * eb;
+          s1[e] = s0[e] + (size_t)v.win_nrecv[p] * eb;
+        }
+      } else {
+        if (ns)
+          CUP_CUDA(cudaMalloc(&v.d_ssend, ns * eb));
+        if (nr)
+          CUP_CUDA(cudaMalloc(&v.d_srecv, nr * eb));
+        v.slab_stride = 0;
+        for (size_t e = 0; e < ns; e++)
+          s0[e] = s1[e] = (char *)v.d_ssend + e * eb;
+      }
+      CUP_TRY(up((char ***)&v.d_sptr0, s0));
+      CUP_TRY(up((char ***)&v.d_sptr1, s1));
+    }
     CUP_TRY(up((char ***)&v.d_fptr0, f0));
     CUP_TRY(up((char ***)&v.d_fptr1, f1));
     CUP_TRY(up((char ***)&v.d_rptr, rp));
@@ -623,6 +674,33 @@ int halo_post(CupCtx *c, Level &v, SlotVec<Real> u) {
   return CUP_OK;
 }
 
+// publish `ncomp` x `nlayer` ghost planes per face of the leaf level (stencil sweeps) and wait for
+// the peers' ones; afterwards they sit in v.d_srecv (+ parity stride)
+template <typename Real>
+int slab_exchange(CupCtx *c, Level &v, const SlabSrc<Real> &src, int ncomp, int nlayer) {
+  if (!level_has_faces(c, v))
+    return CUP_OK;
+  if (ncomp * nlayer > SLAB_PLANES || !v.d_sptr0) {
+    set_error("slab_exchange: %d x %d planes not provisioned", ncomp, nlayer);
+    return CUP_ERR_STATE;
+  }
+  const int ns = (int)v.face_sslot.size();
+  if (ns) {
+    k_pack_slabs<Real><<<cgrid(c, ns), 64, 0, c->stream>>>(v.d_face_sslot, v.d_face_splane, ns, src, ncomp, nlayer,
+                                                           (Real *const *)v.d_sptr0, (Real *const *)v.d_sptr1,
+                                                           (const unsigned long long *)v.d_seq);
+    c->launches++;
+  }
+  if (v.p2p) {
+    CUP_TRY(post(c, v, K_FACE));
+    CUP_TRY(wait(c, v, K_FACE));
+  } else {
+    CUP_TRY(exchange(c, v.d_ssend, v.face_scnt, v.d_srecv, v.face_rcnt, 64 * SLAB_PLANES * sizeof(Real)));
+  }
+  CUP_CUDA(cudaGetLastError());
+  return CUP_OK;
+}
+
 // the faces posted last are complete in this rank's receive area
 int halo_wait(CupCtx *c, Level &v) {
   if (!level_has_faces(c, v) || !v.p2p)
@@ -674,6 +752,8 @@ int prolong_exchange(CupCtx *c, Level &v, SlotVec<Real> u, SlotVec<Real> us) {
   return CUP_OK;
 }
 
+template int slab_exchange<double>(CupCtx *, Level &, const SlabSrc<double> &, int, int);
+template int slab_exchange<float>(CupCtx *, Level &, const SlabSrc<float> &, int, int);
 template int halo_post<double>(CupCtx *, Level &, SlotVec<double>);
 template int halo_post<float>(CupCtx *, Level &, SlotVec<float>);
 template int restrict_exchange<double>(CupCtx *, Level &, SlotVec<double>, SlotVec<double>);

@@ -22,6 +22,13 @@ inline int halo_exchange(CupCtx *c, Level &v, SlotVec<Real> u) {
   int rc = halo_post<Real>(c, v, u);
   return rc != CUP_OK ? rc : halo_wait(c, v);
 }
+// up to six component vectors (flat [slot][512]) whose ghost slabs travel together
+template <typename Real>
+struct SlabSrc {
+  const Real *c[6];
+};
+template <typename Real>
+int slab_exchange(CupCtx *c, Level &v, const SlabSrc<Real> &src, int ncomp, int nlayer);
 template <typename Real>
 int restrict_exchange(CupCtx *c, Level &v, SlotVec<Real> f, SlotVec<Real> u);
 template <typename Real>

@@ -73,6 +73,7 @@ struct Level {
   std::vector<int> pro_speer, pro_sidx;    // [received children] dest rank (the child's owner), entry in its prolong area
   std::vector<long long> win_face, win_res, win_pro;  // [nranks] offsets (Reals) of rank p's areas for this level
   std::vector<int> win_nrecv;              // [nranks] faces rank p receives per exchange (parity stride / 64)
+  std::vector<long long> win_slab;         // [nranks] offset of rank p's SLAB area (finest level only, else -1)
   // device scratch (comm.cu): faces out/in [n][64], restriction out/in [n][128]
   void *d_fsend = nullptr, *d_frecv = nullptr, *d_rsend = nullptr, *d_rrecv = nullptr;
   void *d_precv = nullptr;                 // prolongation corrections for children with a remote parent
@@ -83,6 +84,10 @@ struct Level {
   bool p2p = false;
   long long rface_stride = 0;              // Reals between the two parities of the face area
   void *d_seq = nullptr;                   // this level's sequence numbers (one-sided mode)
+  // multi-component / multi-layer ghost slabs of the stencil sweeps (SLAB_PLANES planes per face)
+  void *d_ssend = nullptr, *d_srecv = nullptr;  // staging (NCCL mode) / receive area
+  void **d_sptr0 = nullptr, **d_sptr1 = nullptr;
+  long long slab_stride = 0;               // Reals between the two parities of the slab area
   // fused sweep + exchange (smooth_tma.cu): work order = boundary blocks first, then interior
   std::vector<int> order, bsend;           // [nact] act indices; [nact][6] send entry of (block, plane) or -1
   int *d_order = nullptr, *d_bsend = nullptr;
@@ -181,6 +186,6 @@ void free_krylov(CupCtx *c);
 int comm_init(CupCtx *c, int rank, int nranks, const void *id, size_t id_bytes);
 int comm_unique_id(void *out, size_t bytes);
 
-enum { SCAL_N = 256 };
+enum { SCAL_N = 256, SLAB_PLANES = 9 };  // 3 components x 3 layers (k_advdiff) is the largest slab
 
 }  // namespace cup

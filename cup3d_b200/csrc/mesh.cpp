@@ -498,6 +498,11 @@ int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner_
   }
   // lay out every rank's receive window: per level [faces parity 0][faces parity 1][restrict][prolong]
   m->win_reals.assign(nranks, 0);
+  int finest = m->top;
+  while (finest > 0 && m->lv[finest].gnact == 0)
+    finest--;
+  for (int L = 0; L <= m->top; L++)
+    m->lv[L].win_slab.assign(nranks, -1);
   for (int p = 0; p < nranks; p++) {
     long long off = 0;
     for (int L = 0; L <= m->top; L++) {
@@ -509,6 +514,10 @@ int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner_
       off += nres * 128;
       v.win_pro[p] = off;
       off += npro * 64;
+      if (L == finest) {  // ghost slabs of the stencil sweeps live on the leaf level
+        v.win_slab[p] = off;
+        off += 2LL * v.win_nrecv[p] * 64 * SLAB_PLANES;
+      }
     }
     m->win_reals[p] = off;
   }

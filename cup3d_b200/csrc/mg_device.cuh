@@ -47,7 +47,19 @@ struct LevelView {
   // coarse-fine interfaces (AMR): ext[k][6][4] -- kCoarse: {coarse slot, quadrant of its face};
   // kFine: the four finer blocks across the face, quadrant-major (a/4 + 2*(c/4))
   const int *ext;
+  // ghost slabs received from other ranks (stencil sweeps): [face][SLAB planes][64], double buffered
+  const void *rslab;
+  long long rslab_stride;
 };
+
+enum { kSlabPlanes = 9 };
+template <typename Real>
+__device__ __forceinline__ const Real *rslab_of(const LevelView &lv) {
+  const Real *p = (const Real *)lv.rslab;
+  if (lv.seq && (*lv.seq & 1))
+    p += lv.rslab_stride;
+  return p;
+}
 
 template <typename Real>
 __device__ __forceinline__ const Real *rface_of(const LevelView &lv) {

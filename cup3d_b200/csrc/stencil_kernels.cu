@@ -10,6 +10,7 @@
 // Wall ghosts copy the nearest interior cell, with the wall-normal component of
 // vector fields negated (free slip; gen_table.py:195-231).
 #include <cmath>
+#include <cstdlib>
 
 #include "blas_kernels.cuh"
 #include "cup_internal.h"
@@ -41,8 +42,8 @@ __device__ __forceinline__ Real upwind(Real U, Real um3, Real um2, Real um1, Rea
 
 enum { AD_ROW = 16, AD_SLAB = 14 * 16 };  // padded tile: [8 z][14 y][16 x], halo offset 3
 
-template <typename Real>
-__global__ void __launch_bounds__(TPB) k_advdiff(LevelView lv, const Real *__restrict__ v0, const Real *__restrict__ v1,
+template <typename Real, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) k_advdiff(LevelView lv, const Real *__restrict__ v0, const Real *__restrict__ v1,
                                                  const Real *__restrict__ v2, Real *__restrict__ t0,
                                                  Real *__restrict__ t1, Real *__restrict__ t2, Real fac_a, Real fac_d,
                                                  Real ux, Real uy, Real uz) {
@@ -52,6 +53,11 @@ __global__ void __launch_bounds__(TPB) k_advdiff(LevelView lv, const Real *__res
   const Real *vel[3] = {v0, v1, v2};
   Real *tmp[3] = {t0, t1, t2};
   const Real uinf[3] = {ux, uy, uz};
+  const Real *rsl = lv.rslab ? rslab_of<Real>(lv) : nullptr;
+  // ghost value of component c, layer l (counted from the face) of the slab received for code nbc
+  auto rem = [&](int nbc, int c, int l) -> Real {
+    return rsl[(size_t)(kRemote0 - nbc) * (64 * kSlabPlanes) + (c * 3 + l) * 64 + t];
+  };
   for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
     const size_t own = (size_t)lv.act[b] * 512;
     const int *nbr6 = lv.nbr + (size_t)b * 6;
@@ -77,8 +83,10 @@ __global__ void __launch_bounds__(TPB) k_advdiff(LevelView lv, const Real *__res
         const Real sg = (c == 2) ? (Real)-1 : (Real)1;
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-          line[i] = nb[4] >= 0 ? vc[(size_t)nb[4] * 512 + (5 + i) * 64 + t] : sg * vv[c][0];
-          line[11 + i] = nb[5] >= 0 ? vc[(size_t)nb[5] * 512 + i * 64 + t] : sg * vv[c][7];
+          line[i] = nb[4] >= 0 ? vc[(size_t)nb[4] * 512 + (5 + i) * 64 + t]
+                               : (nb[4] == kWall ? sg * vv[c][0] : rem(nb[4], c, 2 - i));
+          line[11 + i] = nb[5] >= 0 ? vc[(size_t)nb[5] * 512 + i * 64 + t]
+                                    : (nb[5] == kWall ? sg * vv[c][7] : rem(nb[5], c, i));
         }
       }
       __syncthreads();  // previous component's tile fully consumed
@@ -90,13 +98,17 @@ __global__ void __launch_bounds__(TPB) k_advdiff(LevelView lv, const Real *__res
 #pragma unroll
         for (int p = 0; p < 3; p++) {
           // -x / +x: element (y = a, z = c2)
-          const Real xm = nb[0] >= 0 ? vc[(size_t)nb[0] * 512 + c2 * 64 + a * 8 + (5 + p)] : sx * vc[own + c2 * 64 + a * 8];
-          const Real xp = nb[1] >= 0 ? vc[(size_t)nb[1] * 512 + c2 * 64 + a * 8 + p] : sx * vc[own + c2 * 64 + a * 8 + 7];
+          const Real xm = nb[0] >= 0 ? vc[(size_t)nb[0] * 512 + c2 * 64 + a * 8 + (5 + p)]
+                                     : (nb[0] == kWall ? sx * vc[own + c2 * 64 + a * 8] : rem(nb[0], c, 2 - p));
+          const Real xp = nb[1] >= 0 ? vc[(size_t)nb[1] * 512 + c2 * 64 + a * 8 + p]
+                                     : (nb[1] == kWall ? sx * vc[own + c2 * 64 + a * 8 + 7] : rem(nb[1], c, p));
           tile[c2 * AD_SLAB + (a + 3) * AD_ROW + p] = xm;
           tile[c2 * AD_SLAB + (a + 3) * AD_ROW + 11 + p] = xp;
           // -y / +y: element (x = a, z = c2)
-          const Real ym = nb[2] >= 0 ? vc[(size_t)nb[2] * 512 + c2 * 64 + (5 + p) * 8 + a] : sy * vc[own + c2 * 64 + a];
-          const Real yp = nb[3] >= 0 ? vc[(size_t)nb[3] * 512 + c2 * 64 + p * 8 + a] : sy * vc[own + c2 * 64 + 56 + a];
+          const Real ym = nb[2] >= 0 ? vc[(size_t)nb[2] * 512 + c2 * 64 + (5 + p) * 8 + a]
+                                     : (nb[2] == kWall ? sy * vc[own + c2 * 64 + a] : rem(nb[2], c, 2 - p));
+          const Real yp = nb[3] >= 0 ? vc[(size_t)nb[3] * 512 + c2 * 64 + p * 8 + a]
+                                     : (nb[3] == kWall ? sy * vc[own + c2 * 64 + 56 + a] : rem(nb[3], c, p));
           tile[c2 * AD_SLAB + p * AD_ROW + (a + 3)] = ym;
           tile[c2 * AD_SLAB + (11 + p) * AD_ROW + (a + 3)] = yp;
         }
@@ -153,6 +165,9 @@ __global__ void __launch_bounds__(TPB) k_prhs(LevelView lv, const Real *__restri
   __shared__ Real hl[4][2][64];    // their -/+ faces (x faces for u/udef_x, y faces for v/udef_y)
   const int t = threadIdx.x, x = t & 7, y = t >> 3;
   const int a = t & 7, c2 = t >> 3;
+  const Real *rsl = lv.rslab ? rslab_of<Real>(lv) : nullptr;
+  // component q (0..5 = u v w udef_x udef_y udef_z), single layer, of the slab received for code nbc
+  auto rem = [&](int nbc, int q) -> Real { return rsl[(size_t)(kRemote0 - nbc) * (64 * kSlabPlanes) + q * 64 + t]; };
   for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
     const size_t own = (size_t)lv.act[b] * 512;
     const int *nbr6 = lv.nbr + (size_t)b * 6;
@@ -168,20 +183,20 @@ __global__ void __launch_bounds__(TPB) k_prhs(LevelView lv, const Real *__restri
       dz[k] = d2[own + k * 64 + t];
     }
     // x faces of u and udef_x: element (y = a, z = c2); wall: -own (normal component flips)
-    hl[0][0][t] = n0 >= 0 ? v0[(size_t)n0 * 512 + c2 * 64 + a * 8 + 7] : -v0[own + c2 * 64 + a * 8];
-    hl[0][1][t] = n1 >= 0 ? v0[(size_t)n1 * 512 + c2 * 64 + a * 8] : -v0[own + c2 * 64 + a * 8 + 7];
-    hl[2][0][t] = n0 >= 0 ? d0[(size_t)n0 * 512 + c2 * 64 + a * 8 + 7] : -d0[own + c2 * 64 + a * 8];
-    hl[2][1][t] = n1 >= 0 ? d0[(size_t)n1 * 512 + c2 * 64 + a * 8] : -d0[own + c2 * 64 + a * 8 + 7];
+    hl[0][0][t] = n0 >= 0 ? v0[(size_t)n0 * 512 + c2 * 64 + a * 8 + 7] : (n0 == kWall ? -v0[own + c2 * 64 + a * 8] : rem(n0, 0));
+    hl[0][1][t] = n1 >= 0 ? v0[(size_t)n1 * 512 + c2 * 64 + a * 8] : (n1 == kWall ? -v0[own + c2 * 64 + a * 8 + 7] : rem(n1, 0));
+    hl[2][0][t] = n0 >= 0 ? d0[(size_t)n0 * 512 + c2 * 64 + a * 8 + 7] : (n0 == kWall ? -d0[own + c2 * 64 + a * 8] : rem(n0, 3));
+    hl[2][1][t] = n1 >= 0 ? d0[(size_t)n1 * 512 + c2 * 64 + a * 8] : (n1 == kWall ? -d0[own + c2 * 64 + a * 8 + 7] : rem(n1, 3));
     // y faces of v and udef_y: element (x = a, z = c2)
-    hl[1][0][t] = n2 >= 0 ? v1[(size_t)n2 * 512 + c2 * 64 + 56 + a] : -v1[own + c2 * 64 + a];
-    hl[1][1][t] = n3 >= 0 ? v1[(size_t)n3 * 512 + c2 * 64 + a] : -v1[own + c2 * 64 + 56 + a];
-    hl[3][0][t] = n2 >= 0 ? d1[(size_t)n2 * 512 + c2 * 64 + 56 + a] : -d1[own + c2 * 64 + a];
-    hl[3][1][t] = n3 >= 0 ? d1[(size_t)n3 * 512 + c2 * 64 + a] : -d1[own + c2 * 64 + 56 + a];
+    hl[1][0][t] = n2 >= 0 ? v1[(size_t)n2 * 512 + c2 * 64 + 56 + a] : (n2 == kWall ? -v1[own + c2 * 64 + a] : rem(n2, 1));
+    hl[1][1][t] = n3 >= 0 ? v1[(size_t)n3 * 512 + c2 * 64 + a] : (n3 == kWall ? -v1[own + c2 * 64 + 56 + a] : rem(n3, 1));
+    hl[3][0][t] = n2 >= 0 ? d1[(size_t)n2 * 512 + c2 * 64 + 56 + a] : (n2 == kWall ? -d1[own + c2 * 64 + a] : rem(n2, 4));
+    hl[3][1][t] = n3 >= 0 ? d1[(size_t)n3 * 512 + c2 * 64 + a] : (n3 == kWall ? -d1[own + c2 * 64 + 56 + a] : rem(n3, 4));
     // z faces of w and udef_z straight into registers
-    const Real wzm = n4 >= 0 ? v2[(size_t)n4 * 512 + 448 + t] : -w[0];
-    const Real wzp = n5 >= 0 ? v2[(size_t)n5 * 512 + t] : -w[7];
-    const Real dzm = n4 >= 0 ? d2[(size_t)n4 * 512 + 448 + t] : -dz[0];
-    const Real dzp = n5 >= 0 ? d2[(size_t)n5 * 512 + t] : -dz[7];
+    const Real wzm = n4 >= 0 ? v2[(size_t)n4 * 512 + 448 + t] : (n4 == kWall ? -w[0] : rem(n4, 2));
+    const Real wzp = n5 >= 0 ? v2[(size_t)n5 * 512 + t] : (n5 == kWall ? -w[7] : rem(n5, 2));
+    const Real dzm = n4 >= 0 ? d2[(size_t)n4 * 512 + 448 + t] : (n4 == kWall ? -dz[0] : rem(n4, 5));
+    const Real dzp = n5 >= 0 ? d2[(size_t)n5 * 512 + t] : (n5 == kWall ? -dz[7] : rem(n5, 5));
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -226,7 +241,7 @@ __global__ void __launch_bounds__(TPB) k_pres(LevelView lv, const Real *__restri
       uu[k] = p[own + k * 64 + t];
       tu[k * 64 + t] = uu[k];
     }
-    load_halo<Real>(pv, p + own, lv.nbr + (size_t)b * 6, t, halo);
+    load_halo<Real>(pv, p + own, lv.nbr + (size_t)b * 6, t, halo, rface_of<Real>(lv));
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -380,10 +395,24 @@ int stencil_t(CupCtx *c, CupStencilId id, const int *d_sub, long long nsub) {
   if (!c->leaf_uniform && id != CUP_ST_LHS && id != CUP_ST_MG)
     return stencil_amr_t<Real>(c, id);
   const Level &v = *leaf_level(c);
-  LevelView lv{v.d_act, v.d_nbr, (int)v.act.size(), v.d_frecv, (const unsigned long long *)v.d_seq, v.rface_stride, v.d_ext};
-  if (c->nranks > 1 && id != CUP_ST_LHS && id != CUP_ST_MG) {
-    set_error("stencil sweeps other than LHS/MG are single-rank in this build");
-    return CUP_ERR_UNSUPPORTED;
+  LevelView lv{v.d_act, v.d_nbr, (int)v.act.size(), v.d_frecv, (const unsigned long long *)v.d_seq,
+               v.rface_stride, v.d_ext, v.d_srecv, v.slab_stride};
+  if (c->nranks > 1) {
+    // ghost data owned by other ranks (halo_sync, main.c:3632)
+    Level &vm = const_cast<Level &>(v);
+    if (id == CUP_ST_ADVDIFF) {
+      SlabSrc<Real> src{{(const Real *)c->state[CUP_F_VEL], (const Real *)c->state[CUP_F_VEL + 1],
+                         (const Real *)c->state[CUP_F_VEL + 2], nullptr, nullptr, nullptr}};
+      CUP_TRY(slab_exchange<Real>(c, vm, src, 3, 3));
+    } else if (id == CUP_ST_PRHS) {
+      SlabSrc<Real> src{{(const Real *)c->state[CUP_F_VEL], (const Real *)c->state[CUP_F_VEL + 1],
+                         (const Real *)c->state[CUP_F_VEL + 2], (const Real *)c->state[CUP_F_TMP],
+                         (const Real *)c->state[CUP_F_TMP + 1], (const Real *)c->state[CUP_F_TMP + 2]}};
+      CUP_TRY(slab_exchange<Real>(c, vm, src, 6, 1));
+    } else if (id == CUP_ST_DIVP || id == CUP_ST_GRADP) {
+      SlotVec<Real> pv{(Real *)c->state[CUP_F_PRES], nullptr, (int)c->nblk};
+      CUP_TRY(halo_exchange<Real>(c, vm, pv));
+    }
   }
   if (d_sub) {
     set_error("stencil_run: block sub-lists are only supported for CUP_ST_MG/CUP_ST_LHS");
@@ -398,9 +427,20 @@ int stencil_t(CupCtx *c, CupStencilId id, const int *d_sub, long long nsub) {
     // fac_a = -dt/h*h^3 ; fac_d = (nu/h)*(dt/h)*h^3   (main.c:4993-4995, coef = 1)
     const double h3 = hd * hd * hd;
     const double fa = -dt / hd * h3 * 1.0, fd = (c->prm.nu / hd) * (dt / hd) * h3 * 1.0;
-    k_advdiff<Real><<<bgrid(c, c->nblk, 8), TPB, 0, c->stream>>>(
-        lv, S[CUP_F_VEL], S[CUP_F_VEL + 1], S[CUP_F_VEL + 2], S[CUP_F_TMP], S[CUP_F_TMP + 1], S[CUP_F_TMP + 2],
-        (Real)fa, (Real)fd, (Real)c->prm.uinf[0], (Real)c->prm.uinf[1], (Real)c->prm.uinf[2]);
+    static int minb = getenv("CUP_ADV_MINB") ? atoi(getenv("CUP_ADV_MINB")) : 8;
+#define ADV_LAUNCH(M)                                                                                              \
+  k_advdiff<Real, M><<<bgrid(c, c->nblk, M), TPB, 0, c->stream>>>(                                                 \
+      lv, S[CUP_F_VEL], S[CUP_F_VEL + 1], S[CUP_F_VEL + 2], S[CUP_F_TMP], S[CUP_F_TMP + 1], S[CUP_F_TMP + 2],      \
+      (Real)fa, (Real)fd, (Real)c->prm.uinf[0], (Real)c->prm.uinf[1], (Real)c->prm.uinf[2])
+    if (minb == 5)
+      ADV_LAUNCH(5);
+    else if (minb == 10)
+      ADV_LAUNCH(10);
+    else if (minb == 12)
+      ADV_LAUNCH(12);
+    else
+      ADV_LAUNCH(8);
+#undef ADV_LAUNCH
     break;
   }
   case CUP_ST_PRHS: {
