@@ -1,7 +1,7 @@
 // amr_kernels.cuh -- launchers of the kernels for levels with coarse-fine interfaces
 #pragma once
+#include "cup_internal.h"
 #include "mg_device.cuh"
-struct CupCtx;
 namespace cup {
 int amr_setup_constants();
 // src: ping-pong source (same-level neighbours); can: canonical vector (coarser leaves)
@@ -22,4 +22,7 @@ int pres_amr_launch(CupCtx *c, LevelView lv, const void *hblk, const Real *p, Re
 // k_prhs; S = the nine state components, idt2 = 1/dt
 template <typename Real>
 int prhs_amr_launch(CupCtx *c, LevelView lv, const void *hblk, Real *const *S, Real idt2);
+// k_advdiff on the leaves of a multi-level mesh (amr_advdiff.cu)
+template <typename Real>
+int advdiff_amr_launch(CupCtx *c, const Level &v, Real *const *S);
 }  // namespace cup

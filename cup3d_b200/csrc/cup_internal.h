@@ -47,6 +47,13 @@ struct Level {
   std::vector<int> nbr;    // [nact][6] slot of -x,+x,-y,+y,-z,+z neighbour, NBR_WALL / NBR_COARSE / NBR_FINE
   std::vector<int> ext;    // [nact][6][4] coarse-fine faces: {coarse slot, quadrant} or the 4 finer slots
   std::vector<double> hblk;  // [nact] cell size per block (leaf context only; MG levels share v.h)
+  // leaf context only: block coordinates and a (level,ix,iy,iz) -> slot hash for the wide (ss = 3)
+  // coarse-fine ghost fill of k_advdiff, which samples the coarse-level view around a block
+  std::vector<int> bijk;                   // [nact][4] level, ix, iy, iz
+  std::vector<unsigned long long> hkeys;   // open addressing, 0 = empty
+  std::vector<int> hvals;
+  int *d_bijk = nullptr, *d_hvals = nullptr;
+  unsigned long long *d_hkeys = nullptr;
   std::vector<int> pslot;  // [nact] slot of the parent (level L-1), L >= 1
   std::vector<int> oct;    // [nact] octant inside the parent, (ix&1)+2(iy&1)+4(iz&1)
   std::vector<int> par;    // [npar] indices into act[] of blocks that are synthesised parents

@@ -205,6 +205,26 @@ int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner_
         }
       }
       lf.uniform = false;
+      // device hash of all leaves: key = key_of(...) + 1 (0 marks an empty bucket)
+      size_t cap = 64;
+      while (cap < (size_t)G * 2)
+        cap *= 2;
+      lf.hkeys.assign(cap, 0ULL);
+      lf.hvals.assign(cap, -1);
+      for (long long i = 0; i < G; i++) {
+        if (owner[i] != rank)
+          continue;
+        const unsigned long long k = key_of(gblk[i].level, gblk[i].ix, gblk[i].iy, gblk[i].iz) + 1;
+        size_t h = (size_t)((k * 0x9E3779B97F4A7C15ULL) >> 20) & (cap - 1);
+        while (lf.hkeys[h] != 0)
+          h = (h + 1) & (cap - 1);
+        lf.hkeys[h] = k;
+        lf.hvals[h] = g2l[i];
+        lf.bijk.push_back(gblk[i].level);
+        lf.bijk.push_back(gblk[i].ix);
+        lf.bijk.push_back(gblk[i].iy);
+        lf.bijk.push_back(gblk[i].iz);
+      }
     }
   }
 
@@ -559,6 +579,9 @@ void free_mesh(CupCtx *c) {
     cudaFree(v.d_nbr);
     cudaFree(v.d_ext);
     cudaFree(v.d_hblk);
+    cudaFree(v.d_bijk);
+    cudaFree(v.d_hkeys);
+    cudaFree(v.d_hvals);
     v = Level();
   }
   c->blk.clear();
@@ -607,6 +630,9 @@ int build_mesh(CupCtx *c, const CupBlk *gblk, long long G, const int *owner, con
     CUP_TRY(upload(&v.d_act, v.act));
     CUP_TRY(upload(&v.d_nbr, v.nbr));
     CUP_TRY(upload(&v.d_ext, v.ext));
+    CUP_TRY(upload(&v.d_bijk, v.bijk));
+    CUP_TRY(upload(&v.d_hkeys, v.hkeys));
+    CUP_TRY(upload(&v.d_hvals, v.hvals));
     if (!v.hblk.empty()) {
       if (c->real_bytes == 8) {
         CUP_TRY(upload((double **)&v.d_hblk, v.hblk));

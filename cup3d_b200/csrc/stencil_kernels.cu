@@ -353,6 +353,21 @@ int need_uniform(CupCtx *c, const char *what) {
   return CUP_OK;
 }
 
+// RK3 stage update with per-block h (multi-level meshes): V += TMP*alpha/h^3 ; TMP *= beta
+template <typename Real>
+__global__ void __launch_bounds__(256) k_rk_update_blk(Real *__restrict__ v, Real *__restrict__ tm,
+                                                       const Real *__restrict__ h3, long long nblk, Real alpha,
+                                                       Real beta) {
+  for (long long b = blockIdx.x; b < nblk; b += gridDim.x) {
+    const Real ih3 = alpha / h3[b];
+    for (int j = threadIdx.x; j < 512; j += blockDim.x) {
+      const Real tv = tm[b * 512 + j];
+      v[b * 512 + j] += tv * ih3;
+      tm[b * 512 + j] = tv * beta;
+    }
+  }
+}
+
 // v += g / h^3 per block (projection's velocity update on multi-level meshes, :5907-5916)
 template <typename Real>
 __global__ void __launch_bounds__(256) k_vel_add_blk(Real *__restrict__ v, const Real *__restrict__ g,
@@ -371,6 +386,9 @@ int stencil_amr_t(CupCtx *c, CupStencilId id) {
   Real **S = (Real **)c->state;
   const double dt = c->prm.dt;
   switch (id) {
+  case CUP_ST_ADVDIFF:
+    CUP_TRY(advdiff_amr_launch<Real>(c, v, S));
+    break;
   case CUP_ST_PRHS:
     CUP_TRY(prhs_amr_launch<Real>(c, lv, v.d_hblk, S, (Real)(1.0 / dt)));
     break;
@@ -496,8 +514,12 @@ int advdiff_t(CupCtx *c) {
     CUP_TRY(stencil_t<Real>(c, CUP_ST_ADVDIFF, nullptr, 0));
     const double ih3 = alpha[s] / (v.h * v.h * v.h);
     for (int q = 0; q < 3; q++) {
-      k_rk_update<Real><<<sgrid(c, N), 256, 0, c->stream>>>(S[CUP_F_VEL + q], S[CUP_F_TMP + q], N, (Real)ih3,
-                                                             (Real)beta[s]);
+      if (c->leaf_uniform)
+        k_rk_update<Real><<<sgrid(c, N), 256, 0, c->stream>>>(S[CUP_F_VEL + q], S[CUP_F_TMP + q], N, (Real)ih3,
+                                                               (Real)beta[s]);
+      else
+        k_rk_update_blk<Real><<<bgrid(c, c->nblk, 8), 256, 0, c->stream>>>(
+            S[CUP_F_VEL + q], S[CUP_F_TMP + q], (const Real *)c->d_hw, c->nblk, (Real)alpha[s], (Real)beta[s]);
       c->launches++;
     }
   }
@@ -556,8 +578,6 @@ int projection_t(CupCtx *c, CupSolveInfo *info) {
 }  // namespace
 
 int stencil_run(CupCtx *c, CupStencilId id, const long long *list, long long n) {
-  if (id == CUP_ST_ADVDIFF)
-    CUP_TRY(need_uniform(c, "stencil_run(advdiff)"));
   if (c->nblk == 0) {
     set_error("stencil_run: no mesh uploaded");
     return CUP_ERR_STATE;
@@ -570,7 +590,10 @@ int stencil_run(CupCtx *c, CupStencilId id, const long long *list, long long n) 
 }
 
 int advdiff(CupCtx *c) {
-  CUP_TRY(need_uniform(c, "advdiff"));
+  if (c->nblk == 0) {
+    set_error("advdiff: no mesh uploaded");
+    return CUP_ERR_STATE;
+  }
   return c->real_bytes == 8 ? advdiff_t<double>(c) : advdiff_t<float>(c);
 }
 

@@ -136,11 +136,11 @@ def worker(case):
             R.state_set(st)
             R.stencil(name)
             g["st_" + name] = R.state_get()[:, f0:f0 + nc]
-        if case not in ADAPT:
-            R.set_scalars(dt=dt, nu=nu, uinf=uinf, step=5, mean_constraint=2)
-            R.state_set(st)
-            R.advdiff()
-            g["advdiff"] = R.state_get()[:, R.F_VEL:R.F_VEL + 6]  # VEL, TMP
+        R.set_scalars(dt=dt, nu=nu, uinf=uinf, step=5, mean_constraint=2)
+        R.state_set(st)
+        R.advdiff()
+        # VEL, TMP (multi-level cases keep only VEL: TMP is beta[2] = 0 times something)
+        g["advdiff"] = R.state_get()[:, R.F_VEL:R.F_VEL + (6 if case not in ADAPT else 3)]
     # --- pois_solve (main.c:4875): rhs = F_LHS with zero mean, guess F_PRES = 0
     if case != "b222_l0":
         for mc in ((2, 1) if tier != "big" and case not in ADAPT else (2,)):

@@ -88,7 +88,7 @@ def test_amr_pois_solve(built):
 
 
 @pytest.mark.parametrize("st,sid,f0,nc", [("prhs", capi.ST_PRHS, 8, 1), ("divp", capi.ST_DIVP, 5, 1),
-                                          ("gradp", capi.ST_GRADP, 5, 3)])
+                                          ("gradp", capi.ST_GRADP, 5, 3), ("advdiff", capi.ST_ADVDIFF, 5, 3)])
 def test_amr_projection_sweeps(built, st, sid, f0, nc):
     """k_prhs / k_divp / k_gradp with their flux correction on a 2-level mesh"""
     c = case("amr2")
@@ -114,4 +114,17 @@ def test_amr_projection(built):
     assert info.residual < max(1e-10, 1e-12 * info.rhs_norm)
     assert relerr(out[:, 1], ref[:, 0]) < 1e-7
     assert relerr(out[:, 2:5], ref[:, 1:4]) < 1e-9
+    ctx.close()
+
+
+def test_amr_advdiff_rk3(built):
+    """advdiff() (three k_advdiff sweeps with the ss = 3 coarse-fine ghost fill + RK3 updates)"""
+    c = case("amr2")
+    ctx = make_ctx(c)
+    s0 = c.state0()
+    ctx.state_h2d(s0)
+    ctx.advdiff()
+    out = np.zeros_like(s0)
+    ctx.state_d2h(out)
+    assert relerr(out[:, 2:5], c.g["advdiff"][:, 0:3]) < 1e-12
     ctx.close()
