@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libcup3d_b200.so")
 
 BS3 = 512
 F_CHI, F_PRES, F_VEL, F_TMP, F_LHS, F_N = 0, 1, 2, 5, 8, 9
-ST_LHS, ST_MG, ST_ADVDIFF, ST_PRHS, ST_DIVP, ST_GRADP = range(6)
+ST_LHS, ST_MG, ST_ADVDIFF, ST_PRHS, ST_DIVP, ST_GRADP, ST_VORT, ST_Q = range(8)
 
 
 class CupBlk(C.Structure):  # struct Blk, reference main.c:59-63

@@ -265,6 +265,80 @@ __global__ void __launch_bounds__(TPB) k_pres(LevelView lv, const Real *__restri
 }
 
 // ---------------------------------------------------------------------------
+// k_vort (main.c:5736): TMP_a = h^2/2 * ((d_b u_c) - (d_c u_b)) central differences, b=(a+1)%3,
+// c=(a+2)%3 (vorticity() then scales by 1/h^3, :5786);  k_q (:5762): Q-criterion
+// q = -1/2 sum_ab g_ab g_ba, g_ab = (u_a(+b) - u_a(-b)) / 2h  -> F_LHS.
+// All three velocity components are needed on all six faces.
+// ---------------------------------------------------------------------------
+template <typename Real, int WHAT>  // 0 vorticity, 1 Q
+__global__ void __launch_bounds__(TPB) k_velgrad(LevelView lv, const Real *__restrict__ v0,
+                                                 const Real *__restrict__ v1, const Real *__restrict__ v2,
+                                                 Real *__restrict__ o0, Real *__restrict__ o1, Real *__restrict__ o2,
+                                                 Real h) {
+  __shared__ Real tl[3][512];
+  __shared__ Real hl[3][6][64];
+  const int t = threadIdx.x, x = t & 7, y = t >> 3, a = t & 7, c2 = t >> 3;
+  const Real *vel[3] = {v0, v1, v2};
+  for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
+    const size_t own = (size_t)lv.act[b] * 512;
+    const int *nbr6 = lv.nbr + (size_t)b * 6;
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        tl[q][k * 64 + t] = vel[q][own + k * 64 + t];
+#pragma unroll
+      for (int f = 0; f < 6; f++) {
+        const int nb = nbr6[f];
+        const int p = (nb >= 0) ? ((f & 1) ? 0 : 7) : ((f & 1) ? 7 : 0);
+        const int idx = f < 2 ? (c2 << 6) + (a << 3) + p : (f < 4 ? (c2 << 6) + (p << 3) + a : (p << 6) + t);
+        // wall: nearest interior cell, wall-normal component negated (OP_BC, vflip = 0)
+        hl[q][f][t] = nb >= 0 ? vel[q][(size_t)nb * 512 + idx] : ((f >> 1) == q ? -vel[q][own + idx] : vel[q][own + idx]);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int i = k * 64 + t;
+      // g[q][d] = u_q(+d) - u_q(-d)
+      Real g[3][3];
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        const Real xp = x < 7 ? tl[q][i + 1] : hl[q][1][y + 8 * k], xm = x > 0 ? tl[q][i - 1] : hl[q][0][y + 8 * k];
+        const Real yp = y < 7 ? tl[q][i + 8] : hl[q][3][x + 8 * k], ym = y > 0 ? tl[q][i - 8] : hl[q][2][x + 8 * k];
+        const Real zp = k < 7 ? tl[q][i + 64] : hl[q][5][t], zm = k > 0 ? tl[q][i - 64] : hl[q][4][t];
+        g[q][0] = xp - xm;
+        g[q][1] = yp - ym;
+        g[q][2] = zp - zm;
+      }
+      if (WHAT == 0) {
+        const Real inv2h = (Real).5 * h * h;
+        // o_a = inv2h * ((LS(b,1,c) - LS(b,-1,c)) - (LS(c,1,b) - LS(c,-1,b))): LS(axis, k, comp)
+        o0[own + i] = inv2h * (g[2][1] - g[1][2]);
+        o1[own + i] = inv2h * (g[0][2] - g[2][0]);
+        o2[own + i] = inv2h * (g[1][0] - g[0][1]);
+      } else {
+        const Real inv2h = (Real).5 / h;
+        Real gg[3][3];
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+#pragma unroll
+          for (int d = 0; d < 3; d++)
+            gg[q][d] = inv2h * g[q][d];
+        Real qq = 0;
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+#pragma unroll
+          for (int d = 0; d < 3; d++)
+            qq -= (Real)0.5 * gg[q][d] * gg[d][q];
+        o0[own + i] = qq;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
 // pointwise pieces of projection() (main.c:5841-5916)
 // ---------------------------------------------------------------------------
 template <typename Real>
@@ -341,17 +415,6 @@ const Level *leaf_level(CupCtx *c) {
   return &c->lv[top];
 }
 
-int need_uniform(CupCtx *c, const char *what) {
-  if (c->nblk == 0) {
-    set_error("%s: no mesh uploaded", what);
-    return CUP_ERR_STATE;
-  }
-  if (!c->leaf_uniform) {
-    set_error("%s: multi-level (AMR) meshes are not available in this build", what);
-    return CUP_ERR_UNSUPPORTED;
-  }
-  return CUP_OK;
-}
 
 // RK3 stage update with per-block h (multi-level meshes): V += TMP*alpha/h^3 ; TMP *= beta
 template <typename Real>
@@ -478,6 +541,24 @@ int stencil_t(CupCtx *c, CupStencilId id, const int *d_sub, long long nsub) {
                                                                   S[CUP_F_TMP + 2], (Real)fac);
     break;
   }
+  case CUP_ST_VORT:
+    if (c->nranks > 1) {
+      set_error("k_vort is single-rank in this build");
+      return CUP_ERR_UNSUPPORTED;
+    }
+    k_velgrad<Real, 0><<<bgrid(c, c->nblk, 8), TPB, 0, c->stream>>>(lv, S[CUP_F_VEL], S[CUP_F_VEL + 1],
+                                                                    S[CUP_F_VEL + 2], S[CUP_F_TMP], S[CUP_F_TMP + 1],
+                                                                    S[CUP_F_TMP + 2], h);
+    break;
+  case CUP_ST_Q:
+    if (c->nranks > 1) {
+      set_error("k_q is single-rank in this build");
+      return CUP_ERR_UNSUPPORTED;
+    }
+    k_velgrad<Real, 1><<<bgrid(c, c->nblk, 8), TPB, 0, c->stream>>>(lv, S[CUP_F_VEL], S[CUP_F_VEL + 1],
+                                                                    S[CUP_F_VEL + 2], S[CUP_F_LHS], nullptr, nullptr,
+                                                                    h);
+    break;
   case CUP_ST_LHS:
   case CUP_ST_MG: {
     // k_lhs / k_mg on the state: F_PRES -> F_LHS, no mean term (that is pois_op's); st_mg has no

@@ -131,6 +131,8 @@ def worker(case):
     if tier != "big":
         keep = {"lhs": (R.F_LHS, 1), "advdiff": (R.F_TMP, 3), "prhs": (R.F_LHS, 1), "divp": (R.F_TMP, 1),
                 "gradp": (R.F_TMP, 3)}
+        if case not in ADAPT:
+            keep.update({"vort": (R.F_TMP, 3), "q": (R.F_LHS, 1)})
         for name, (f0, nc) in keep.items():
             R.set_scalars(dt=dt, nu=nu, uinf=uinf, step=5, mean_constraint=2)
             R.state_set(st)

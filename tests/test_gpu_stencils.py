@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 # stencil -> (C ABI id, first output field, components)
 ST = {"lhs": (capi.ST_LHS, capi.F_LHS, 1), "advdiff": (capi.ST_ADVDIFF, capi.F_TMP, 3),
       "prhs": (capi.ST_PRHS, capi.F_LHS, 1), "divp": (capi.ST_DIVP, capi.F_TMP, 1),
-      "gradp": (capi.ST_GRADP, capi.F_TMP, 3)}
+      "gradp": (capi.ST_GRADP, capi.F_TMP, 3), "vort": (capi.ST_VORT, capi.F_TMP, 3),
+      "q": (capi.ST_Q, capi.F_LHS, 1)}
 
 
 def make_ctx(c, step=5, **params):
