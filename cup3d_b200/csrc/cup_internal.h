@@ -99,6 +99,9 @@ struct Level {
   std::vector<int> order, bsend;           // [nact] act indices; [nact][6] send entry of (block, plane) or -1
   int *d_order = nullptr, *d_bsend = nullptr;
   unsigned int *d_counters = nullptr;      // [2] retired boundary blocks / CTAs
+  // fused prolongation (UpFuse, smooth_tma.cuh): [nact][7] parent index/octant of own + face neighbours
+  std::vector<int> upinfo;
+  int *d_upinfo = nullptr;
 };
 
 // pure-host result of the topology build (mesh.cpp); also what the CPU tests inspect

@@ -565,6 +565,7 @@ void free_mesh(CupCtx *c) {
     cudaFree(v.d_par);
     cudaFree(v.d_ext);
     cudaFree(v.d_hblk);
+    cudaFree(v.d_upinfo);
     cudaFree(v.d_inner);
     cudaFree(v.d_bnd);
     cudaFree(v.d_face_sslot);
@@ -618,6 +619,29 @@ int build_mesh(CupCtx *c, const CupBlk *gblk, long long G, const int *owner, con
     CUP_TRY(upload(&v.d_oct, v.oct));
     CUP_TRY(upload(&v.d_par, v.par));
     CUP_TRY(upload(&v.d_ext, v.ext));
+    // fused prolongation needs every parent local and every neighbour at the same level
+    v.upinfo.clear();
+    if (v.L >= 1 && v.uniform && !v.act.empty()) {
+      bool ok = true;
+      std::unordered_map<int, int> idx_of;
+      idx_of.reserve(v.act.size() * 2);
+      for (size_t k = 0; k < v.act.size(); k++) {
+        idx_of[v.act[k]] = (int)k;
+        ok = ok && v.pslot[k] >= (int)c->nblk;
+      }
+      if (ok) {
+        v.upinfo.resize(v.act.size() * 7);
+        for (size_t k = 0; k < v.act.size(); k++) {
+          auto pack = [&](size_t j) { return ((v.pslot[j] - (int)c->nblk) << 3) | v.oct[j]; };
+          v.upinfo[k * 7] = pack(k);
+          for (int f = 0; f < 6; f++) {
+            const int nb = v.nbr[k * 6 + f];
+            v.upinfo[k * 7 + 1 + f] = nb >= 0 ? pack((size_t)idx_of.at(nb)) : (nb == NBR_WALL ? pack(k) : -1);
+          }
+        }
+      }
+    }
+    CUP_TRY(upload(&v.d_upinfo, v.upinfo));
     CUP_TRY(upload(&v.d_inner, v.inner));
     CUP_TRY(upload(&v.d_bnd, v.bnd));
     CUP_TRY(upload(&v.d_face_sslot, v.face_sslot));

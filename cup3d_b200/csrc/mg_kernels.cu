@@ -246,6 +246,20 @@ __global__ void __launch_bounds__(256) k_level_sum(LevelView lv, SlotVec<Real> f
   }
 }
 
+// us <- u - us on the synthesised parents of a level: the correction d that the next finer
+// level's first post-smoothing sweep prolongates on the fly (UpFuse)
+template <typename Real>
+__global__ void __launch_bounds__(256) k_delta(LevelView lv, const int *__restrict__ sub, int nsub, SlotVec<Real> u,
+                                               SlotVec<Real> us) {
+  for (int i = blockIdx.x; i < nsub; i += gridDim.x) {
+    const int slot = lv.act[sub[i]];
+    const Real *a = u.at(slot);
+    Real *d = us.at(slot);
+    for (int j = threadIdx.x; j < 512; j += blockDim.x)
+      d[j] = a[j] - d[j];
+  }
+}
+
 // ---------------------------------------------------------------------------
 // mg_bottom (main.c:4808) when level 0 is ONE block (bpd = 1): subtract the
 // mean of f and run all MG_BOT = 50 sweeps inside a single CTA.  All six faces
@@ -366,11 +380,11 @@ static int smooth_minb() {
 template <typename Real>
 int launch_smooth0(CupCtx *c, int grid, LevelView lv, SlotVec<Real> src, SlotVec<Real> dst, SlotVec<Real> f, Real h,
                    Real invh, Real om, const double *fmean, const int *sub = nullptr, int nsub = -1,
-                   const FusedComm *fused = nullptr) {
+                   const FusedComm *fused = nullptr, const UpFuse *upf = nullptr, const void *d_extra = nullptr) {
   const Real *W = (const Real *)c->d_W;
   if (smooth_use_tma())
     return smooth_tma_launch<Real>(c, c->stream, grid, lv, sub, nsub < 0 ? lv.nact : nsub, src, dst, f, h, invh, om,
-                                   fmean, fused);
+                                   fmean, fused, upf, d_extra);
   if (sub) {
     set_error("block sub-lists need the TMA smoother");
     return CUP_ERR_UNSUPPORTED;
@@ -384,8 +398,23 @@ int launch_smooth0(CupCtx *c, int grid, LevelView lv, SlotVec<Real> src, SlotVec
   return CUP_OK;
 }
 
+static bool upfuse_ok() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("CUP_UPFUSE");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// can the prolongation into level v be folded into its first post-smoothing sweep?
+static bool can_upfuse(const CupCtx *c, const Level &v) {
+  return upfuse_ok() && smooth_use_tma() && v.d_upinfo != nullptr && c->nranks == 1;
+}
+
 template <typename Real>
-int smooth_level(CupCtx *c, Level &v, int n, Arr<Real> &a, bool first_is_zero, const double *fmean) {
+int smooth_level(CupCtx *c, Level &v, int n, Arr<Real> &a, bool first_is_zero, const double *fmean,
+                 bool first_is_prolong = false) {
   if (n == 0 || (v.act.empty() && v.gnact == 0))
     return CUP_OK;
   if (!v.uniform) {
@@ -412,6 +441,15 @@ int smooth_level(CupCtx *c, Level &v, int n, Arr<Real> &a, bool first_is_zero, c
     // Every sweep CONSUMES the ghost faces of `src` posted by whoever produced it and POSTS the
     // faces of `dst` as soon as its boundary blocks are done; blocks without a remote neighbour
     // are swept while those faces travel (comm/compute overlap on one stream).
+    if (it == 0 && first_is_prolong) {
+      // first post-smoothing sweep with the prolongation folded in: reads u + P(d), d in a.us
+      UpFuse up{v.d_upinfo};
+      CUP_TRY(launch_smooth0<Real>(c, grid, view(v), src, dst, a.f, h, invh, om, fmean, nullptr, -1, nullptr, &up,
+                                   a.us.extra));
+      c->launches++;
+      CUP_TRY(halo_post<Real>(c, v, dst));
+      continue;
+    }
     FusedComm fc;
     if (!zero && smooth_use_tma() && fused_ok() && comm_fused_desc(c, v, &fc)) {
       // ONE kernel: wait for the peers' faces, sweep boundary blocks, push their new faces over
@@ -578,6 +616,18 @@ int vcycle_t(CupCtx *c, const Real *d_in, Real *d_out) {
 bottom_done:
   for (int L = 1; L <= top; L++) {
     Level &v = c->lv[L];
+    if (can_upfuse(c, v)) {
+      // d = u_c - us on the parents (in place of us), then the first post-smoothing sweep of this
+      // level prolongates it on the fly: no separate pass over u (saves 2.25 Reals per cell)
+      Level &w = c->lv[L - 1];
+      k_delta<Real><<<grid_for(c, (long long)w.par.size(), 8), 256, 0, c->stream>>>(view(w), w.d_par,
+                                                                                   (int)w.par.size(), a.u0, a.us);
+      c->launches++;
+      g_tr.mark(c, "L" + std::to_string(L) + " up");
+      CUP_TRY(smooth_level<Real>(c, v, MG_POST, a, false, nullptr, true));
+      g_tr.mark(c, "L" + std::to_string(L) + " post");
+      continue;
+    }
     CUP_TRY(prolong_exchange<Real>(c, v, a.u0, a.us));
     if (!v.act.empty()) {
       const int grid = grid_for(c, (long long)v.act.size(), 16);

@@ -32,13 +32,19 @@ struct TmaCfg {
   static constexpr uint32_t BYTES = (512 * 2 + 64 * 2 + 64 * 2 + 64 * NCOL * 2) * (uint32_t)sizeof(Real);
 };
 
-template <typename Real, bool COMM>
-__global__ void __launch_bounds__(TPB, 12)
-    k_smooth_tma(LevelView lv, const int *__restrict__ sub, int nsub, FusedComm fc, SlotVec<Real> usrc, SlotVec<Real> udst, SlotVec<Real> fvec, const Real *__restrict__ Wl,
+template <typename Real, bool COMM, bool UPF>
+__global__ void __launch_bounds__(TPB, UPF ? 10 : 12)
+    k_smooth_tma(LevelView lv, const int *__restrict__ sub, int nsub, FusedComm fc, UpFuse up, SlotVec<Real> usrc, SlotVec<Real> udst, SlotVec<Real> fvec, const Real *__restrict__ Wl,
                  Real h, Real invh, Real omega, const double *__restrict__ fmean,
                  const __grid_constant__ CUtensorMap mx_leaf, const __grid_constant__ CUtensorMap my_leaf,
-                 const __grid_constant__ CUtensorMap mx_extra, const __grid_constant__ CUtensorMap my_extra) {
+                 const __grid_constant__ CUtensorMap mx_extra, const __grid_constant__ CUtensorMap my_extra,
+                 const __grid_constant__ CUtensorMap md_oct, const __grid_constant__ CUtensorMap md_x,
+                 const __grid_constant__ CUtensorMap md_y, const __grid_constant__ CUtensorMap md_z) {
   constexpr int NCOL = TmaCfg<Real>::NCOL;
+  __shared__ __align__(128) Real s_d[UPF ? 64 : 1];                // parent's correction, own octant [z][y][x]
+  __shared__ __align__(128) Real s_dz[2][UPF ? 16 : 1];            // neighbours' parents: 4x4 patches
+  __shared__ __align__(128) Real s_dy[2][UPF ? 16 : 1];
+  __shared__ __align__(128) Real s_dx[2][UPF ? 16 * NCOL : 1];
   __shared__ __align__(128) Real s_u[512];
   __shared__ __align__(128) Real s_f[512];
   __shared__ __align__(128) Real s_z[2][64];
@@ -68,7 +74,7 @@ __global__ void __launch_bounds__(TPB, 12)
   }
 
   // thread 0 is the TMA producer: stage one block (its u, f and six ghost faces)
-  auto issue = [&](int slot, const int (&nb)[6]) {
+  auto issue = [&](int slot, const int (&nb)[6], const int (&ui)[7]) {
     int wall = 0;
 #pragma unroll
     for (int f = 0; f < 6; f++)
@@ -78,7 +84,33 @@ __global__ void __launch_bounds__(TPB, 12)
     uint32_t bytes = TmaCfg<Real>::BYTES;
     if (nb[0] <= kRemote0) bytes -= 64 * (NCOL - 1) * (uint32_t)sizeof(Real);
     if (nb[1] <= kRemote0) bytes -= 64 * (NCOL - 1) * (uint32_t)sizeof(Real);
+    if (UPF) {
+      bytes += 64 * (uint32_t)sizeof(Real);
+#pragma unroll
+      for (int f = 0; f < 6; f++)
+        if (nb[f] > kRemote0)
+          bytes += (f < 2 ? 16 * NCOL : 16) * (uint32_t)sizeof(Real);
+    }
     mbar_arrive_expect_tx(&mbar, bytes);
+    if (UPF) {
+      // own octant of the parent's d, and for every face the 4x4 coarse cells behind it: the
+      // neighbour's parent on the neighbour's facing side, the own parent on the own side at a wall
+      tma_load_3d(s_d, &md_oct, 4 * (ui[0] & 1), 4 * ((ui[0] >> 1) & 1), (ui[0] >> 3) * 8 + 4 * ((ui[0] >> 2) & 1), &mbar);
+#pragma unroll
+      for (int f = 0; f < 6; f++) {
+        if (nb[f] <= kRemote0)
+          continue;
+        const int w = nb[f] >= 0 ? ui[1 + f] : ui[0];
+        const int ox = 4 * (w & 1), oy = 4 * ((w >> 1) & 1), oz = (w >> 3) * 8 + 4 * ((w >> 2) & 1);
+        const bool high = (nb[f] >= 0) ? !(f & 1) : (f & 1);
+        if (f < 2)
+          tma_load_3d(s_dx[f], &md_x, ox + (high ? 4 - NCOL : 0), oy, oz, &mbar);
+        else if (f < 4)
+          tma_load_3d(s_dy[f - 2], &md_y, ox, oy + (high ? 3 : 0), oz, &mbar);
+        else
+          tma_load_3d(s_dz[f - 4], &md_z, ox, oy, oz + (high ? 3 : 0), &mbar);
+      }
+    }
     const Real *own = usrc.at(slot);
     tma_load_1d(s_u, own, 512 * sizeof(Real), &mbar);
     tma_load_1d(s_f, fvec.at(slot), 512 * sizeof(Real), &mbar);
@@ -130,18 +162,23 @@ __global__ void __launch_bounds__(TPB, 12)
   }
   if (t == 0 && i < nsub) {
     const int b0 = sub ? sub[i] : i;
-    int nb[6];
+    int nb[6], ui[7] = {0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int f = 0; f < 6; f++)
       nb[f] = lv.nbr[(size_t)b0 * 6 + f];
-    issue(lv.act[b0], nb);
+    if (UPF) {
+#pragma unroll
+      for (int j = 0; j < 7; j++)
+        ui[j] = up.info[(size_t)b0 * 7 + j];
+    }
+    issue(lv.act[b0], nb, ui);
   }
   uint32_t phase = 0;
   for (; i < nsub; i += G) {
     const int b = sub ? sub[i] : i;
     const int slot = lv.act[b];
     // producer: fetch the NEXT block's indices now so they are in registers when needed
-    int nslot = 0, nnb[6] = {0, 0, 0, 0, 0, 0};
+    int nslot = 0, nnb[6] = {0, 0, 0, 0, 0, 0}, nui[7] = {0, 0, 0, 0, 0, 0, 0};
     const bool more = (i + G) < nsub;
     if (t == 0 && more) {
       const int bn = sub ? sub[i + G] : i + G;
@@ -149,6 +186,11 @@ __global__ void __launch_bounds__(TPB, 12)
 #pragma unroll
       for (int f = 0; f < 6; f++)
         nnb[f] = lv.nbr[(size_t)bn * 6 + f];
+      if (UPF) {
+#pragma unroll
+        for (int j = 0; j < 7; j++)
+          nui[j] = up.info[(size_t)bn * 7 + j];
+      }
     }
     mbar_wait(&mbar, phase);
     phase ^= 1;
@@ -191,13 +233,46 @@ __global__ void __launch_bounds__(TPB, 12)
         for (int k = 0; k < 8; k++)
           g[k] += s_y[1][k * 8 + x];
       }
+      if (UPF) {
+        // prolongated correction: own cells ...
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          uu[k] += s_d[(k >> 1) * 16 + (y >> 1) * 4 + (x >> 1)];
+        // ... and the ghosts (faces received from other ranks already carry it)
+        if (!(wall & 0x1000))
+          g[0] += s_dz[0][(y >> 1) * 4 + (x >> 1)];
+        if (!(wall & 0x2000))
+          g[7] += s_dz[1][(y >> 1) * 4 + (x >> 1)];
+        if (x == 0 && !(wall & 0x100)) {
+          const int col = (wall & 1) ? 0 : NCOL - 1;
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+            g[k] += s_dx[0][((k >> 1) * 4 + (y >> 1)) * NCOL + col];
+        }
+        if (x == 7 && !(wall & 0x200)) {
+          const int col = (wall & 2) ? NCOL - 1 : 0;
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+            g[k] += s_dx[1][((k >> 1) * 4 + (y >> 1)) * NCOL + col];
+        }
+        if (y == 0 && !(wall & 0x400)) {
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+            g[k] += s_dy[0][(k >> 1) * 4 + (x >> 1)];
+        }
+        if (y == 7 && !(wall & 0x800)) {
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+            g[k] += s_dy[1][(k >> 1) * 4 + (x >> 1)];
+        }
+      }
 #pragma unroll
       for (int k = 0; k < 8; k++)
         v[k] = invh * ((v[k] - q0) - h * g[k]);
     }
     __syncthreads();  // stage fully consumed
     if (t == 0 && more)
-      issue(nslot, nnb);
+      issue(nslot, nnb, nui);
     fdm_solve<Real>(v, ex, w, t);
     Real *ob = udst.at(slot);
 #pragma unroll
@@ -318,6 +393,11 @@ int get_map(CupCtx *c, const void *base, long long nblocks, int kind, CUtensorMa
   cuuint64_t dims[3] = {8, 8, (cuuint64_t)nblocks * 8};
   cuuint64_t strides[2] = {8 * rb, 64 * rb};
   cuuint32_t box[3] = {kind == 0 ? (cuuint32_t)(16 / rb) : 8u, kind == 0 ? 8u : 1u, 8u};
+  // kinds 2..5: parent-level correction d: 4^3 octant, x patch {16 B,4,4}, y patch {4,1,4}, z patch {4,4,1}
+  if (kind == 2) { box[0] = 4; box[1] = 4; box[2] = 4; }
+  if (kind == 3) { box[0] = (cuuint32_t)(16 / rb); box[1] = 4; box[2] = 4; }
+  if (kind == 4) { box[0] = 4; box[1] = 1; box[2] = 4; }
+  if (kind == 5) { box[0] = 4; box[1] = 4; box[2] = 1; }
   cuuint32_t es[3] = {1, 1, 1};
   CUtensorMap m;
   CUresult r = enc(&m, c->real_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
@@ -356,8 +436,16 @@ void free_tma_cache(CupCtx *c) {
 template <typename Real>
 int smooth_tma_launch(CupCtx *c, cudaStream_t stream, int grid, LevelView lv, const int *sub, int nsub,
                       SlotVec<Real> src, SlotVec<Real> dst, SlotVec<Real> f, Real h,
-                      Real invh, Real om, const double *fmean, const FusedComm *fused) {
+                      Real invh, Real om, const double *fmean, const FusedComm *fused, const UpFuse *upf,
+                      const void *d_extra) {
   CUtensorMap mxl, myl, mxe, mye;
+  CUtensorMap md[4];
+  if (upf) {
+    for (int k = 0; k < 4; k++)
+      CUP_TRY(get_map(c, d_extra, c->nslot - c->nblk + 1, 2 + k, &md[k]));
+  } else {
+    memset(md, 0, sizeof md);
+  }
   const long long nleaf = c->nblk, nx = c->nslot - c->nblk + 1;
   // a part that holds no blocks of this vector still needs a valid (unused) descriptor
   const void *lb = src.leaf ? (const void *)src.leaf : (const void *)src.extra;
@@ -366,20 +454,30 @@ int smooth_tma_launch(CupCtx *c, cudaStream_t stream, int grid, LevelView lv, co
   CUP_TRY(get_map(c, lb, src.leaf ? nleaf : 1, 1, &myl));
   CUP_TRY(get_map(c, eb, src.extra ? nx : 1, 0, &mxe));
   CUP_TRY(get_map(c, eb, src.extra ? nx : 1, 1, &mye));
-  if (fused)
-    k_smooth_tma<Real, true><<<grid, TPB, 0, stream>>>(lv, sub, nsub, *fused, src, dst, f, (const Real *)c->d_W, h,
-                                                        invh, om, fmean, mxl, myl, mxe, mye);
+  const Real *W = (const Real *)c->d_W;
+  if (upf && fused)
+    k_smooth_tma<Real, true, true><<<grid, TPB, 0, stream>>>(lv, sub, nsub, *fused, *upf, src, dst, f, W, h, invh, om,
+                                                              fmean, mxl, myl, mxe, mye, md[0], md[1], md[2], md[3]);
+  else if (upf)
+    k_smooth_tma<Real, false, true><<<grid, TPB, 0, stream>>>(lv, sub, nsub, FusedComm{}, *upf, src, dst, f, W, h,
+                                                               invh, om, fmean, mxl, myl, mxe, mye, md[0], md[1],
+                                                               md[2], md[3]);
+  else if (fused)
+    k_smooth_tma<Real, true, false><<<grid, TPB, 0, stream>>>(lv, sub, nsub, *fused, UpFuse{}, src, dst, f, W, h, invh,
+                                                               om, fmean, mxl, myl, mxe, mye, md[0], md[1], md[2],
+                                                               md[3]);
   else
-    k_smooth_tma<Real, false><<<grid, TPB, 0, stream>>>(lv, sub, nsub, FusedComm{}, src, dst, f,
-                                                         (const Real *)c->d_W, h, invh, om, fmean, mxl, myl, mxe, mye);
+    k_smooth_tma<Real, false, false><<<grid, TPB, 0, stream>>>(lv, sub, nsub, FusedComm{}, UpFuse{}, src, dst, f, W, h,
+                                                                invh, om, fmean, mxl, myl, mxe, mye, md[0], md[1],
+                                                                md[2], md[3]);
   return CUP_OK;
 }
 
 template int smooth_tma_launch<double>(CupCtx *, cudaStream_t, int, LevelView, const int *, int, SlotVec<double>,
                                        SlotVec<double>, SlotVec<double>, double, double, double, const double *,
-                                       const FusedComm *);
+                                       const FusedComm *, const UpFuse *, const void *);
 template int smooth_tma_launch<float>(CupCtx *, cudaStream_t, int, LevelView, const int *, int, SlotVec<float>,
                                       SlotVec<float>, SlotVec<float>, float, float, float, const double *,
-                                      const FusedComm *);
+                                      const FusedComm *, const UpFuse *, const void *);
 
 }  // namespace cup

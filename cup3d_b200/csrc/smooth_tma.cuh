@@ -25,9 +25,19 @@ struct FusedComm {
   int nbnd;
 };
 
+// Fused prolongation (mg_up/mg_up2, main.c:4787-4807): the first post-smoothing sweep of a level
+// reads u + P(d), d = u_c - us of the parent level (precomputed in place of us), instead of a
+// separate pass that adds the correction to u.  Per block the producer additionally stages the
+// 4^3 octant of the parent's d and the 4x4 patches of the six neighbours' parents.
+struct UpFuse {
+  const int *info;  // [nact][7]: own + six face neighbours: (parent index in the extra part << 3) | octant;
+                    // -1 for faces received from another rank (their owner adds the correction)
+};
+
 template <typename Real>
 int smooth_tma_launch(CupCtx *c, cudaStream_t stream, int grid, LevelView lv, const int *sub, int nsub,
                       SlotVec<Real> src, SlotVec<Real> dst, SlotVec<Real> f, Real h,
-                      Real invh, Real om, const double *fmean, const FusedComm *fused = nullptr);
+                      Real invh, Real om, const double *fmean, const FusedComm *fused = nullptr,
+                      const UpFuse *upf = nullptr, const void *d_extra = nullptr);
 void free_tma_cache(CupCtx *c);
 }  // namespace cup
