@@ -401,15 +401,17 @@ int launch_smooth0(CupCtx *c, int grid, LevelView lv, SlotVec<Real> src, SlotVec
 static bool upfuse_ok() {
   static int v = -1;
   if (v < 0) {
+    // measured (r01, 512^3): no gain -- the sweep with 15 TMA operations per block and 96 registers
+    // loses what the saved pass over u wins -- so it is opt-in (CUP_UPFUSE=1), fp64 only
     const char *e = getenv("CUP_UPFUSE");
-    v = (e && atoi(e) == 0) ? 0 : 1;
+    v = (e && atoi(e) == 1) ? 1 : 0;
   }
   return v == 1;
 }
 
 // can the prolongation into level v be folded into its first post-smoothing sweep?
 static bool can_upfuse(const CupCtx *c, const Level &v) {
-  return upfuse_ok() && smooth_use_tma() && v.d_upinfo != nullptr && c->nranks == 1;
+  return upfuse_ok() && smooth_use_tma() && v.d_upinfo != nullptr && c->nranks == 1 && c->real_bytes == 8;
 }
 
 template <typename Real>
