@@ -69,6 +69,7 @@ SYMBOLS = {
     "cup_advdiff": (_i, [_vp]),
     "cup_projection": (_i, [_vp, C.POINTER(CupSolveInfo)]),
     "cup_projection_udef_ready": (_i, [_vp, _i]),
+    "cup_umax": (_i, [_vp, _dp]),
     "cup_comm_init": (_i, [_vp, _i, _i, _vp, C.c_size_t]),
     "cup_nccl_unique_id": (_i, [_vp, C.c_size_t]),
     "cup_plan_build": (_i, [C.POINTER(CupBlk), _ll, C.POINTER(_i), _i, _i, C.POINTER(_i), _i, _i,
@@ -271,6 +272,11 @@ class Context:
         info = CupSolveInfo()
         check(self.L.cup_projection(self.h, C.byref(info)))
         return info
+
+    def umax(self):
+        r = C.c_double()
+        check(self.L.cup_umax(self.h, C.byref(r)))
+        return r.value
 
     def synchronize(self):
         check(self.L.cup_synchronize(self.h))

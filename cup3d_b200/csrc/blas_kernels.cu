@@ -83,6 +83,65 @@ int wdot(CupCtx *c, const void *a, const void *b, int idx) {
   return comm_allreduce(c, idx, 1);  // MPI_Allreduce of pois_dot, main.c:4860
 }
 
+// sta_umax (main.c:5918-5939): max over cells of max(|u+uinf_x|, |v+uinf_y|, |w+uinf_z|).  The
+// result is non-negative, so the IEEE bit pattern orders like the value and atomicMax on it works.
+template <typename Real>
+__global__ void __launch_bounds__(256) k_umax(const Real *__restrict__ u, const Real *__restrict__ v,
+                                              const Real *__restrict__ w, long long n, double ux, double uy, double uz,
+                                              unsigned long long *out) {
+  __shared__ double red[8];
+  double m = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double a = fabs((double)u[i] + ux), b = fabs((double)v[i] + uy), cc = fabs((double)w[i] + uz);
+    double ul = a;
+    if (ul < b)
+      ul = b;
+    if (ul < cc)
+      ul = cc;
+    if (m < ul)
+      m = ul;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double t = __shfl_xor_sync(0xffffffffu, m, o);
+    m = m < t ? t : m;
+  }
+  if ((threadIdx.x & 31) == 0)
+    red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; i++)
+      m = m < red[i] ? red[i] : m;
+    m = m < red[0] ? red[0] : m;
+    atomicMax(out, (unsigned long long)__double_as_longlong(m));
+  }
+}
+
+int umax(CupCtx *c, double *out) {
+  if (c->nblk == 0) {
+    set_error("umax: no mesh uploaded");
+    return CUP_ERR_STATE;
+  }
+  const long long n = c->nblk * 512;
+  double *d = c->d_scal + 6;
+  CUP_CUDA(cudaMemsetAsync(d, 0, sizeof(double), c->stream));
+  if (c->real_bytes == 8)
+    k_umax<double><<<sgrid(c, n), 256, 0, c->stream>>>((const double *)c->state[CUP_F_VEL],
+                                                       (const double *)c->state[CUP_F_VEL + 1],
+                                                       (const double *)c->state[CUP_F_VEL + 2], n, c->prm.uinf[0],
+                                                       c->prm.uinf[1], c->prm.uinf[2], (unsigned long long *)d);
+  else
+    k_umax<float><<<sgrid(c, n), 256, 0, c->stream>>>((const float *)c->state[CUP_F_VEL],
+                                                      (const float *)c->state[CUP_F_VEL + 1],
+                                                      (const float *)c->state[CUP_F_VEL + 2], n, c->prm.uinf[0],
+                                                      c->prm.uinf[1], c->prm.uinf[2], (unsigned long long *)d);
+  c->launches++;
+  CUP_CUDA(cudaGetLastError());
+  CUP_TRY(comm_allreduce_max(c, 6, 1));
+  CUP_TRY(fetch_scalars(c, 6, 1));
+  *out = c->h_scal[6];
+  return CUP_OK;
+}
+
 int fetch_scalars(CupCtx *c, int first, int n) {
   CUP_CUDA(cudaMemcpyAsync(c->h_scal + first, c->d_scal + first, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost,
                            c->stream));

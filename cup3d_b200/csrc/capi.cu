@@ -274,6 +274,7 @@ int cup_pois_dot_dev(CupCtx *c, const void *a, const void *b, double *result) {
 }
 
 int cup_pois_solve(CupCtx *c, CupSolveInfo *info) { return pois_solve(c, info); }
+int cup_umax(CupCtx *c, double *out) { return umax(c, out); }
 int cup_advdiff(CupCtx *c) { return advdiff(c); }
 int cup_projection(CupCtx *c, CupSolveInfo *info) { return projection(c, info); }
 int cup_projection_udef_ready(CupCtx *c, int flag) {

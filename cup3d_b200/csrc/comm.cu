@@ -216,6 +216,14 @@ int comm_allreduce(CupCtx *c, int first, int n) {
 // ===========================================================================
 enum { K_FACE = 0, K_RES = 1, K_PRO = 2 };
 
+int comm_allreduce_max(CupCtx *c, int first, int n) {
+  if (c->nranks == 1)
+    return CUP_OK;
+  Comm *cm = (Comm *)c->comm;
+  CUP_NCCL(g_nccl.AllReduce(c->d_scal + first, c->d_scal + first, (size_t)n, ncclDouble, ncclMax, cm->nccl, c->stream));
+  return CUP_OK;
+}
+
 // grouped point-to-point exchange: entries of `entry_bytes` bytes, peer-major on both sides
 static int exchange(CupCtx *c, const void *sbuf, const std::vector<int> &scnt, void *rbuf,
                     const std::vector<int> &rcnt, size_t entry_bytes) {

@@ -7,6 +7,7 @@
 namespace cup {
 int comm_gather_blocks(CupCtx *c, const CupBlk *blk, long long n, std::vector<CupBlk> &gblk, std::vector<int> &owner);
 int comm_allreduce(CupCtx *c, int first, int n);  // in-place sum of d_scal[first..first+n) over ranks
+int comm_allreduce_max(CupCtx *c, int first, int n);
 int comm_alloc_level_buffers(CupCtx *c);
 struct FusedComm;
 // descriptor of the fused sweep+exchange for level v; false when the level cannot use it

@@ -184,6 +184,7 @@ int time_smooth(CupCtx *c, int level, int reps, float *ms);
 // blas_kernels.cu
 int wdot(CupCtx *c, const void *a, const void *b, int scal_idx);  // -> d_scal[idx] (accumulates from 0)
 int fetch_scalars(CupCtx *c, int first, int n);                   // d_scal -> h_scal, synchronises
+int umax(CupCtx *c, double *out);                                 // sta_umax over all ranks
 
 // solver.cu
 int pois_solve(CupCtx *c, CupSolveInfo *info);

@@ -137,6 +137,10 @@ int cup_projection(CupCtx *ctx, CupSolveInfo *info);
  * has uploaded F_TMP = fish_tmpv() result already and the zeroing is skipped. */
 int cup_projection_udef_ready(CupCtx *ctx, int flag);
 
+/* sta_umax (main.c:5918): max over all cells (all ranks) of max_a |u_a + uinf_a|; the time-step
+ * control (sta_dt) needs only this scalar, so F_VEL can stay on the device. */
+int cup_umax(CupCtx *ctx, double *umax);
+
 /* One rank per GPU.  nccl_id = the 128 bytes of an ncclUniqueId created on
  * rank 0 and distributed by the caller (torch.distributed / MPI_Bcast). */
 int cup_comm_init(CupCtx *ctx, int rank, int nranks, const void *nccl_id, size_t id_bytes);

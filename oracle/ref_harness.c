@@ -156,6 +156,9 @@ API double ref_time_stencil(int id, int w, int n) {
   return now() - t0;
 }
 
+/* sta_umax (main.c:5918): max over cells of max_a |u_a + uinf_a| */
+API double ref_umax(void) { return sta_umax(); }
+
 /* one mesh adaptation pass with the reference's own tagging (main.c:4012ff) */
 API void ref_mesh_adapt(double rtol, double ctol) {
   sim.rtol = rtol;

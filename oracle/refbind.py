@@ -55,6 +55,7 @@ def init(**kw):
         raise RuntimeError("ref_init failed: %d" % rc)
     lib.ref_nblk.restype = C.c_longlong
     lib.ref_pois_dot.restype = C.c_double
+    lib.ref_umax.restype = C.c_double
     lib.ref_time_vcycle.restype = C.c_double
     lib.ref_time_stencil.restype = C.c_double
     lib.ref_set_scalars.argtypes = [C.c_double] * 5 + [C.c_int, C.c_int, C.c_double, C.c_double]
@@ -137,6 +138,10 @@ def advdiff():
 
 def projection():
     _lib.ref_projection()
+
+
+def umax():
+    return float(_lib.ref_umax())
 
 
 def stencil(name):

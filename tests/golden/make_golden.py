@@ -128,6 +128,9 @@ def worker(case):
     dt, nu, uinf = 1e-3, 1e-3, (0.1, -0.05, 0.02)
     g["scalars"] = np.array([dt, nu, *uinf])
     st = state0(F, n)
+    R.set_scalars(dt=dt, nu=nu, uinf=uinf, step=5, mean_constraint=2)
+    R.state_set(st)
+    g["umax"] = np.float64(R.umax())  # sta_umax (main.c:5918) of the test state
     if tier != "big":
         keep = {"lhs": (R.F_LHS, 1), "advdiff": (R.F_TMP, 3), "prhs": (R.F_LHS, 1), "divp": (R.F_TMP, 1),
                 "gradp": (R.F_TMP, 3)}

@@ -77,3 +77,13 @@ def test_projection(built, name, step):
     ev = relerr(out[:, 2:5], ref[:, 1:4])
     assert ep < 1e-7 and ev < 1e-9, (ep, ev, info.iterations)
     ctx.close()
+
+
+@pytest.mark.parametrize("name", STENCIL_CASES + ["amr2"])
+def test_umax(built, name):
+    """sta_umax (main.c:5918) on the device"""
+    c = case(name)
+    ctx = make_ctx(c)
+    ctx.state_h2d(c.state0())
+    assert abs(ctx.umax() - float(c.g["umax"])) <= 1e-15 * float(c.g["umax"])
+    ctx.close()
