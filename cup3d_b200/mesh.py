@@ -76,3 +76,89 @@ def cell_centers(ib, rb):
     Y = np.broadcast_to(Y, (len(h), 8, 8, 8))
     Z = np.broadcast_to(Z, (len(h), 8, 8, 8))
     return X, Y, Z
+
+
+def amr_blocks(base_level, max_level, refine, bpd=(1, 1, 1), extent=1.0):
+    """A 2:1-balanced multi-level block list for synthetic tests/benchmarks.
+
+    Starts from the uniform `base_level` grid and refines every leaf (below `max_level`) for which
+    refine(level, x0, y0, z0, size) is true, then enforces the reference's balance rule (no leaf
+    touches -- over its 26 neighbours -- a leaf more than one level coarser; mesh_fix, main.c:3717).
+    Leaves are ordered along the Hilbert curve of the finest level (children stay contiguous), like
+    the reference's blk_sort.  Returns (ib, rb) as uniform_blocks."""
+    h0 = extent / max(bpd) / 8.0
+    leaves = set()
+    n0 = [b << base_level for b in bpd]
+    for k in range(n0[2]):
+        for j in range(n0[1]):
+            for i in range(n0[0]):
+                leaves.add((base_level, i, j, k))
+
+    def split(leaf):
+        l, i, j, k = leaf
+        leaves.discard(leaf)
+        for dk in range(2):
+            for dj in range(2):
+                for di in range(2):
+                    leaves.add((l + 1, 2 * i + di, 2 * j + dj, 2 * k + dk))
+
+    for _ in range(max_level - base_level):
+        for leaf in list(leaves):
+            l, i, j, k = leaf
+            s = 8 * h0 / (1 << l)
+            if l < max_level and refine(l, i * s, j * s, k * s, s):
+                split(leaf)
+
+    def covering(l, i, j, k):
+        """leaf covering block (l,i,j,k) at its own or a coarser level, else None"""
+        while l >= 0:
+            if (l, i, j, k) in leaves:
+                return (l, i, j, k)
+            l, i, j, k = l - 1, i >> 1, j >> 1, k >> 1
+        return None
+
+    changed = True
+    while changed:
+        changed = False
+        for leaf in sorted(leaves, key=lambda t: -t[0]):
+            if leaf not in leaves:
+                continue
+            l, i, j, k = leaf
+            nl = [b << l for b in bpd]
+            for dk in (-1, 0, 1):
+                for dj in (-1, 0, 1):
+                    for di in (-1, 0, 1):
+                        a, b, c = i + di, j + dj, k + dk
+                        if (di, dj, dk) == (0, 0, 0) or not (0 <= a < nl[0] and 0 <= b < nl[1] and 0 <= c < nl[2]):
+                            continue
+                        cov = covering(l, a, b, c)
+                        if cov is not None and cov[0] < l - 1:
+                            split(cov)
+                            changed = True
+    arr = np.array(sorted(leaves), dtype=np.int64)
+    lv, ix, iy, iz = arr[:, 0], arr[:, 1], arr[:, 2], arr[:, 3]
+    sh = max_level - lv
+    nmax = max(bpd) << max_level
+    bits = int(np.ceil(np.log2(nmax))) if nmax > 1 else 0
+    key = hilbert_index(ix << sh, iy << sh, iz << sh, bits)
+    order = np.lexsort((lv, key))
+    lv, ix, iy, iz = lv[order], ix[order], iy[order], iz[order]
+    h = h0 / (1 << lv).astype(np.float64)
+    ib = np.stack([lv, ix, iy, iz], 1).astype(np.int32)
+    rb = np.stack([h, ix * 8 * h, iy * 8 * h, iz * 8 * h], 1).astype(np.float64)
+    return ib, rb
+
+
+def sphere_shell(center, radius, band=1.0):
+    """refine() predicate: blocks intersecting the shell | |x - c| - radius | < band * block size"""
+    c = np.asarray(center, float)
+
+    def f(level, x0, y0, z0, s):
+        lo = np.array([x0, y0, z0])
+        nearest = np.clip(c, lo, lo + s)
+        dmin = np.linalg.norm(nearest - c)
+        far = np.where(np.abs(lo - c) > np.abs(lo + s - c), lo, lo + s)
+        dmax = np.linalg.norm(far - c)
+        return dmin - band * s < radius < dmax + band * s
+
+    return f
