@@ -66,7 +66,8 @@ __device__ __forceinline__ void halo_amr_phase2(const Real *own, const int *nbr6
 // a coarse face depends on the block's own OLD values through the blend, which is exactly what
 // A u_old contains).
 template <typename Real>
-__global__ void __launch_bounds__(TPB) k_smooth_amr(LevelView lv, SlotVec<Real> usrc, SlotVec<Real> ucan,
+__global__ void __launch_bounds__(TPB) k_smooth_amr(LevelView lv, const int *__restrict__ sub, int nsub,
+                                                    SlotVec<Real> usrc, SlotVec<Real> ucan,
                                                     SlotVec<Real> udst, SlotVec<Real> fvec,
                                                     const Real *__restrict__ Wl, Real h, Real invh, Real omega,
                                                     const double *__restrict__ fmean, int zero_src) {
@@ -79,7 +80,8 @@ __global__ void __launch_bounds__(TPB) k_smooth_amr(LevelView lv, SlotVec<Real> 
   for (int k = 0; k < 8; k++)
     w[k] = Wl[k * 64 + t];
   const Real q0 = fmean ? (Real)(*fmean) : (Real)0;
-  for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
+  for (int i = blockIdx.x; i < nsub; i += gridDim.x) {
+    const int b = sub ? sub[i] : i;
     const int slot = lv.act[b];
     const Real *fb = fvec.at(slot);
     Real uu[8], v[8];
@@ -117,15 +119,16 @@ __global__ void __launch_bounds__(TPB) k_smooth_amr(LevelView lv, SlotVec<Real> 
 
 // mg_down on a level with coarser neighbours
 template <typename Real>
-__global__ void __launch_bounds__(TPB) k_down_amr(LevelView lv, const int *__restrict__ pslot,
-                                                  const int *__restrict__ oct, SlotVec<Real> u, SlotVec<Real> f,
-                                                  Real h) {
+__global__ void __launch_bounds__(TPB) k_down_amr(LevelView lv, const int *__restrict__ sub, int nsub,
+                                                  const int *__restrict__ pslot, const int *__restrict__ oct,
+                                                  SlotVec<Real> u, SlotVec<Real> f, Real h) {
   __shared__ Real tu[512];
   __shared__ Real tr[512];
   __shared__ Real halo[6][64];
   __shared__ Real patch[6][16];
   const int t = threadIdx.x, x = t & 7, y = t >> 3;
-  for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
+  for (int i = blockIdx.x; i < nsub; i += gridDim.x) {
+    const int b = sub ? sub[i] : i;
     const int slot = lv.act[b];
     const Real *ub = u.at(slot);
     const Real *fb = f.at(slot);
@@ -469,8 +472,10 @@ static inline int agrid(const CupCtx *c, long long n) {
 
 template <typename Real>
 int smooth_amr_launch(CupCtx *c, LevelView lv, SlotVec<Real> src, SlotVec<Real> can, SlotVec<Real> dst,
-                      SlotVec<Real> f, Real h, const double *fmean, bool zero_src) {
-  k_smooth_amr<Real><<<agrid(c, lv.nact), TPB, 0, c->stream>>>(lv, src, can, dst, f, (const Real *)c->d_W, h,
+                      SlotVec<Real> f, Real h, const double *fmean, bool zero_src, const int *sub, int nsub) {
+  if (nsub < 0)
+    nsub = lv.nact;
+  k_smooth_amr<Real><<<agrid(c, nsub), TPB, 0, c->stream>>>(lv, sub, nsub, src, can, dst, f, (const Real *)c->d_W, h,
                                                                (Real)(1.0 / (double)h), (Real)0.8, fmean,
                                                                zero_src ? 1 : 0);
   return CUP_OK;
@@ -478,8 +483,10 @@ int smooth_amr_launch(CupCtx *c, LevelView lv, SlotVec<Real> src, SlotVec<Real> 
 
 template <typename Real>
 int down_amr_launch(CupCtx *c, LevelView lv, const int *pslot, const int *oct, SlotVec<Real> u, SlotVec<Real> f,
-                    Real h) {
-  k_down_amr<Real><<<agrid(c, lv.nact), TPB, 0, c->stream>>>(lv, pslot, oct, u, f, h);
+                    Real h, const int *sub, int nsub) {
+  if (nsub < 0)
+    nsub = lv.nact;
+  k_down_amr<Real><<<agrid(c, nsub), TPB, 0, c->stream>>>(lv, sub, nsub, pslot, oct, u, f, h);
   return CUP_OK;
 }
 
@@ -524,13 +531,13 @@ template int prhs_amr_launch<double>(CupCtx *, LevelView, const void *, double *
 template int prhs_amr_launch<float>(CupCtx *, LevelView, const void *, float *const *, float);
 
 template int smooth_amr_launch<double>(CupCtx *, LevelView, SlotVec<double>, SlotVec<double>, SlotVec<double>,
-                                       SlotVec<double>, double, const double *, bool);
+                                       SlotVec<double>, double, const double *, bool, const int *, int);
 template int smooth_amr_launch<float>(CupCtx *, LevelView, SlotVec<float>, SlotVec<float>, SlotVec<float>,
-                                      SlotVec<float>, float, const double *, bool);
+                                      SlotVec<float>, float, const double *, bool, const int *, int);
 template int down_amr_launch<double>(CupCtx *, LevelView, const int *, const int *, SlotVec<double>, SlotVec<double>,
-                                     double);
+                                     double, const int *, int);
 template int down_amr_launch<float>(CupCtx *, LevelView, const int *, const int *, SlotVec<float>, SlotVec<float>,
-                                    float);
+                                    float, const int *, int);
 template int apply_amr_launch<double>(CupCtx *, LevelView, const int *, int, SlotVec<double>, SlotVec<double>,
                                       SlotVec<double>, double, const void *, const double *, int);
 template int apply_amr_launch<float>(CupCtx *, LevelView, const int *, int, SlotVec<float>, SlotVec<float>,

@@ -7,10 +7,11 @@ int amr_setup_constants();
 // src: ping-pong source (same-level neighbours); can: canonical vector (coarser leaves)
 template <typename Real>
 int smooth_amr_launch(CupCtx *c, LevelView lv, SlotVec<Real> src, SlotVec<Real> can, SlotVec<Real> dst,
-                      SlotVec<Real> f, Real h, const double *fmean, bool zero_src);
+                      SlotVec<Real> f, Real h, const double *fmean, bool zero_src, const int *sub = nullptr,
+                      int nsub = -1);
 template <typename Real>
 int down_amr_launch(CupCtx *c, LevelView lv, const int *pslot, const int *oct, SlotVec<Real> u, SlotVec<Real> f,
-                    Real h);
+                    Real h, const int *sub = nullptr, int nsub = -1);
 // mode 0: out = A u (+shift h^3); 1: tau (out += A u, us = u); 2: out = A u with flux correction
 template <typename Real>
 int apply_amr_launch(CupCtx *c, LevelView lv, const int *sub, int nsub, SlotVec<Real> u, SlotVec<Real> out,

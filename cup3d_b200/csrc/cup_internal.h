@@ -102,6 +102,10 @@ struct Level {
   // fused prolongation (UpFuse, smooth_tma.cuh): [nact][7] parent index/octant of own + face neighbours
   std::vector<int> upinfo;
   int *d_upinfo = nullptr;
+  // levels with coarse-fine interfaces: blocks whose six neighbours are all same-level / wall run
+  // the fast (TMA) kernels, the others the generic ghost fill
+  std::vector<int> reg, irr, par_reg, par_irr;
+  int *d_reg = nullptr, *d_irr = nullptr, *d_par_reg = nullptr, *d_par_irr = nullptr;
 };
 
 // pure-host result of the topology build (mesh.cpp); also what the CPU tests inspect

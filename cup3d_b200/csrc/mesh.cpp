@@ -566,6 +566,10 @@ void free_mesh(CupCtx *c) {
     cudaFree(v.d_ext);
     cudaFree(v.d_hblk);
     cudaFree(v.d_upinfo);
+    cudaFree(v.d_reg);
+    cudaFree(v.d_irr);
+    cudaFree(v.d_par_reg);
+    cudaFree(v.d_par_irr);
     cudaFree(v.d_inner);
     cudaFree(v.d_bnd);
     cudaFree(v.d_face_sslot);
@@ -642,6 +646,24 @@ int build_mesh(CupCtx *c, const CupBlk *gblk, long long G, const int *owner, con
       }
     }
     CUP_TRY(upload(&v.d_upinfo, v.upinfo));
+    v.reg.clear();
+    v.irr.clear();
+    v.par_reg.clear();
+    v.par_irr.clear();
+    if (!v.uniform) {
+      std::vector<char> is_irr(v.act.size(), 0);
+      for (size_t k = 0; k < v.act.size(); k++) {
+        for (int f = 0; f < 6; f++)
+          is_irr[k] |= (v.nbr[k * 6 + f] == NBR_COARSE || v.nbr[k * 6 + f] == NBR_FINE);
+        (is_irr[k] ? v.irr : v.reg).push_back((int)k);
+      }
+      for (int k : v.par)
+        (is_irr[(size_t)k] ? v.par_irr : v.par_reg).push_back(k);
+    }
+    CUP_TRY(upload(&v.d_reg, v.reg));
+    CUP_TRY(upload(&v.d_irr, v.irr));
+    CUP_TRY(upload(&v.d_par_reg, v.par_reg));
+    CUP_TRY(upload(&v.d_par_irr, v.par_irr));
     CUP_TRY(upload(&v.d_inner, v.inner));
     CUP_TRY(upload(&v.d_bnd, v.bnd));
     CUP_TRY(upload(&v.d_face_sslot, v.face_sslot));

@@ -398,6 +398,15 @@ int launch_smooth0(CupCtx *c, int grid, LevelView lv, SlotVec<Real> src, SlotVec
   return CUP_OK;
 }
 
+static bool amr_split() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("CUP_AMR_SPLIT");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static bool upfuse_ok() {
   static int v = -1;
   if (v < 0) {
@@ -428,7 +437,21 @@ int smooth_level(CupCtx *c, Level &v, int n, Arr<Real> &a, bool first_is_zero, c
     for (int it = 0; it < n; it++) {
       SlotVec<Real> &src = (it & 1) ? a.u1 : a.u0;
       SlotVec<Real> &dst = (it & 1) ? a.u0 : a.u1;
-      CUP_TRY(smooth_amr_launch<Real>(c, view(v), src, a.u0, dst, a.f, (Real)v.h, fmean, it == 0 && first_is_zero));
+      const bool zero = it == 0 && first_is_zero;
+      if (!zero && smooth_use_tma() && amr_split() && !v.reg.empty()) {
+        // regular blocks (all neighbours same level / wall): TMA sweep; interface blocks: generic
+        const Real hh = (Real)v.h;
+        CUP_TRY(launch_smooth0<Real>(c, grid_for(c, (long long)v.reg.size(), smooth_per_sm()), view(v), src, dst, a.f,
+                                     hh, (Real)(1.0 / v.h), (Real)0.8, fmean, v.d_reg, (int)v.reg.size()));
+        c->launches++;
+        if (!v.irr.empty()) {
+          CUP_TRY(smooth_amr_launch<Real>(c, view(v), src, a.u0, dst, a.f, hh, fmean, false, v.d_irr,
+                                          (int)v.irr.size()));
+          c->launches++;
+        }
+        continue;
+      }
+      CUP_TRY(smooth_amr_launch<Real>(c, view(v), src, a.u0, dst, a.f, (Real)v.h, fmean, zero));
       c->launches++;
     }
     CUP_CUDA(cudaGetLastError());
@@ -559,7 +582,15 @@ int vcycle_t(CupCtx *c, const Real *d_in, Real *d_out) {
     CUP_TRY(halo_wait(c, v));  // faces of u0 were posted by the last sweep
     if (!v.act.empty()) {
       const int grid = grid_for(c, (long long)v.act.size(), 12);
-      if (!v.uniform)
+      if (!v.uniform && smooth_use_tma() && amr_split() && !v.reg.empty()) {
+        CUP_TRY(down_tma_launch<Real>(c, view(v), v.d_pslot, v.d_oct, a.u0, a.f, (Real)v.h, v.d_rptr, v.d_reg,
+                                      (int)v.reg.size()));
+        if (!v.irr.empty()) {
+          CUP_TRY(down_amr_launch<Real>(c, view(v), v.d_pslot, v.d_oct, a.u0, a.f, (Real)v.h, v.d_irr,
+                                        (int)v.irr.size()));
+          c->launches++;
+        }
+      } else if (!v.uniform)
         CUP_TRY(down_amr_launch<Real>(c, view(v), v.d_pslot, v.d_oct, a.u0, a.f, (Real)v.h));
       else if (smooth_use_tma())
         CUP_TRY(down_tma_launch<Real>(c, view(v), v.d_pslot, v.d_oct, a.u0, a.f, (Real)v.h, v.d_rptr));
@@ -575,7 +606,16 @@ int vcycle_t(CupCtx *c, const Real *d_in, Real *d_out) {
     CUP_TRY(halo_wait(c, w));
     if (!w.par.empty()) {
       const int gridw = grid_for(c, (long long)w.par.size(), 12);
-      if (!w.uniform)
+      if (!w.uniform && smooth_use_tma() && amr_split()) {
+        if (!w.par_reg.empty())
+          CUP_TRY(apply_tma_launch<Real>(c, view(w), w.d_par_reg, (int)w.par_reg.size(), a.u0, a.f, a.us, (Real)w.h,
+                                         nullptr, (Real)0, true));
+        if (!w.par_irr.empty()) {
+          CUP_TRY(apply_amr_launch<Real>(c, view(w), w.d_par_irr, (int)w.par_irr.size(), a.u0, a.f, a.us, (Real)w.h,
+                                         nullptr, nullptr, 1));
+          c->launches++;
+        }
+      } else if (!w.uniform)
         CUP_TRY(apply_amr_launch<Real>(c, view(w), w.d_par, (int)w.par.size(), a.u0, a.f, a.us, (Real)w.h, nullptr,
                                        nullptr, 1));
       else if (smooth_use_tma())

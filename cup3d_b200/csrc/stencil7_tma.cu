@@ -17,7 +17,8 @@ namespace cup {
 // order differs from mg_sum's left-to-right sum by rounding only.
 template <typename Real>
 __global__ void __launch_bounds__(TPB, 12)
-    k_down_tma(LevelView lv, const int *__restrict__ pslot, const int *__restrict__ oct, SlotVec<Real> u,
+    k_down_tma(LevelView lv, const int *__restrict__ sub, int nsub, const int *__restrict__ pslot,
+               const int *__restrict__ oct, SlotVec<Real> u,
                SlotVec<Real> f, Real h, Real *const *__restrict__ rptr, const __grid_constant__ CUtensorMap mxl,
                const __grid_constant__ CUtensorMap myl, const __grid_constant__ CUtensorMap mxe,
                const __grid_constant__ CUtensorMap mye) {
@@ -30,24 +31,27 @@ __global__ void __launch_bounds__(TPB, 12)
   }
   __syncthreads();
   int i = blockIdx.x;
-  if (t == 0 && i < lv.nact) {
+  if (t == 0 && i < nsub) {
+    const int b0 = sub ? sub[i] : i;
     int nb[6];
 #pragma unroll
     for (int q = 0; q < 6; q++)
-      nb[q] = lv.nbr[(size_t)i * 6 + q];
-    stage_issue<Real, true>(st, u, f, lv.act[i], nb, rf, &mxl, &myl, &mxe, &mye);
+      nb[q] = lv.nbr[(size_t)b0 * 6 + q];
+    stage_issue<Real, true>(st, u, f, lv.act[b0], nb, rf, &mxl, &myl, &mxe, &mye);
   }
   uint32_t phase = 0;
-  for (; i < lv.nact; i += G) {
+  for (; i < nsub; i += G) {
+    const int b = sub ? sub[i] : i;
     int nslot = 0, nnb[6] = {0, 0, 0, 0, 0, 0};
-    const bool more = (i + G) < lv.nact;
+    const bool more = (i + G) < nsub;
     if (t == 0 && more) {
-      nslot = lv.act[i + G];
+      const int bn = sub ? sub[i + G] : i + G;
+      nslot = lv.act[bn];
 #pragma unroll
       for (int q = 0; q < 6; q++)
-        nnb[q] = lv.nbr[(size_t)(i + G) * 6 + q];
+        nnb[q] = lv.nbr[(size_t)bn * 6 + q];
     }
-    const int ps = pslot[i], o = oct[i];
+    const int ps = pslot[b], o = oct[b];
     mbar_wait(&st.mbar, phase);
     phase ^= 1;
     const XFace<Real> xf(st.flags);
@@ -172,11 +176,13 @@ static inline int pgrid(const CupCtx *c, long long n) {
 
 template <typename Real>
 int down_tma_launch(CupCtx *c, LevelView lv, const int *pslot, const int *oct, SlotVec<Real> u, SlotVec<Real> f,
-                    Real h, void *const *rptr) {
+                    Real h, void *const *rptr, const int *sub, int nsub) {
   CUtensorMap m[4];
   CUP_TRY(tma_face_maps(c, u.leaf, u.extra, m));
-  k_down_tma<Real><<<pgrid(c, lv.nact), TPB, 0, c->stream>>>(lv, pslot, oct, u, f, h, (Real *const *)rptr, m[0], m[1],
-                                                            m[2], m[3]);
+  if (nsub < 0)
+    nsub = lv.nact;
+  k_down_tma<Real><<<pgrid(c, nsub), TPB, 0, c->stream>>>(lv, sub, nsub, pslot, oct, u, f, h, (Real *const *)rptr,
+                                                         m[0], m[1], m[2], m[3]);
   return CUP_OK;
 }
 
@@ -195,9 +201,9 @@ int apply_tma_launch(CupCtx *c, LevelView lv, const int *sub, int nsub, SlotVec<
 }
 
 template int down_tma_launch<double>(CupCtx *, LevelView, const int *, const int *, SlotVec<double>, SlotVec<double>,
-                                     double, void *const *);
+                                     double, void *const *, const int *, int);
 template int down_tma_launch<float>(CupCtx *, LevelView, const int *, const int *, SlotVec<float>, SlotVec<float>,
-                                    float, void *const *);
+                                    float, void *const *, const int *, int);
 template int apply_tma_launch<double>(CupCtx *, LevelView, const int *, int, SlotVec<double>, SlotVec<double>,
                                       SlotVec<double>, double, const double *, double, bool);
 template int apply_tma_launch<float>(CupCtx *, LevelView, const int *, int, SlotVec<float>, SlotVec<float>,
