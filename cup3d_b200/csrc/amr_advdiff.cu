@@ -167,7 +167,8 @@ __device__ __forceinline__ Real fine_avg_layer(const Real *__restrict__ cp, cons
 enum { AD_ROW = 16, AD_SLAB = 14 * 16 };
 
 template <typename Real>
-__global__ void __launch_bounds__(TPB) k_advdiff_amr(LevelView lv, LeafGeom geo, const Real *__restrict__ hblk,
+__global__ void __launch_bounds__(TPB) k_advdiff_amr(LevelView lv, const int *__restrict__ sub, int nsub, LeafGeom geo,
+                                                     const Real *__restrict__ hblk,
                                                      const Real *__restrict__ v0, const Real *__restrict__ v1,
                                                      const Real *__restrict__ v2, Real *__restrict__ t0,
                                                      Real *__restrict__ t1, Real *__restrict__ t2, Real dt, Real nu,
@@ -178,7 +179,8 @@ __global__ void __launch_bounds__(TPB) k_advdiff_amr(LevelView lv, LeafGeom geo,
   const Real *vel[3] = {v0, v1, v2};
   Real *tmp[3] = {t0, t1, t2};
   const Real uinf[3] = {ux, uy, uz};
-  for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
+  for (int wi = blockIdx.x; wi < nsub; wi += gridDim.x) {
+    const int b = sub ? sub[wi] : wi;
     const int slot = lv.act[b];
     const size_t own = (size_t)slot * 512;
     const int *ext24 = lv.ext + (size_t)b * 24;
@@ -328,7 +330,7 @@ __global__ void __launch_bounds__(TPB) k_advdiff_amr(LevelView lv, LeafGeom geo,
 }
 
 template <typename Real>
-int advdiff_amr_launch(CupCtx *c, const Level &v, Real *const *S) {
+int advdiff_amr_launch(CupCtx *c, const Level &v, Real *const *S, const int *sub, int nsub) {
   LevelView lv{v.d_act, v.d_nbr, (int)v.act.size(), nullptr, nullptr, 0, v.d_ext};
   LeafGeom g;
   g.bijk = v.d_bijk;
@@ -337,10 +339,12 @@ int advdiff_amr_launch(CupCtx *c, const Level &v, Real *const *S) {
   g.hmask = (unsigned long long)v.hkeys.size() - 1;
   for (int d = 0; d < 3; d++)
     g.bpd[d] = c->bpd[d];
+  if (nsub < 0)
+    nsub = (int)v.act.size();
   long long grid = (long long)c->num_sms * 4;
-  if (grid > (long long)v.act.size())
-    grid = (long long)v.act.size();
-  k_advdiff_amr<Real><<<(int)grid, TPB, 0, c->stream>>>(lv, g, (const Real *)v.d_hblk, S[CUP_F_VEL], S[CUP_F_VEL + 1],
+  if (grid > (long long)nsub)
+    grid = nsub < 1 ? 1 : nsub;
+  k_advdiff_amr<Real><<<(int)grid, TPB, 0, c->stream>>>(lv, sub, nsub, g, (const Real *)v.d_hblk, S[CUP_F_VEL], S[CUP_F_VEL + 1],
                                                        S[CUP_F_VEL + 2], S[CUP_F_TMP], S[CUP_F_TMP + 1],
                                                        S[CUP_F_TMP + 2], (Real)c->prm.dt, (Real)c->prm.nu,
                                                        (Real)c->prm.uinf[0], (Real)c->prm.uinf[1],
@@ -348,7 +352,7 @@ int advdiff_amr_launch(CupCtx *c, const Level &v, Real *const *S) {
   return CUP_OK;
 }
 
-template int advdiff_amr_launch<double>(CupCtx *, const Level &, double *const *);
-template int advdiff_amr_launch<float>(CupCtx *, const Level &, float *const *);
+template int advdiff_amr_launch<double>(CupCtx *, const Level &, double *const *, const int *, int);
+template int advdiff_amr_launch<float>(CupCtx *, const Level &, float *const *, const int *, int);
 
 }  // namespace cup

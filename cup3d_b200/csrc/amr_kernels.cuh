@@ -25,5 +25,5 @@ template <typename Real>
 int prhs_amr_launch(CupCtx *c, LevelView lv, const void *hblk, Real *const *S, Real idt2);
 // k_advdiff on the leaves of a multi-level mesh (amr_advdiff.cu)
 template <typename Real>
-int advdiff_amr_launch(CupCtx *c, const Level &v, Real *const *S);
+int advdiff_amr_launch(CupCtx *c, const Level &v, Real *const *S, const int *sub = nullptr, int nsub = -1);
 }  // namespace cup

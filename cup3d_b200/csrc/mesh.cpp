@@ -584,6 +584,8 @@ void free_mesh(CupCtx *c) {
     cudaFree(v.d_nbr);
     cudaFree(v.d_ext);
     cudaFree(v.d_hblk);
+    cudaFree(v.d_reg);
+    cudaFree(v.d_irr);
     cudaFree(v.d_bijk);
     cudaFree(v.d_hkeys);
     cudaFree(v.d_hvals);
@@ -676,6 +678,16 @@ int build_mesh(CupCtx *c, const CupBlk *gblk, long long G, const int *owner, con
     CUP_TRY(upload(&v.d_act, v.act));
     CUP_TRY(upload(&v.d_nbr, v.nbr));
     CUP_TRY(upload(&v.d_ext, v.ext));
+    v.reg.clear();
+    v.irr.clear();
+    for (size_t k = 0; k < v.act.size(); k++) {
+      bool ir = false;
+      for (int f = 0; f < 6; f++)
+        ir |= (v.nbr[k * 6 + f] == NBR_COARSE || v.nbr[k * 6 + f] == NBR_FINE);
+      (ir ? v.irr : v.reg).push_back((int)k);
+    }
+    CUP_TRY(upload(&v.d_reg, v.reg));
+    CUP_TRY(upload(&v.d_irr, v.irr));
     CUP_TRY(upload(&v.d_bijk, v.bijk));
     CUP_TRY(upload(&v.d_hkeys, v.hkeys));
     CUP_TRY(upload(&v.d_hvals, v.hvals));

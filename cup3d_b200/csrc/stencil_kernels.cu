@@ -43,10 +43,12 @@ __device__ __forceinline__ Real upwind(Real U, Real um3, Real um2, Real um1, Rea
 enum { AD_ROW = 16, AD_SLAB = 14 * 16 };  // padded tile: [8 z][14 y][16 x], halo offset 3
 
 template <typename Real, int MINB>
-__global__ void __launch_bounds__(TPB, MINB) k_advdiff(LevelView lv, const Real *__restrict__ v0, const Real *__restrict__ v1,
-                                                 const Real *__restrict__ v2, Real *__restrict__ t0,
-                                                 Real *__restrict__ t1, Real *__restrict__ t2, Real fac_a, Real fac_d,
-                                                 Real ux, Real uy, Real uz) {
+__global__ void __launch_bounds__(TPB, MINB) k_advdiff(LevelView lv, const int *__restrict__ sub, int nsub,
+                                                       const Real *__restrict__ hblk, Real dtnu_dt, Real dtnu_nu,
+                                                       const Real *__restrict__ v0, const Real *__restrict__ v1,
+                                                       const Real *__restrict__ v2, Real *__restrict__ t0,
+                                                       Real *__restrict__ t1, Real *__restrict__ t2, Real fac_a0,
+                                                       Real fac_d0, Real ux, Real uy, Real uz) {
   __shared__ Real tile[8 * AD_SLAB];
   const int t = threadIdx.x, x = t & 7, y = t >> 3;
   const int a = t & 7, c2 = t >> 3;  // halo element coordinates
@@ -58,13 +60,21 @@ __global__ void __launch_bounds__(TPB, MINB) k_advdiff(LevelView lv, const Real 
   auto rem = [&](int nbc, int c, int l) -> Real {
     return rsl[(size_t)(kRemote0 - nbc) * (64 * kSlabPlanes) + (c * 3 + l) * 64 + t];
   };
-  for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
+  for (int wi = blockIdx.x; wi < nsub; wi += gridDim.x) {
+    const int b = sub ? sub[wi] : wi;
     const size_t own = (size_t)lv.act[b] * 512;
     const int *nbr6 = lv.nbr + (size_t)b * 6;
     int nb[6];
 #pragma unroll
     for (int f = 0; f < 6; f++)
       nb[f] = nbr6[f];
+    // per-block factors on multi-level meshes (main.c:4993-4995), else the level's
+    Real fac_a = fac_a0, fac_d = fac_d0;
+    if (hblk) {
+      const Real hb = hblk[b], h3b = hb * hb * hb;
+      fac_a = -dtnu_dt / hb * h3b;
+      fac_d = (dtnu_nu / hb) * (dtnu_dt / hb) * h3b;
+    }
     Real vv[3][8];
 #pragma unroll
     for (int c = 0; c < 3; c++)
@@ -450,7 +460,17 @@ int stencil_amr_t(CupCtx *c, CupStencilId id) {
   const double dt = c->prm.dt;
   switch (id) {
   case CUP_ST_ADVDIFF:
-    CUP_TRY(advdiff_amr_launch<Real>(c, v, S));
+    // blocks whose neighbours are all same-level / wall: the uniform kernel with per-block factors;
+    // interface blocks: the ss = 3 coarse-fine ghost fill
+    if (!v.reg.empty()) {
+      k_advdiff<Real, 8><<<bgrid(c, (long long)v.reg.size(), 8), TPB, 0, c->stream>>>(
+          lv, v.d_reg, (int)v.reg.size(), (const Real *)v.d_hblk, (Real)dt, (Real)c->prm.nu, S[CUP_F_VEL],
+          S[CUP_F_VEL + 1], S[CUP_F_VEL + 2], S[CUP_F_TMP], S[CUP_F_TMP + 1], S[CUP_F_TMP + 2], (Real)0, (Real)0,
+          (Real)c->prm.uinf[0], (Real)c->prm.uinf[1], (Real)c->prm.uinf[2]);
+      c->launches++;
+    }
+    if (!v.irr.empty())
+      CUP_TRY(advdiff_amr_launch<Real>(c, v, S, v.d_irr, (int)v.irr.size()));
     break;
   case CUP_ST_PRHS:
     CUP_TRY(prhs_amr_launch<Real>(c, lv, v.d_hblk, S, (Real)(1.0 / dt)));
@@ -511,8 +531,9 @@ int stencil_t(CupCtx *c, CupStencilId id, const int *d_sub, long long nsub) {
     static int minb = getenv("CUP_ADV_MINB") ? atoi(getenv("CUP_ADV_MINB")) : 8;
 #define ADV_LAUNCH(M)                                                                                              \
   k_advdiff<Real, M><<<bgrid(c, c->nblk, M), TPB, 0, c->stream>>>(                                                 \
-      lv, S[CUP_F_VEL], S[CUP_F_VEL + 1], S[CUP_F_VEL + 2], S[CUP_F_TMP], S[CUP_F_TMP + 1], S[CUP_F_TMP + 2],      \
-      (Real)fa, (Real)fd, (Real)c->prm.uinf[0], (Real)c->prm.uinf[1], (Real)c->prm.uinf[2])
+      lv, nullptr, lv.nact, nullptr, (Real)0, (Real)0, S[CUP_F_VEL], S[CUP_F_VEL + 1], S[CUP_F_VEL + 2],          \
+      S[CUP_F_TMP], S[CUP_F_TMP + 1], S[CUP_F_TMP + 2], (Real)fa, (Real)fd, (Real)c->prm.uinf[0],                 \
+      (Real)c->prm.uinf[1], (Real)c->prm.uinf[2])
     if (minb == 5)
       ADV_LAUNCH(5);
     else if (minb == 10)
