@@ -1,6 +1,4 @@
 // capi.cu -- the extern "C" boundary declared in include/cup3d_b200.h.
-#include <mutex>
-
 #include "blas_kernels.cuh"
 #include "cup_internal.h"
 #include "smooth_tma.cuh"
@@ -112,9 +110,6 @@ int cup_create(CupCtx **out, int device, int real_bytes) {
   // (implicitly ordered against legacy-default-stream work of the caller) unless one is set
   CUP_CUDA(cudaStreamCreate(&c->own_stream));
   c->stream = c->own_stream;
-  CUP_CUDA(cudaStreamCreateWithFlags(&c->cstream, cudaStreamNonBlocking));
-  CUP_CUDA(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
-  CUP_CUDA(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
   *out = c;
   return CUP_OK;
 }
@@ -145,10 +140,7 @@ int cup_destroy(CupCtx *c) {
   cudaFree(c->d_hw);
   cudaFree(c->d_scal);
   cudaFreeHost(c->h_scal);
-  cudaStreamDestroy(c->cstream);
   cudaStreamDestroy(c->own_stream);
-  cudaEventDestroy(c->ev_ready);
-  cudaEventDestroy(c->ev_halo);
   delete c;
   return CUP_OK;
 }

@@ -72,8 +72,6 @@ static int load_nccl() {
 
 struct Comm {
   ncclComm_t nccl = nullptr;
-  void *gather_dev = nullptr;
-  size_t gather_bytes = 0;
   // ---- one-sided mode: every rank exposes one receive window through CUDA IPC ----
   bool p2p = false;
   char *win = nullptr;                 // [flags | per-level receive areas]
@@ -140,7 +138,6 @@ void comm_free(CupCtx *c) {
   Comm *cm = (Comm *)c->comm;
   if (!cm)
     return;
-  cudaFree(cm->gather_dev);
   if (cm->nccl)
     g_nccl.CommDestroy(cm->nccl);
   delete cm;

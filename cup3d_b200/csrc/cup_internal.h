@@ -131,8 +131,6 @@ struct CupCtx {
   int num_sms = 148;
   cudaStream_t stream = nullptr;    // where all work is enqueued (own_stream unless the caller set one)
   cudaStream_t own_stream = nullptr;  // blocking stream: ordered against the legacy default stream
-  cudaStream_t cstream = nullptr;   // halo exchanges overlapped with interior sweeps
-  cudaEvent_t ev_ready = nullptr, ev_halo = nullptr;
   CupParams prm{};
   long long nblk = 0, nslot = 0;   // LOCAL leaves / local slots
   long long gblocks = 0;           // leaves over all ranks
@@ -158,8 +156,6 @@ struct CupCtx {
   void *d_hw = nullptr;         // per-leaf 1/h^3 (pois.hw, main.c:4886)
   double *d_scal = nullptr;     // device scalars (reductions); always double
   double *h_scal = nullptr;     // pinned mirror
-  void *pinned = nullptr;       // pinned staging for h2d/d2h
-  size_t pinned_bytes = 0;
   cup::Krylov *kr = nullptr;
   long long launches = 0;
   void *p_old = nullptr;        // projection(): previous pressure

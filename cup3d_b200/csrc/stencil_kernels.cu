@@ -20,13 +20,6 @@
 
 namespace cup {
 
-struct Vec3P {
-  const void *c[3];
-};
-struct Vec3W {
-  void *c[3];
-};
-
 // ---------------------------------------------------------------------------
 // k_advdiff: TMP_c += fac_a * (u . grad) u_c + fac_d * lap u_c
 // ---------------------------------------------------------------------------
