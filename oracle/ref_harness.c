@@ -165,3 +165,88 @@ API void ref_mesh_adapt(double rtol, double ctol) {
   sim.ctol = ctol;
   mesh_adapt();
 }
+
+/* ---- obstacle (fish) path: SURVEY 8(f) row 1 ------------------------------------------
+ * Drives the reference's own per-step phases one at a time so that goldens can be
+ * captured between them (advance(), main.c:5984-6003). */
+API void ref_sta_fields(void) { sta_fields(); }
+API int ref_nfish(void) { return sim.nfish; }
+API double ref_sta_dt(void) { return sta_dt(); }
+API void ref_step_end(void) {
+  sta.step++;
+  sta.time += sta.dt;
+}
+/* 0 fish_build  1 advdiff  2 fish_vel  3 fish_pen  4 projection  5 fish_tmpv  6 mesh_adapt */
+API int ref_phase(int p) {
+  switch (p) {
+  case 0: fish_build(); break;
+  case 1: advdiff(); break;
+  case 2: fish_vel(); break;
+  case 3: fish_pen(); break;
+  case 4: projection(); break;
+  case 5: fish_tmpv(); break;
+  case 6: mesh_adapt(); break;
+  default: return 1;
+  }
+  return 0;
+}
+/* dt lambda uinf[3] step time */
+API void ref_get_scalars(double *o) {
+  o[0] = sta.dt;
+  o[1] = sta.lambda;
+  o[2] = sta.uinf[0];
+  o[3] = sta.uinf[1];
+  o[4] = sta.uinf[2];
+  o[5] = sta.step;
+  o[6] = sta.time;
+}
+API void ref_set_lambda(double l) { sta.lambda = l; }
+API int ref_fish_nob(int k) {
+  long long i;
+  int n = 0;
+  for (i = 0; i < sta.nblk; i++)
+    n += oblock(&sta.fish[k], i) != NULL;
+  return n;
+}
+/* obstacle blocks of fish k in block order: index, chi[512], udef[512][3] (struct layout) */
+API void ref_fish_ob(int k, int *blk, double *chi, double *udef) {
+  long long i;
+  int n = 0;
+  for (i = 0; i < sta.nblk; i++) {
+    struct ObstacleBlock *o = oblock(&sta.fish[k], i);
+    if (o == NULL)
+      continue;
+    blk[n] = (int)i;
+    memcpy(chi + (size_t)n * BS3, o->chi, BS3 * sizeof(Real));
+    memcpy(udef + (size_t)n * 3 * BS3, o->udef, 3 * BS3 * sizeof(Real));
+    n++;
+  }
+}
+/* com[3] vel[3] omega[3] */
+API void ref_fish_motion(int k, double *o) {
+  struct Fish *f = &sta.fish[k];
+  int d;
+  for (d = 0; d < 3; d++) {
+    o[d] = f->com[d];
+    o[3 + d] = f->vel[d];
+    o[6 + d] = f->omega[d];
+  }
+}
+API int ref_m_n(void) { return M_N; }
+/* per-block moments (fish_mom_blk, main.c:5057) summed over blocks in block order, as the
+ * first loop of fish_vel does (main.c:5315-5325); fish_solve is NOT called */
+API void ref_fish_mom(int k, double *M) {
+  struct Fish *f = &sta.fish[k];
+  long long i;
+  int q;
+  for (q = 0; q < M_N; q++)
+    M[q] = 0;
+  for (i = 0; i < sta.nblk; i++) {
+    struct ObstacleBlock *o = oblock(f, i);
+    if (o == NULL)
+      continue;
+    fish_mom_blk(i, f);
+    for (q = 0; q < M_N; q++)
+      M[q] += o->mom[q];
+  }
+}

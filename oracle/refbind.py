@@ -160,3 +160,62 @@ def time_vcycle(x, warmup, n):
 
 def time_stencil(name, warmup, n):
     return float(_lib.ref_time_stencil(STENCILS[name], warmup, n))
+
+
+# ---- obstacle (fish) phases, SURVEY 8(f) row 1 ---------------------------------------
+PHASES = {"fish_build": 0, "advdiff": 1, "fish_vel": 2, "fish_pen": 3, "projection": 4, "fish_tmpv": 5,
+          "mesh_adapt": 6}
+
+
+def sta_fields():
+    _lib.ref_sta_fields()
+
+
+def sta_dt():
+    _lib.ref_sta_dt.restype = C.c_double
+    return float(_lib.ref_sta_dt())
+
+
+def phase(name):
+    assert _lib.ref_phase(PHASES[name]) == 0
+
+
+def step_end():
+    _lib.ref_step_end()
+
+
+def get_scalars():
+    o = np.zeros(7)
+    _lib.ref_get_scalars(_p(o))
+    return dict(dt=o[0], lam=o[1], uinf=tuple(o[2:5]), step=int(o[5]), time=o[6])
+
+
+def set_lambda(lam):
+    _lib.ref_set_lambda.argtypes = [C.c_double]
+    _lib.ref_set_lambda(lam)
+
+
+def nfish():
+    return int(_lib.ref_nfish())
+
+
+def fish_obstacle(k):
+    """-> (blk int32 [nob], chi [nob,512], udef [nob,512,3]) of fish k (struct ObstacleBlock, main.c:96)"""
+    n = int(_lib.ref_fish_nob(k))
+    blk = np.zeros(n, np.int32)
+    chi = np.zeros((n, BS3))
+    udef = np.zeros((n, BS3, 3))
+    _lib.ref_fish_ob(k, blk.ctypes.data_as(C.POINTER(C.c_int)), _p(chi), _p(udef))
+    return blk, chi, udef
+
+
+def fish_motion(k):
+    o = np.zeros(9)
+    _lib.ref_fish_motion(k, _p(o))
+    return o[0:3].copy(), o[3:6].copy(), o[6:9].copy()
+
+
+def fish_mom(k):
+    M = np.zeros(int(_lib.ref_m_n()))
+    _lib.ref_fish_mom(k, _p(M))
+    return M
