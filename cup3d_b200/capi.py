@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libcup3d_b200.so")
 BS3 = 512
 F_CHI, F_PRES, F_VEL, F_TMP, F_LHS, F_N = 0, 1, 2, 5, 8, 9
 ST_LHS, ST_MG, ST_ADVDIFF, ST_PRHS, ST_DIVP, ST_GRADP, ST_VORT, ST_Q = range(8)
+M_N = 29  # CUP_M_N: entries of ObstacleBlock.mom (enum M_*, main.c:64-95)
 
 
 class CupBlk(C.Structure):  # struct Blk, reference main.c:59-63
@@ -24,7 +25,7 @@ class CupBlk(C.Structure):  # struct Blk, reference main.c:59-63
 
 class CupParams(C.Structure):
     _fields_ = [("dt", C.c_double), ("nu", C.c_double), ("uinf", C.c_double * 3), ("step", C.c_int),
-                ("mean_constraint", C.c_int), ("ptol", C.c_double), ("ptol_rel", C.c_double)]
+                ("mean_constraint", C.c_int), ("ptol", C.c_double), ("ptol_rel", C.c_double), ("lam", C.c_double)]
 
 
 class CupSolveInfo(C.Structure):
@@ -42,6 +43,7 @@ class CupPlan(C.Structure):
 
 # every symbol include/cup3d_b200.h declares: name -> (restype, argtypes)
 _vp, _i, _ll, _dp = C.c_void_p, C.c_int, C.c_longlong, C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
 SYMBOLS = {
     "cup_last_error": (C.c_char_p, []),
     "cup_version": (_i, []),
@@ -69,6 +71,12 @@ SYMBOLS = {
     "cup_advdiff": (_i, [_vp]),
     "cup_projection": (_i, [_vp, C.POINTER(CupSolveInfo)]),
     "cup_projection_udef_ready": (_i, [_vp, _i]),
+    "cup_obstacle_upload": (_i, [_vp, _i, _i, _ip, _dp, _dp]),
+    "cup_obstacle_motion": (_i, [_vp, _i, _dp, _dp, _dp]),
+    "cup_obstacle_clear": (_i, [_vp]),
+    "cup_obstacle_moments": (_i, [_vp, _i, _dp]),
+    "cup_obstacle_penalize": (_i, [_vp]),
+    "cup_obstacle_tmpv": (_i, [_vp]),
     "cup_umax": (_i, [_vp, _dp]),
     "cup_comm_init": (_i, [_vp, _i, _i, _vp, C.c_size_t]),
     "cup_nccl_unique_id": (_i, [_vp, C.c_size_t]),
@@ -177,7 +185,7 @@ class Context:
         self.h = h
         self.real_bytes = real_bytes
         self.params = CupParams(dt=0.0, nu=1e-3, uinf=(C.c_double * 3)(0, 0, 0), step=0, mean_constraint=2,
-                                ptol=1e-6, ptol_rel=1e-4)
+                                ptol=1e-6, ptol_rel=1e-4, lam=1e6)
 
     def close(self):
         if self.h:
@@ -272,6 +280,36 @@ class Context:
         info = CupSolveInfo()
         check(self.L.cup_projection(self.h, C.byref(info)))
         return info
+
+    # ---- obstacle (fish) phases: fish_mom_blk / fish_pen_blk / fish_tmpv on the device
+    def obstacle_upload(self, body, blk, chi, udef):
+        """blk int32 [nob], chi [nob,512], udef [nob,512,3] (struct ObstacleBlock layout, main.c:96)"""
+        blk = np.ascontiguousarray(blk, np.int32)
+        chi = np.ascontiguousarray(chi, np.float64)
+        udef = np.ascontiguousarray(udef, np.float64)
+        n = len(blk)
+        assert chi.shape == (n, BS3) and udef.shape == (n, BS3, 3)
+        check(self.L.cup_obstacle_upload(self.h, body, n, blk.ctypes.data_as(_ip), chi.ctypes.data_as(_dp),
+                                         udef.ctypes.data_as(_dp)))
+
+    def obstacle_motion(self, body, com=None, vel=None, omega=None):
+        def p(v):
+            return None if v is None else (C.c_double * 3)(*[float(x) for x in v])
+        check(self.L.cup_obstacle_motion(self.h, body, p(com), p(vel), p(omega)))
+
+    def obstacle_clear(self):
+        check(self.L.cup_obstacle_clear(self.h))
+
+    def obstacle_moments(self, body):
+        M = np.zeros(M_N)
+        check(self.L.cup_obstacle_moments(self.h, body, M.ctypes.data_as(_dp)))
+        return M
+
+    def obstacle_penalize(self):
+        check(self.L.cup_obstacle_penalize(self.h))
+
+    def obstacle_tmpv(self):
+        check(self.L.cup_obstacle_tmpv(self.h))
 
     def umax(self):
         r = C.c_double()

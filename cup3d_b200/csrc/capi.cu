@@ -120,6 +120,7 @@ int cup_destroy(CupCtx *c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   free_krylov(c);
+  free_obstacles(c);
   free_graph_cache(c);
   comm_free_level_buffers(c);
   free_mesh(c);
@@ -168,6 +169,7 @@ int cup_mesh_upload(CupCtx *c, const CupBlk *blk, long long n, const int bpd[3],
   CUP_CUDA(cudaSetDevice(c->device));
   CUP_CUDA(cudaStreamSynchronize(c->stream));
   free_krylov(c);
+  free_obstacles(c);
   free_graph_cache(c);
   comm_free_level_buffers(c);
   // tree_sync (main.c:2928): all ranks learn all blocks; owner = contributing rank
@@ -273,6 +275,22 @@ int cup_projection_udef_ready(CupCtx *c, int flag) {
   c->keep_tmp_udef = flag != 0;
   return CUP_OK;
 }
+int cup_obstacle_upload(CupCtx *c, int body, int nob, const int *blk, const double *chi, const double *udef) {
+  return obstacle_upload(c, body, nob, blk, chi, udef);
+}
+int cup_obstacle_motion(CupCtx *c, int body, const double com[3], const double vel[3], const double omega[3]) {
+  return obstacle_motion(c, body, com, vel, omega);
+}
+int cup_obstacle_clear(CupCtx *c) { return obstacle_clear(c); }
+int cup_obstacle_moments(CupCtx *c, int body, double *M) {
+  if (!M) {
+    set_error("cup_obstacle_moments: M is NULL");
+    return CUP_ERR_ARG;
+  }
+  return obstacle_moments(c, body, M);
+}
+int cup_obstacle_penalize(CupCtx *c) { return obstacle_penalize(c); }
+int cup_obstacle_tmpv(CupCtx *c) { return obstacle_tmpv(c); }
 int cup_stencil_apply(CupCtx *c, CupStencilId id) { return stencil_run(c, id, nullptr, c->nblk); }
 int cup_stencil_run(CupCtx *c, CupStencilId id, const long long *list, long long n) {
   return stencil_run(c, id, list, n);

@@ -162,6 +162,7 @@ struct CupCtx {
   void *graph_cache = nullptr;  // captured V-cycles keyed by (in, out) (mg_kernels.cu)
   void *tma_cache = nullptr;    // tensor-map cache (smooth_tma.cu)
   bool no_flux_correction = false;  // st_mg on the leaves (stencil_apply(CUP_ST_MG)): k_mg has no flux faces
+  void *obst = nullptr;         // cup::Obstacles (obstacle.cu)
   bool keep_tmp_udef = false;   // projection(): F_TMP already holds fish_tmpv()'s udef
 };
 
@@ -192,6 +193,16 @@ int advdiff(CupCtx *c);
 int projection(CupCtx *c, CupSolveInfo *info);
 int stencil_run(CupCtx *c, CupStencilId id, const long long *list, long long n);
 void free_krylov(CupCtx *c);
+
+// obstacle.cu
+int obstacle_upload(CupCtx *c, int body, int nob, const int *blk, const double *chi, const double *udef);
+int obstacle_motion(CupCtx *c, int body, const double com[3], const double vel[3], const double omega[3]);
+int obstacle_clear(CupCtx *c);
+int obstacle_moments(CupCtx *c, int body, double *M);
+int obstacle_penalize(CupCtx *c);
+int obstacle_tmpv(CupCtx *c);
+int obstacle_count(const CupCtx *c);
+void free_obstacles(CupCtx *c);
 
 // comm.cu
 int comm_init(CupCtx *c, int rank, int nranks, const void *id, size_t id_bytes);

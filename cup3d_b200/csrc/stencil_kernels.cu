@@ -629,12 +629,15 @@ int projection_t(CupCtx *c, CupSolveInfo *info) {
   const size_t rb = sizeof(Real);
   Real **S = (Real **)c->state;
   enum { STEP_2ND = 2 };  // main.c:130
-  // p_old = p ; TMP = 0   (fish_tmpv would add udef into TMP here: the caller uploads F_TMP
-  // already containing it when fish are present -- see INTEGRATION.md)
+  // p_old = p ; TMP = 0 ; fish_tmpv adds udef into TMP (main.c:5842-5847).  keep_tmp_udef: the
+  // caller uploaded F_TMP already containing it.
   CUP_CUDA(cudaMemcpyAsync(c->p_old, S[CUP_F_PRES], N * rb, cudaMemcpyDeviceToDevice, c->stream));
-  if (!c->keep_tmp_udef)
+  if (!c->keep_tmp_udef) {
     for (int q = 0; q < 3; q++)
       CUP_CUDA(cudaMemsetAsync(S[CUP_F_TMP + q], 0, N * rb, c->stream));
+    if (obstacle_count(c) > 0)
+      CUP_TRY(obstacle_tmpv(c));
+  }
   CUP_TRY(stencil_t<Real>(c, CUP_ST_PRHS, nullptr, 0));
   if (c->prm.step > STEP_2ND) {
     CUP_TRY(stencil_t<Real>(c, CUP_ST_DIVP, nullptr, 0));

@@ -76,6 +76,7 @@ typedef struct CupParams {
   int step;              /* sta.step (incremental pressure after STEP_2ND) */
   int mean_constraint;   /* sim.mean_constraint (bMeanConstraint) */
   double ptol, ptol_rel; /* sim.ptol, sim.ptol_rel */
+  double lambda;         /* sta.lambda (penalisation coefficient, main.c:5969) */
 } CupParams;
 
 typedef struct CupSolveInfo {
@@ -132,10 +133,39 @@ int cup_pois_dot_dev(CupCtx *ctx, const void *d_a, const void *d_b, double *resu
 int cup_pois_solve(CupCtx *ctx, CupSolveInfo *info);
 int cup_advdiff(CupCtx *ctx);
 int cup_projection(CupCtx *ctx, CupSolveInfo *info);
-/* projection() zeroes F_TMP and lets fish_tmpv() (host, main.c:5799) add the
- * deformation velocity before the divergence sweep.  With flag != 0 the caller
- * has uploaded F_TMP = fish_tmpv() result already and the zeroing is skipped. */
+/* projection() zeroes F_TMP and lets fish_tmpv() (main.c:5799) add the deformation velocity
+ * before the divergence sweep: done on the device for bodies given by cup_obstacle_upload.
+ * Alternatively, with flag != 0 the caller has uploaded F_TMP = fish_tmpv() result already
+ * and both the zeroing and the device fish_tmpv are skipped. */
 int cup_projection_udef_ready(CupCtx *ctx, int flag);
+
+/* ---- obstacle (fish) phases of advance() between advdiff and projection (main.c:5993-5997) ----
+ * The host keeps producing the obstacle blocks (fish_build) and solving the 6x6 rigid-body
+ * system (fish_solve); the per-cell work runs on the device so F_VEL / F_TMP never leave HBM.
+ * A "body" is one struct Fish (main.c:37); its blocks are struct ObstacleBlock (main.c:96-102). */
+enum { CUP_MAX_BODIES = 64 };
+/* index of each entry of ObstacleBlock.mom / the M[] of fish_vel (enum M_*, main.c:64-95) */
+enum {
+  CUP_M_V = 0, CUP_M_FX = 1, CUP_M_TX = 4, CUP_M_J0 = 7, CUP_M_GFX = 13, CUP_M_GPX = 14, CUP_M_GJ0 = 17,
+  CUP_M_GUX = 23, CUP_M_GAX = 26, CUP_M_N = 29
+};
+/* after fish_build: blk[nob] = local block index of every block with oblock(f,i) != NULL,
+ * chi [nob][512] = ObstacleBlock.chi, udef [nob][512][3] = ObstacleBlock.udef (reference layout).
+ * nob = 0 removes the body.  Synchronous (the host arrays may be reused on return). */
+int cup_obstacle_upload(CupCtx *ctx, int body, int nob, const int *blk, const double *chi, const double *udef);
+/* f->com, f->vel, f->omega (NULL = keep) */
+int cup_obstacle_motion(CupCtx *ctx, int body, const double com[3], const double vel[3], const double omega[3]);
+int cup_obstacle_clear(CupCtx *ctx);
+/* fish_mom_blk over the body's blocks + the block sum and MPI_Allreduce of fish_vel
+ * (main.c:5057-5118, :5315-5326) -> M[CUP_M_N]; uses params dt, lambda and the body's com.
+ * Synchronous.  The caller feeds M into fish_solve and returns vel/omega with cup_obstacle_motion. */
+int cup_obstacle_moments(CupCtx *ctx, int body, double *M);
+/* the loop of fish_pen (main.c:5656-5661) over all bodies: F_VEL is penalised towards the body
+ * velocity; fish_hit (collisions, host) is NOT part of it */
+int cup_obstacle_penalize(CupCtx *ctx);
+/* fish_tmpv (main.c:5799): F_TMP += udef inside the bodies.  cup_projection calls it itself
+ * when bodies are uploaded; exposed for tests and for callers that drive the sweeps one by one */
+int cup_obstacle_tmpv(CupCtx *ctx);
 
 /* sta_umax (main.c:5918): max over all cells (all ranks) of max_a |u_a + uinf_a|; the time-step
  * control (sta_dt) needs only this scalar, so F_VEL can stay on the device. */

@@ -96,3 +96,26 @@ def test_port_fdm_block_inverse_is_exact_inverse(P):
     back = o.pre_blk((h * lap).reshape(-1), 1 / h)
     assert relerr(back, u.reshape(-1)) < 1e-13
     o.close()
+
+
+# ---- the numpy restatement of the pointwise obstacle phases (oracle/fish_port.py) ----------
+from fishutil import FISH_CASES, fish_case  # noqa: E402
+
+
+@pytest.mark.parametrize("name", FISH_CASES)
+def test_fish_port(name):
+    from oracle import fish_port as FP
+    c = fish_case(name)
+    vel = np.zeros((c.n, 3, 512))
+    vel[c.obu] = c.g["adv_vel"]          # velocity after advdiff (obstacle blocks are all that matter)
+    for k in range(c.nfish):
+        M = FP.moments(c.ib, c.rb, vel, *c.obs[k], c.com[k], c.dt, c.lam)
+        assert np.max(np.abs(M - c.mom[k])) < 1e-12 * np.max(np.abs(c.mom[k]))
+    for k in range(c.nfish):
+        FP.penalize(c.ib, c.rb, vel, c.chi_field, *c.obs[k], c.com[k], c.vel[k], c.omega[k], c.dt, c.lam)
+    assert relerr(vel[c.obu], c.g["pen_vel"]) < 1e-14
+    tmp = np.zeros((c.n, 3, 512))
+    for k in range(c.nfish):
+        FP.tmpv(tmp, c.chi_field, *c.obs[k])
+    assert np.array_equal(tmp[c.obu], c.g["tmpv"])
+    assert not np.any(np.delete(tmp, c.obu, axis=0))
