@@ -398,6 +398,10 @@ int get_map(CupCtx *c, const void *base, long long nblocks, int kind, CUtensorMa
   if (kind == 3) { box[0] = (cuuint32_t)(16 / rb); box[1] = 4; box[2] = 4; }
   if (kind == 4) { box[0] = 4; box[1] = 1; box[2] = 4; }
   if (kind == 5) { box[0] = 4; box[1] = 4; box[2] = 1; }
+  // kinds 6, 7: three ghost layers of the 5th-order upwind stencil (k_advdiff_tma): x slab {4,8,8}
+  // (the layers are columns 1..3 or 0..2 of it), y slab {8,3,8}
+  if (kind == 6) { box[0] = 4; box[1] = 8; box[2] = 8; }
+  if (kind == 7) { box[0] = 8; box[1] = 3; box[2] = 8; }
   cuuint32_t es[3] = {1, 1, 1};
   CUtensorMap m;
   CUresult r = enc(&m, c->real_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
@@ -415,6 +419,12 @@ int get_map(CupCtx *c, const void *base, long long nblocks, int kind, CUtensorMa
 }
 
 }  // namespace
+
+int tma_slab_maps(CupCtx *c, const void *leaf, CUtensorMap out[2]) {
+  CUP_TRY(get_map(c, leaf, c->nblk, 6, &out[0]));
+  CUP_TRY(get_map(c, leaf, c->nblk, 7, &out[1]));
+  return CUP_OK;
+}
 
 int tma_face_maps(CupCtx *c, const void *leaf, const void *extra, CUtensorMap out[4]) {
   const long long nleaf = c->nblk, nx = c->nslot - c->nblk + 1;

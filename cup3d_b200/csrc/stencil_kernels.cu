@@ -15,6 +15,7 @@
 #include "blas_kernels.cuh"
 #include "cup_internal.h"
 #include "comm.cuh"
+#include "advdiff_tma.cuh"
 #include "amr_kernels.cuh"
 #include "mg_device.cuh"
 
@@ -23,17 +24,33 @@ namespace cup {
 // ---------------------------------------------------------------------------
 // k_advdiff: TMP_c += fac_a * (u . grad) u_c + fac_d * lap u_c
 // ---------------------------------------------------------------------------
+// x / 60 correctly rounded without the division sequence: q0 = x*c, one FMA residual, one FMA
+// correction (Markstein; c = RN(1/60) and 60's significand is not all ones, so the result equals
+// IEEE x/60 -- checked exhaustively-at-random on 2e9 doubles against the division).
 template <typename Real>
-__device__ __forceinline__ Real upwind(Real U, Real um3, Real um2, Real um1, Real u, Real up1, Real up2, Real up3) {
-  // derivative(), main.c:4980-4985: 5th-order upwind-biased, /60
-  if (U > 0)
-    return (((((Real)-2 * um3 + (Real)15 * um2) - (Real)60 * um1) + (Real)20 * u) + (Real)30 * up1 - (Real)3 * up2) /
-           (Real)60.;
-  return ((((((Real)2 * up3 - (Real)15 * up2) + (Real)60 * up1) - (Real)20 * u) - (Real)30 * um1) + (Real)3 * um2) /
-         (Real)60.;
+__device__ __forceinline__ Real div60(Real x) {
+  const Real c = (Real)1 / (Real)60;
+  const Real q0 = x * c;
+  const Real r = fma(-q0, (Real)60, x);
+  return fma(r, c, q0);
 }
 
-enum { AD_ROW = 16, AD_SLAB = 14 * 16 };  // padded tile: [8 z][14 y][16 x], halo offset 3
+template <typename Real>
+__device__ __forceinline__ Real upwind(Real U, Real um3, Real um2, Real um1, Real u, Real up1, Real up2, Real up3) {
+  // derivative(), main.c:4980-4985: 5th-order upwind-biased, /60.  The U <= 0 branch is the exact
+  // negation of the U > 0 expression on the mirrored operands (same operation order), so one
+  // polynomial on selected operands gives both, bit for bit.
+  const bool pos = U > 0;
+  const Real a3 = pos ? um3 : up3, a2 = pos ? um2 : up2, a1 = pos ? um1 : up1;
+  const Real b1 = pos ? up1 : um1, b2 = pos ? up2 : um2;
+  const Real r = (((((Real)-2 * a3 + (Real)15 * a2) - (Real)60 * a1) + (Real)20 * u) + (Real)30 * b1 - (Real)3 * b2);
+  const Real q = div60<Real>(r);
+  return pos ? q : -q;
+}
+
+// padded tile [8 z][14 y][14 x], halo offset 3.  Row stride 24 and slab stride = 8 (mod 16) Reals keep
+// the per-half-warp accesses (two y rows, or two z planes of a y halo) on disjoint banks.
+enum { AD_ROW = 24, AD_SLAB = 14 * 24 + 8 };
 
 template <typename Real, int MINB>
 __global__ void __launch_bounds__(TPB, MINB) k_advdiff(LevelView lv, const int *__restrict__ sub, int nsub,
@@ -50,8 +67,9 @@ __global__ void __launch_bounds__(TPB, MINB) k_advdiff(LevelView lv, const int *
   const Real uinf[3] = {ux, uy, uz};
   const Real *rsl = lv.rslab ? rslab_of<Real>(lv) : nullptr;
   // ghost value of component c, layer l (counted from the face) of the slab received for code nbc
-  auto rem = [&](int nbc, int c, int l) -> Real {
-    return rsl[(size_t)(kRemote0 - nbc) * (64 * kSlabPlanes) + (c * 3 + l) * 64 + t];
+  // (element e of the 8x8 face: the thread's own for z and y faces, any for x faces)
+  auto rem = [&](int nbc, int c, int l, int e) -> Real {
+    return rsl[(size_t)(kRemote0 - nbc) * (64 * kSlabPlanes) + (c * 3 + l) * 64 + e];
   };
   for (int wi = blockIdx.x; wi < nsub; wi += gridDim.x) {
     const int b = sub ? sub[wi] : wi;
@@ -87,9 +105,9 @@ __global__ void __launch_bounds__(TPB, MINB) k_advdiff(LevelView lv, const int *
 #pragma unroll
         for (int i = 0; i < 3; i++) {
           line[i] = nb[4] >= 0 ? vc[(size_t)nb[4] * 512 + (5 + i) * 64 + t]
-                               : (nb[4] == kWall ? sg * vv[c][0] : rem(nb[4], c, 2 - i));
+                               : (nb[4] == kWall ? sg * vv[c][0] : rem(nb[4], c, 2 - i, t));
           line[11 + i] = nb[5] >= 0 ? vc[(size_t)nb[5] * 512 + i * 64 + t]
-                                    : (nb[5] == kWall ? sg * vv[c][7] : rem(nb[5], c, i));
+                                    : (nb[5] == kWall ? sg * vv[c][7] : rem(nb[5], c, i, t));
         }
       }
       __syncthreads();  // previous component's tile fully consumed
@@ -98,20 +116,27 @@ __global__ void __launch_bounds__(TPB, MINB) k_advdiff(LevelView lv, const int *
         tile[k * AD_SLAB + (y + 3) * AD_ROW + (x + 3)] = vv[c][k];
       {
         const Real sx = (c == 0) ? (Real)-1 : (Real)1, sy = (c == 1) ? (Real)-1 : (Real)1;
+        // -x / +x: 2 sides x 3 layers x 64 (y,z) = 6 elements per thread, layer fastest so that three
+        // lanes share a sector and neighbouring lanes spread over the banks
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+          const int r = (j % 3) * 64 + t, p = r % 3, yz = r / 3, yo = (yz & 7) * 8 + (yz >> 3) * 64;
+          Real g;
+          if (j < 3)
+            g = nb[0] >= 0 ? vc[(size_t)nb[0] * 512 + yo + (5 + p)]
+                           : (nb[0] == kWall ? sx * vc[own + yo] : rem(nb[0], c, 2 - p, yz));
+          else
+            g = nb[1] >= 0 ? vc[(size_t)nb[1] * 512 + yo + p]
+                           : (nb[1] == kWall ? sx * vc[own + yo + 7] : rem(nb[1], c, p, yz));
+          tile[(yz >> 3) * AD_SLAB + ((yz & 7) + 3) * AD_ROW + (j < 3 ? 0 : 11) + p] = g;
+        }
 #pragma unroll
         for (int p = 0; p < 3; p++) {
-          // -x / +x: element (y = a, z = c2)
-          const Real xm = nb[0] >= 0 ? vc[(size_t)nb[0] * 512 + c2 * 64 + a * 8 + (5 + p)]
-                                     : (nb[0] == kWall ? sx * vc[own + c2 * 64 + a * 8] : rem(nb[0], c, 2 - p));
-          const Real xp = nb[1] >= 0 ? vc[(size_t)nb[1] * 512 + c2 * 64 + a * 8 + p]
-                                     : (nb[1] == kWall ? sx * vc[own + c2 * 64 + a * 8 + 7] : rem(nb[1], c, p));
-          tile[c2 * AD_SLAB + (a + 3) * AD_ROW + p] = xm;
-          tile[c2 * AD_SLAB + (a + 3) * AD_ROW + 11 + p] = xp;
           // -y / +y: element (x = a, z = c2)
           const Real ym = nb[2] >= 0 ? vc[(size_t)nb[2] * 512 + c2 * 64 + (5 + p) * 8 + a]
-                                     : (nb[2] == kWall ? sy * vc[own + c2 * 64 + a] : rem(nb[2], c, 2 - p));
+                                     : (nb[2] == kWall ? sy * vc[own + c2 * 64 + a] : rem(nb[2], c, 2 - p, t));
           const Real yp = nb[3] >= 0 ? vc[(size_t)nb[3] * 512 + c2 * 64 + p * 8 + a]
-                                     : (nb[3] == kWall ? sy * vc[own + c2 * 64 + 56 + a] : rem(nb[3], c, p));
+                                     : (nb[3] == kWall ? sy * vc[own + c2 * 64 + 56 + a] : rem(nb[3], c, p, t));
           tile[c2 * AD_SLAB + p * AD_ROW + (a + 3)] = ym;
           tile[c2 * AD_SLAB + (11 + p) * AD_ROW + (a + 3)] = yp;
         }
@@ -411,6 +436,16 @@ inline int bgrid(const CupCtx *c, long long nb, int per_sm) {
   return (int)(g < nb ? g : (nb < 1 ? 1 : nb));
 }
 
+// CUP_ADV_IMPL=ldg selects the plain-load k_advdiff (diagnostics); default: TMA-staged ghosts
+bool adv_tma() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("CUP_ADV_IMPL");
+    v = !(e && !strcmp(e, "ldg"));
+  }
+  return v != 0;
+}
+
 const Level *leaf_level(CupCtx *c) {
   int top = c->top;
   while (top > 0 && c->lv[top].gnact == 0)
@@ -455,7 +490,9 @@ int stencil_amr_t(CupCtx *c, CupStencilId id) {
   case CUP_ST_ADVDIFF:
     // blocks whose neighbours are all same-level / wall: the uniform kernel with per-block factors;
     // interface blocks: the ss = 3 coarse-fine ghost fill
-    if (!v.reg.empty()) {
+    if (!v.reg.empty() && adv_tma()) {
+      CUP_TRY(advdiff_tma_launch<Real>(c, lv, v.d_reg, (int)v.reg.size(), v.d_hblk, dt, c->prm.nu, 0.0, 0.0));
+    } else if (!v.reg.empty()) {
       k_advdiff<Real, 8><<<bgrid(c, (long long)v.reg.size(), 8), TPB, 0, c->stream>>>(
           lv, v.d_reg, (int)v.reg.size(), (const Real *)v.d_hblk, (Real)dt, (Real)c->prm.nu, S[CUP_F_VEL],
           S[CUP_F_VEL + 1], S[CUP_F_VEL + 2], S[CUP_F_TMP], S[CUP_F_TMP + 1], S[CUP_F_TMP + 2], (Real)0, (Real)0,
@@ -521,6 +558,8 @@ int stencil_t(CupCtx *c, CupStencilId id, const int *d_sub, long long nsub) {
     // fac_a = -dt/h*h^3 ; fac_d = (nu/h)*(dt/h)*h^3   (main.c:4993-4995, coef = 1)
     const double h3 = hd * hd * hd;
     const double fa = -dt / hd * h3 * 1.0, fd = (c->prm.nu / hd) * (dt / hd) * h3 * 1.0;
+    if (adv_tma())
+      return advdiff_tma_launch<Real>(c, lv, nullptr, lv.nact, nullptr, 0.0, 0.0, fa, fd);
     static int minb = getenv("CUP_ADV_MINB") ? atoi(getenv("CUP_ADV_MINB")) : 8;
 #define ADV_LAUNCH(M)                                                                                              \
   k_advdiff<Real, M><<<bgrid(c, c->nblk, M), TPB, 0, c->stream>>>(                                                 \
@@ -529,6 +568,8 @@ int stencil_t(CupCtx *c, CupStencilId id, const int *d_sub, long long nsub) {
       (Real)c->prm.uinf[1], (Real)c->prm.uinf[2])
     if (minb == 5)
       ADV_LAUNCH(5);
+    else if (minb == 6)
+      ADV_LAUNCH(6);
     else if (minb == 10)
       ADV_LAUNCH(10);
     else if (minb == 12)
