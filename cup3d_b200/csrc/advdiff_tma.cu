@@ -89,11 +89,13 @@ __device__ __forceinline__ void issue_halo(Real *h, uint64_t *bar, const Real *v
     tma_load_3d(h + O_XHI, mx, 0, 0, nb[1] * 8, bar);
 }
 
-template <typename Real>
-__global__ void __launch_bounds__(TPB, 6) k_advdiff_tma(LevelView lv, AdvArgs<Real> A,
-                                                        const __grid_constant__ AdvMaps M) {
+// NS = 2: ghost arrays double buffered (32 KB per CTA in fp64, 6 CTAs per SM); NS = 1: single
+// buffered (22 KB, 8 CTAs per SM), the next item's ghosts are requested when the current item is done
+template <typename Real, int NS, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) k_advdiff_tma(LevelView lv, AdvArgs<Real> A,
+                                                           const __grid_constant__ AdvMaps M) {
   __shared__ __align__(128) Real core[3][CORE];
-  __shared__ __align__(128) Real halo[2][HALO];
+  __shared__ __align__(128) Real halo[NS][HALO];
   __shared__ __align__(8) uint64_t bar_core[3], bar_halo[2];
   const int t = threadIdx.x, x = t & 7, y = t >> 3;
   const Real *rsl = lv.rslab ? rslab_of<Real>(lv) : nullptr;
@@ -137,7 +139,8 @@ __global__ void __launch_bounds__(TPB, 6) k_advdiff_tma(LevelView lv, AdvArgs<Re
       tma_load_1d(core[c], A.vel[c] + own, CORE * sizeof(Real), &bar_core[c]);
     }
     issue_halo<Real>(halo[0], &bar_halo[0], A.vel[0], &M.x[0], &M.y[0], nbc);
-    issue_halo<Real>(halo[1], &bar_halo[1], A.vel[1], &M.x[1], &M.y[1], nbc);
+    if (NS == 2)
+      issue_halo<Real>(halo[1], &bar_halo[1], A.vel[1], &M.x[1], &M.y[1], nbc);
   }
   int item = 0;
   for (int j = 0; j < nmine; j++) {
@@ -163,15 +166,18 @@ __global__ void __launch_bounds__(TPB, 6) k_advdiff_tma(LevelView lv, AdvArgs<Re
     }
 #pragma unroll
     for (int c = 0; c < 3; c++, item++) {
-      const int s = item & 1;
+      const int s = NS == 2 ? (item & 1) : 0;
       Real *H = halo[s];
       const Real *C = core[c];
       // the accumulator is read-modify-write: get the reads going before anything else
+      // (only where the register budget allows it: NS == 2)
       Real acc[8];
+      if (NS == 2) {
 #pragma unroll
-      for (int k = 0; k < 8; k++)
-        acc[k] = A.tmp[c][own + k * 64 + t];
-      mbar_wait(&bar_halo[s], (item >> 1) & 1);
+        for (int k = 0; k < 8; k++)
+          acc[k] = A.tmp[c][own + k * 64 + t];
+      }
+      mbar_wait(&bar_halo[s], NS == 2 ? (item >> 1) & 1 : item & 1);
       if (odd) {
         const Real sx = (c == 0) ? (Real)-1 : (Real)1, sy = (c == 1) ? (Real)-1 : (Real)1,
                    sz = (c == 2) ? (Real)-1 : (Real)1;
@@ -256,7 +262,10 @@ __global__ void __launch_bounds__(TPB, 6) k_advdiff_tma(LevelView lv, AdvArgs<Re
         const Real Uabs[3] = {U0, U1, U2};
         const Real adv = Uabs[c] * dd[c] + (Uabs[a1] * dd[a1] + Uabs[a2] * dd[a2]);
         const Real lap = (pr[c] + (pr[a1] + pr[a2])) - (Real)6 * u;
-        oc[own + k * 64 + t] = acc[k] + (fac_a * adv + fac_d * lap);
+        if (NS == 2)
+          oc[own + k * 64 + t] = acc[k] + (fac_a * adv + fac_d * lap);
+        else
+          oc[own + k * 64 + t] += fac_a * adv + fac_d * lap;
       }
       __syncthreads();  // core c and ghost slot s are free
       if (t == 0) {
@@ -264,11 +273,19 @@ __global__ void __launch_bounds__(TPB, 6) k_advdiff_tma(LevelView lv, AdvArgs<Re
           mbar_arrive_expect_tx(&bar_core[c], CORE * sizeof(Real));
           tma_load_1d(core[c], A.vel[c] + (size_t)lv.act[bnext] * 512, CORE * sizeof(Real), &bar_core[c]);
         }
-        // item + 2: component (c + 2) % 3 of this block (c == 0) or of the next one
-        if (c == 0)
-          issue_halo<Real>(H, &bar_halo[s], A.vel[2], &M.x[2], &M.y[2], nbc);
-        else if (bnext >= 0)
-          issue_halo<Real>(H, &bar_halo[s], A.vel[c - 1], &M.x[c - 1], &M.y[c - 1], nbn);
+        if (NS == 2) {
+          // item + 2: component (c + 2) % 3 of this block (c == 0) or of the next one
+          if (c == 0)
+            issue_halo<Real>(H, &bar_halo[s], A.vel[2], &M.x[2], &M.y[2], nbc);
+          else if (bnext >= 0)
+            issue_halo<Real>(H, &bar_halo[s], A.vel[c - 1], &M.x[c - 1], &M.y[c - 1], nbn);
+        } else {
+          // item + 1
+          if (c < 2)
+            issue_halo<Real>(H, &bar_halo[s], A.vel[c + 1], &M.x[c + 1], &M.y[c + 1], nbc);
+          else if (bnext >= 0)
+            issue_halo<Real>(H, &bar_halo[s], A.vel[0], &M.x[0], &M.y[0], nbn);
+        }
       }
     }
     // advance to the next block; fetch the neighbour list of the one after
@@ -310,11 +327,17 @@ int advdiff_tma_launch(CupCtx *c, LevelView lv, const int *d_sub, int nsub, cons
   A.dtnu_nu = (Real)dtnu_nu;
   A.fac_a0 = (Real)fac_a;
   A.fac_d0 = (Real)fac_d;
-  static int per_sm = getenv("CUP_ADV_PER_SM") ? atoi(getenv("CUP_ADV_PER_SM")) : 6;
+  static int ns = getenv("CUP_ADV_SLOTS") ? atoi(getenv("CUP_ADV_SLOTS")) : 2;
+  static int per_sm = getenv("CUP_ADV_PER_SM") ? atoi(getenv("CUP_ADV_PER_SM")) : (ns == 2 ? 6 : 8);
   long long g = (long long)c->num_sms * per_sm;
   if (g > nsub)
     g = nsub;
-  k_advdiff_tma<Real><<<(int)g, TPB, 0, c->stream>>>(lv, A, M);
+  if (ns == 2)
+    k_advdiff_tma<Real, 2, 6><<<(int)g, TPB, 0, c->stream>>>(lv, A, M);
+  else if (per_sm <= 7)
+    k_advdiff_tma<Real, 1, 7><<<(int)g, TPB, 0, c->stream>>>(lv, A, M);
+  else
+    k_advdiff_tma<Real, 1, 8><<<(int)g, TPB, 0, c->stream>>>(lv, A, M);
   c->launches++;
   CUP_CUDA(cudaGetLastError());
   return CUP_OK;

@@ -164,7 +164,7 @@ __device__ __forceinline__ Real fine_avg_layer(const Real *__restrict__ cp, cons
   return (Real)0.125 * s;
 }
 
-enum { AD_ROW = 16, AD_SLAB = 14 * 16 };
+enum { AD_ROW = 24, AD_SLAB = 14 * 24 + 8 };  // bank-friendly padding, see stencil_kernels.cu
 
 template <typename Real>
 __global__ void __launch_bounds__(TPB) k_advdiff_amr(LevelView lv, const int *__restrict__ sub, int nsub, LeafGeom geo,

@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(256) k_rk_update(Real *__restrict__ v, Real *_
 // faces instead of 6 x 6.
 // ---------------------------------------------------------------------------
 template <typename Real>
-__global__ void __launch_bounds__(TPB) k_prhs(LevelView lv, const Real *__restrict__ v0, const Real *__restrict__ v1,
+__global__ void __launch_bounds__(TPB, 8) k_prhs(LevelView lv, const Real *__restrict__ v0, const Real *__restrict__ v1,
                                               const Real *__restrict__ v2, const Real *__restrict__ d0,
                                               const Real *__restrict__ d1, const Real *__restrict__ d2,
                                               const Real *__restrict__ chi, Real *__restrict__ lhs, Real fac) {
@@ -196,11 +196,29 @@ __global__ void __launch_bounds__(TPB) k_prhs(LevelView lv, const Real *__restri
   const Real *rsl = lv.rslab ? rslab_of<Real>(lv) : nullptr;
   // component q (0..5 = u v w udef_x udef_y udef_z), single layer, of the slab received for code nbc
   auto rem = [&](int nbc, int q) -> Real { return rsl[(size_t)(kRemote0 - nbc) * (64 * kSlabPlanes) + q * 64 + t]; };
-  for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
-    const size_t own = (size_t)lv.act[b] * 512;
-    const int *nbr6 = lv.nbr + (size_t)b * 6;
-    const int n0 = nbr6[0], n1 = nbr6[1], n2 = nbr6[2], n3 = nbr6[3], n4 = nbr6[4], n5 = nbr6[5];
-    Real w[8], dz[8];
+  // the block index and neighbour list of the NEXT iteration are fetched one iteration ahead, so the
+  // field loads of a block do not wait behind a dependent index load (ncu r01: 17.6 warps per issue
+  // stalled on the long scoreboard, three dependent DRAM round trips per block)
+  int b = blockIdx.x, slot_n = 0, nn[6] = {0, 0, 0, 0, 0, 0};
+  if (b < lv.nact) {
+    slot_n = lv.act[b];
+#pragma unroll
+    for (int f = 0; f < 6; f++)
+      nn[f] = lv.nbr[(size_t)b * 6 + f];
+  }
+  for (; b < lv.nact; b += gridDim.x) {
+    const size_t own = (size_t)slot_n * 512;
+    const int n0 = nn[0], n1 = nn[1], n2 = nn[2], n3 = nn[3], n4 = nn[4], n5 = nn[5];
+    {
+      const int bn = b + gridDim.x;
+      if (bn < lv.nact) {
+        slot_n = lv.act[bn];
+#pragma unroll
+        for (int f = 0; f < 6; f++)
+          nn[f] = lv.nbr[(size_t)bn * 6 + f];
+      }
+    }
+    Real w[8], dz[8], ch[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       tl[0][k * 64 + t] = v0[own + k * 64 + t];
@@ -209,6 +227,7 @@ __global__ void __launch_bounds__(TPB) k_prhs(LevelView lv, const Real *__restri
       tl[3][k * 64 + t] = d1[own + k * 64 + t];
       w[k] = v2[own + k * 64 + t];
       dz[k] = d2[own + k * 64 + t];
+      ch[k] = chi[own + k * 64 + t];
     }
     // x faces of u and udef_x: element (y = a, z = c2); wall: -own (normal component flips)
     hl[0][0][t] = n0 >= 0 ? v0[(size_t)n0 * 512 + c2 * 64 + a * 8 + 7] : (n0 == kWall ? -v0[own + c2 * 64 + a * 8] : rem(n0, 0));
@@ -243,7 +262,7 @@ __global__ void __launch_bounds__(TPB) k_prhs(LevelView lv, const Real *__restri
       const Real dzm_ = k > 0 ? dz[k > 0 ? k - 1 : 0] : dzm;
       Real p = fac * (((((uxp - uxm) + vyp) - vym) + wzp_) - wzm_);
       const Real div_us = ((((dxp - dxm) + dyp) - dym) + dzp_) - dzm_;
-      p += -chi[own + i] * fac * div_us;
+      p += -ch[k] * fac * div_us;
       lhs[own + i] = p;
     }
     __syncthreads();
@@ -581,6 +600,12 @@ int stencil_t(CupCtx *c, CupStencilId id, const int *d_sub, long long nsub) {
   }
   case CUP_ST_PRHS: {
     const double fac = 0.5 * hd * hd / dt;
+    static bool carve = false;  // 8 CTAs x 21.5 KB need the large shared-memory configuration
+    if (!carve) {
+      carve = true;
+      cudaFuncSetAttribute(k_prhs<Real>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared);
+    }
     k_prhs<Real><<<bgrid(c, c->nblk, 8), TPB, 0, c->stream>>>(lv, S[CUP_F_VEL], S[CUP_F_VEL + 1], S[CUP_F_VEL + 2],
                                                               S[CUP_F_TMP], S[CUP_F_TMP + 1], S[CUP_F_TMP + 2],
                                                               S[CUP_F_CHI], S[CUP_F_LHS], (Real)fac);
