@@ -71,6 +71,8 @@ SYMBOLS = {
     "cup_advdiff": (_i, [_vp]),
     "cup_projection": (_i, [_vp, C.POINTER(CupSolveInfo)]),
     "cup_projection_udef_ready": (_i, [_vp, _i]),
+    "cup_vorticity": (_i, [_vp]),
+    "cup_block_linf": (_i, [_vp, _i, _dp, _dp]),
     "cup_obstacle_upload": (_i, [_vp, _i, _i, _ip, _dp, _dp]),
     "cup_obstacle_motion": (_i, [_vp, _i, _dp, _dp, _dp]),
     "cup_obstacle_clear": (_i, [_vp]),
@@ -310,6 +312,16 @@ class Context:
 
     def obstacle_tmpv(self):
         check(self.L.cup_obstacle_tmpv(self.h))
+
+    def vorticity(self):
+        """vorticity() (main.c:5786): F_VEL -> F_TMP, scaled by 1/h^3"""
+        check(self.L.cup_vorticity(self.h))
+
+    def block_linf(self, f0=F_TMP):
+        """-> (linf_all [nblk], linf_fluid [nblk]): mesh_tag_blk's norm, without / with k_gradchi's zeroing"""
+        a, f = np.zeros(self.nblk), np.zeros(self.nblk)
+        check(self.L.cup_block_linf(self.h, f0, a.ctypes.data_as(_dp), f.ctypes.data_as(_dp)))
+        return a, f
 
     def umax(self):
         r = C.c_double()

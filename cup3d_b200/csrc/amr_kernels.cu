@@ -465,6 +465,127 @@ __global__ void __launch_bounds__(TPB) k_prhs_amr(LevelView lv, const Real *__re
 }
 
 // ---------------------------------------------------------------------------
+
+// ---------------------------------------------------------------------------
+// k_vort (main.c:5736) / k_q (:5762) on the leaves of a multi-level mesh.  All three velocity
+// components are needed on all six faces (same ghost fill as the pressure sweeps, per component).
+// k_vort carries a flux correction: face_sum(f, in = 3-a-d, out = a, +-inv2h) for every face
+// direction d and output component a != d (:5752-5758); k_q has none (outc = 0).
+// ---------------------------------------------------------------------------
+template <typename Real, int WHAT>  // 0 vorticity -> o0..o2, 1 Q -> o0
+__global__ void __launch_bounds__(TPB) k_velgrad_amr(LevelView lv, const Real *__restrict__ hblk,
+                                                     const Real *__restrict__ v0, const Real *__restrict__ v1,
+                                                     const Real *__restrict__ v2, Real *__restrict__ o0,
+                                                     Real *__restrict__ o1, Real *__restrict__ o2) {
+  __shared__ Real tl[3][512];
+  __shared__ Real hl[3][6][64];
+  __shared__ Real patch[3][6][16];
+  const int t = threadIdx.x, x = t & 7, y = t >> 3, a = t & 7, c = t >> 3;
+  const Real *vel[3] = {v0, v1, v2};
+  Real *outs[3] = {o0, o1, o2};
+  for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
+    const size_t own = (size_t)lv.act[b] * 512;
+    const int *nbr6 = lv.nbr + (size_t)b * 6;
+    const int *ext24 = lv.ext + (size_t)b * 24;
+    const Real h = hblk[b];
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      SlotVec<Real> pv{const_cast<Real *>(vel[q]), nullptr, 0x7fffffff};
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        tl[q][k * 64 + t] = vel[q][own + k * 64 + t];
+      halo_amr_phase1<Real>(pv, pv, vel[q] + own, nbr6, ext24, t, hl[q], patch[q]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      halo_amr_phase2<Real>(vel[q] + own, nbr6, t, hl[q], patch[q]);
+      // walls: the wall-normal component flips sign (OP_BC); phase 1 copied the boundary cell
+#pragma unroll
+      for (int f = 0; f < 6; f++)
+        if (nbr6[f] == kWall && (f >> 1) == q)
+          hl[q][f][t] = -hl[q][f][t];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int i = k * 64 + t;
+      Real g[3][3];  // g[q][d] = u_q(+d) - u_q(-d)
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        const Real xp = x < 7 ? tl[q][i + 1] : hl[q][1][y + 8 * k], xm = x > 0 ? tl[q][i - 1] : hl[q][0][y + 8 * k];
+        const Real yp = y < 7 ? tl[q][i + 8] : hl[q][3][x + 8 * k], ym = y > 0 ? tl[q][i - 8] : hl[q][2][x + 8 * k];
+        const Real zp = k < 7 ? tl[q][i + 64] : hl[q][5][t], zm = k > 0 ? tl[q][i - 64] : hl[q][4][t];
+        g[q][0] = xp - xm;
+        g[q][1] = yp - ym;
+        g[q][2] = zp - zm;
+      }
+      if (WHAT == 0) {
+        const Real inv2h = (Real).5 * h * h;
+        o0[own + i] = inv2h * (g[2][1] - g[1][2]);
+        o1[own + i] = inv2h * (g[0][2] - g[2][0]);
+        o2[own + i] = inv2h * (g[1][0] - g[0][1]);
+      } else {
+        const Real inv2h = (Real).5 / h;
+        Real gg[3][3];
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+#pragma unroll
+          for (int d = 0; d < 3; d++)
+            gg[q][d] = inv2h * g[q][d];
+        Real qq = 0;
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+#pragma unroll
+          for (int d = 0; d < 3; d++)
+            qq -= (Real)0.5 * gg[q][d] * gg[d][q];
+        o0[own + i] = qq;
+      }
+    }
+    __syncthreads();
+    if (WHAT == 0) {
+#pragma unroll 1
+      for (int f = 0; f < 6; f++) {
+        if (nbr6[f] != kFine)
+          continue;
+        const int d = f >> 1, nI = (f & 1) ? 7 : 0;
+        const int cell = face_idx(f, nI, a, c);
+        const Real hf = (Real)0.5 * h;
+        const Real i2h = (Real).5 * h * h, i2hf = (Real).5 * hf * hf;
+#pragma unroll 1
+        for (int oa = 0; oa < 3; oa++) {
+          if (oa == d)
+            continue;
+          const int q = 3 - oa - d;                            // input component
+          const Real sg = (d == (oa + 1) % 3) ? (Real)1 : (Real)-1;
+          SlotVec<Real> pv{const_cast<Real *>(vel[q]), nullptr, 0x7fffffff};
+          Real lay[2][2][2], mine[16];
+          (void)fine_avg<Real>(pv, ext24 + f * 4, f, a, c, lay);
+#pragma unroll
+          for (int m = 0; m < 16; m++)
+            mine[m] = tl[q][face_idx(f, nI, 4 * (a >> 2) + (m & 3), 4 * (c >> 2) + (m >> 2))];
+          const Real so = (f & 1) ? -(sg * i2h) : sg * i2h;          // face_sum on my face f
+          const Real sf = ((f ^ 1) & 1) ? -(sg * i2hf) : sg * i2hf;  // and on the fine blocks' face f^1
+          const Real Fown = so * (hl[q][f][t] + tl[q][cell]);
+          Real Ff[2][2];
+#pragma unroll
+          for (int j2 = 0; j2 < 2; j2++)
+#pragma unroll
+            for (int j1 = 0; j1 < 2; j1++) {
+              const Real gh =
+                  fd_ghost<Real>(mine, 2 * (a & 3) + j1, 2 * (c & 3) + j2, lay[0][j2][j1], lay[1][j2][j1]);
+              Ff[j2][j1] = sf * (gh + lay[0][j2][j1]);
+            }
+          const Real fsum = (Ff[0][0] + Ff[0][1]) + (Ff[1][0] + Ff[1][1]);
+          outs[oa][own + cell] += Fown + fsum;
+        }
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+  }
+}
+
 static inline int agrid(const CupCtx *c, long long n) {
   long long g = (long long)c->num_sms * 8;
   return (int)(g < n ? g : (n < 1 ? 1 : n));
@@ -522,6 +643,21 @@ int prhs_amr_launch(CupCtx *c, LevelView lv, const void *hblk, Real *const *S, R
                                                              S[CUP_F_TMP + 2], S[CUP_F_CHI], S[CUP_F_LHS], idt2);
   return CUP_OK;
 }
+
+template <typename Real>
+int velgrad_amr_launch(CupCtx *c, LevelView lv, const void *hblk, Real *const *S, int what) {
+  if (what == 0)
+    k_velgrad_amr<Real, 0><<<agrid(c, lv.nact), TPB, 0, c->stream>>>(lv, (const Real *)hblk, S[CUP_F_VEL],
+                                                                     S[CUP_F_VEL + 1], S[CUP_F_VEL + 2], S[CUP_F_TMP],
+                                                                     S[CUP_F_TMP + 1], S[CUP_F_TMP + 2]);
+  else
+    k_velgrad_amr<Real, 1><<<agrid(c, lv.nact), TPB, 0, c->stream>>>(lv, (const Real *)hblk, S[CUP_F_VEL],
+                                                                     S[CUP_F_VEL + 1], S[CUP_F_VEL + 2], S[CUP_F_LHS],
+                                                                     nullptr, nullptr);
+  return CUP_OK;
+}
+template int velgrad_amr_launch<double>(CupCtx *, LevelView, const void *, double *const *, int);
+template int velgrad_amr_launch<float>(CupCtx *, LevelView, const void *, float *const *, int);
 
 template int pres_amr_launch<double>(CupCtx *, LevelView, const void *, const double *, double *, double *, double *,
                                      double, int);

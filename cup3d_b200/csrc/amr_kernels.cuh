@@ -23,6 +23,9 @@ int pres_amr_launch(CupCtx *c, LevelView lv, const void *hblk, const Real *p, Re
 // k_prhs; S = the nine state components, idt2 = 1/dt
 template <typename Real>
 int prhs_amr_launch(CupCtx *c, LevelView lv, const void *hblk, Real *const *S, Real idt2);
+// what 0 = k_vort (F_VEL -> F_TMP, with its flux correction), 1 = k_q (F_VEL -> F_LHS)
+template <typename Real>
+int velgrad_amr_launch(CupCtx *c, LevelView lv, const void *hblk, Real *const *S, int what);
 // k_advdiff on the leaves of a multi-level mesh (amr_advdiff.cu)
 template <typename Real>
 int advdiff_amr_launch(CupCtx *c, const Level &v, Real *const *S, const int *sub = nullptr, int nsub = -1);

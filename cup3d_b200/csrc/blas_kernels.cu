@@ -7,6 +7,9 @@
 // reductions finished with one atomicAdd per CTA into a device scalar so the
 // host never waits for intermediate results.
 #include "blas_kernels.cuh"
+
+#include <algorithm>
+#include <vector>
 #include "cup_internal.h"
 #include "comm.cuh"
 
@@ -139,6 +142,96 @@ int umax(CupCtx *c, double *out) {
   CUP_TRY(comm_allreduce_max(c, 6, 1));
   CUP_TRY(fetch_scalars(c, 6, 1));
   *out = c->h_scal[6];
+  return CUP_OK;
+}
+
+// vorticity()'s scaling (main.c:5789-5796): the three F_TMP components times 1/h^3 of the block
+template <typename Real>
+__global__ void __launch_bounds__(256) k_scale_blk3(Real *__restrict__ a0, Real *__restrict__ a1,
+                                                    Real *__restrict__ a2, const Real *__restrict__ ih3,
+                                                    long long nblk) {
+  for (long long b = blockIdx.x; b < nblk; b += gridDim.x) {
+    const Real f = ih3[b];
+    for (int j = threadIdx.x; j < 512; j += blockDim.x) {
+      a0[b * 512 + j] *= f;
+      a1[b * 512 + j] *= f;
+      a2[b * 512 + j] *= f;
+    }
+  }
+}
+
+int scale_blk3(CupCtx *c, void *a0, void *a1, void *a2) {
+  const int g = (int)std::min<long long>(c->nblk, (long long)c->num_sms * 8);
+  if (c->real_bytes == 8)
+    k_scale_blk3<double><<<g, 256, 0, c->stream>>>((double *)a0, (double *)a1, (double *)a2, (const double *)c->d_hw,
+                                                   c->nblk);
+  else
+    k_scale_blk3<float><<<g, 256, 0, c->stream>>>((float *)a0, (float *)a1, (float *)a2, (const float *)c->d_hw,
+                                                  c->nblk);
+  c->launches++;
+  CUP_CUDA(cudaGetLastError());
+  return CUP_OK;
+}
+
+// mesh_tag_blk's norm (main.c:3683-3688): Linf over the block of |(u0,u1,u2)|, in double, and the same
+// over the cells k_gradchi (main.c:3649) would not have zeroed, i.e. chi <= 0.9.
+// out[2b] = all cells, out[2b+1] = fluid cells.  One warp per block.
+template <typename Real>
+__global__ void __launch_bounds__(256) k_blk_linf(const Real *__restrict__ u0, const Real *__restrict__ u1,
+                                                  const Real *__restrict__ u2, const Real *__restrict__ chi,
+                                                  long long nblk, double *__restrict__ out) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (long long b = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); b < nblk; b += (long long)gridDim.x * wpb) {
+    double ma = 0, mf = 0;
+    for (int j = lane; j < 512; j += 32) {
+      const double a = (double)u0[b * 512 + j], bb = (double)u1[b * 512 + j], cc = (double)u2[b * 512 + j];
+      const double m = fabs(sqrt(a * a + bb * bb + cc * cc));
+      ma = m > ma ? m : ma;
+      if (!((double)chi[b * 512 + j] > 0.9))
+        mf = m > mf ? m : mf;
+    }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) {
+      ma = fmax(ma, __shfl_xor_sync(0xffffffffu, ma, k));
+      mf = fmax(mf, __shfl_xor_sync(0xffffffffu, mf, k));
+    }
+    if (lane == 0) {
+      out[2 * b] = ma;
+      out[2 * b + 1] = mf;
+    }
+  }
+}
+
+int block_linf(CupCtx *c, int f0, double *h_all, double *h_fluid) {
+  if (c->nblk == 0) {
+    set_error("block_linf: no mesh uploaded");
+    return CUP_ERR_STATE;
+  }
+  if (f0 < 0 || f0 + 3 > CUP_F_N) {
+    set_error("block_linf: field %d", f0);
+    return CUP_ERR_ARG;
+  }
+  double *d = (double *)c->tmp_stage;  // nblk*512 doubles of scratch; 2*nblk used
+  const int g = (int)std::min<long long>((c->nblk + 7) / 8, (long long)c->num_sms * 8);
+  if (c->real_bytes == 8)
+    k_blk_linf<double><<<g, 256, 0, c->stream>>>((const double *)c->state[f0], (const double *)c->state[f0 + 1],
+                                                 (const double *)c->state[f0 + 2],
+                                                 (const double *)c->state[CUP_F_CHI], c->nblk, d);
+  else
+    k_blk_linf<float><<<g, 256, 0, c->stream>>>((const float *)c->state[f0], (const float *)c->state[f0 + 1],
+                                                (const float *)c->state[f0 + 2], (const float *)c->state[CUP_F_CHI],
+                                                c->nblk, d);
+  c->launches++;
+  CUP_CUDA(cudaGetLastError());
+  std::vector<double> h((size_t)c->nblk * 2);
+  CUP_CUDA(cudaMemcpyAsync(h.data(), d, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUP_CUDA(cudaStreamSynchronize(c->stream));
+  for (long long b = 0; b < c->nblk; b++) {
+    if (h_all)
+      h_all[b] = h[2 * b];
+    if (h_fluid)
+      h_fluid[b] = h[2 * b + 1];
+  }
   return CUP_OK;
 }
 

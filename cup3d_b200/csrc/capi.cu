@@ -270,6 +270,10 @@ int cup_pois_dot_dev(CupCtx *c, const void *a, const void *b, double *result) {
 int cup_pois_solve(CupCtx *c, CupSolveInfo *info) { return pois_solve(c, info); }
 int cup_umax(CupCtx *c, double *out) { return umax(c, out); }
 int cup_advdiff(CupCtx *c) { return advdiff(c); }
+int cup_vorticity(CupCtx *c) { return vorticity(c); }
+int cup_block_linf(CupCtx *c, int f0, double *linf_all, double *linf_fluid) {
+  return block_linf(c, f0, linf_all, linf_fluid);
+}
 int cup_projection(CupCtx *c, CupSolveInfo *info) { return projection(c, info); }
 int cup_projection_udef_ready(CupCtx *c, int flag) {
   c->keep_tmp_udef = flag != 0;

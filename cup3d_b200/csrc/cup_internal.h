@@ -186,11 +186,14 @@ int time_smooth(CupCtx *c, int level, int reps, float *ms);
 int wdot(CupCtx *c, const void *a, const void *b, int scal_idx);  // -> d_scal[idx] (accumulates from 0)
 int fetch_scalars(CupCtx *c, int first, int n);                   // d_scal -> h_scal, synchronises
 int umax(CupCtx *c, double *out);                                 // sta_umax over all ranks
+int scale_blk3(CupCtx *c, void *a0, void *a1, void *a2);          // a_q[b] *= 1/h_b^3
+int block_linf(CupCtx *c, int f0, double *h_all, double *h_fluid);  // per-block |.|_inf of 3 components
 
 // solver.cu
 int pois_solve(CupCtx *c, CupSolveInfo *info);
 int advdiff(CupCtx *c);
 int projection(CupCtx *c, CupSolveInfo *info);
+int vorticity(CupCtx *c);  // vorticity(), main.c:5786: k_vort then 1/h^3
 int stencil_run(CupCtx *c, CupStencilId id, const long long *list, long long n);
 void free_krylov(CupCtx *c);
 

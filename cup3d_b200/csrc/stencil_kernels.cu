@@ -326,6 +326,7 @@ __global__ void __launch_bounds__(TPB) k_velgrad(LevelView lv, const Real *__res
   __shared__ Real hl[3][6][64];
   const int t = threadIdx.x, x = t & 7, y = t >> 3, a = t & 7, c2 = t >> 3;
   const Real *vel[3] = {v0, v1, v2};
+  const Real *rsl = lv.rslab ? rslab_of<Real>(lv) : nullptr;
   for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
     const size_t own = (size_t)lv.act[b] * 512;
     const int *nbr6 = lv.nbr + (size_t)b * 6;
@@ -340,7 +341,10 @@ __global__ void __launch_bounds__(TPB) k_velgrad(LevelView lv, const Real *__res
         const int p = (nb >= 0) ? ((f & 1) ? 0 : 7) : ((f & 1) ? 7 : 0);
         const int idx = f < 2 ? (c2 << 6) + (a << 3) + p : (f < 4 ? (c2 << 6) + (p << 3) + a : (p << 6) + t);
         // wall: nearest interior cell, wall-normal component negated (OP_BC, vflip = 0)
-        hl[q][f][t] = nb >= 0 ? vel[q][(size_t)nb * 512 + idx] : ((f >> 1) == q ? -vel[q][own + idx] : vel[q][own + idx]);
+        // face owned by another rank: component q, single layer, of the received slab
+        hl[q][f][t] = nb >= 0 ? vel[q][(size_t)nb * 512 + idx]
+                              : (nb == kWall ? ((f >> 1) == q ? -vel[q][own + idx] : vel[q][own + idx])
+                                             : rsl[(size_t)(kRemote0 - nb) * (64 * kSlabPlanes) + q * 64 + t]);
       }
     }
     __syncthreads();
@@ -531,6 +535,12 @@ int stencil_amr_t(CupCtx *c, CupStencilId id) {
     CUP_TRY(pres_amr_launch<Real>(c, lv, v.d_hblk, S[CUP_F_PRES], S[CUP_F_TMP], S[CUP_F_TMP + 1], S[CUP_F_TMP + 2],
                                   (Real)(-0.5 * dt), 1));
     break;
+  case CUP_ST_VORT:
+    CUP_TRY(velgrad_amr_launch<Real>(c, lv, v.d_hblk, S, 0));
+    break;
+  case CUP_ST_Q:
+    CUP_TRY(velgrad_amr_launch<Real>(c, lv, v.d_hblk, S, 1));
+    break;
   default:
     set_error("stencil %d on a multi-level mesh is not available in this build", (int)id);
     return CUP_ERR_UNSUPPORTED;
@@ -559,6 +569,10 @@ int stencil_t(CupCtx *c, CupStencilId id, const int *d_sub, long long nsub) {
                          (const Real *)c->state[CUP_F_VEL + 2], (const Real *)c->state[CUP_F_TMP],
                          (const Real *)c->state[CUP_F_TMP + 1], (const Real *)c->state[CUP_F_TMP + 2]}};
       CUP_TRY(slab_exchange<Real>(c, vm, src, 6, 1));
+    } else if (id == CUP_ST_VORT || id == CUP_ST_Q) {
+      SlabSrc<Real> src{{(const Real *)c->state[CUP_F_VEL], (const Real *)c->state[CUP_F_VEL + 1],
+                         (const Real *)c->state[CUP_F_VEL + 2], nullptr, nullptr, nullptr}};
+      CUP_TRY(slab_exchange<Real>(c, vm, src, 3, 1));
     } else if (id == CUP_ST_DIVP || id == CUP_ST_GRADP) {
       SlotVec<Real> pv{(Real *)c->state[CUP_F_PRES], nullptr, (int)c->nblk};
       CUP_TRY(halo_exchange<Real>(c, vm, pv));
@@ -622,19 +636,11 @@ int stencil_t(CupCtx *c, CupStencilId id, const int *d_sub, long long nsub) {
     break;
   }
   case CUP_ST_VORT:
-    if (c->nranks > 1) {
-      set_error("k_vort is single-rank in this build");
-      return CUP_ERR_UNSUPPORTED;
-    }
     k_velgrad<Real, 0><<<bgrid(c, c->nblk, 8), TPB, 0, c->stream>>>(lv, S[CUP_F_VEL], S[CUP_F_VEL + 1],
                                                                     S[CUP_F_VEL + 2], S[CUP_F_TMP], S[CUP_F_TMP + 1],
                                                                     S[CUP_F_TMP + 2], h);
     break;
   case CUP_ST_Q:
-    if (c->nranks > 1) {
-      set_error("k_q is single-rank in this build");
-      return CUP_ERR_UNSUPPORTED;
-    }
     k_velgrad<Real, 1><<<bgrid(c, c->nblk, 8), TPB, 0, c->stream>>>(lv, S[CUP_F_VEL], S[CUP_F_VEL + 1],
                                                                     S[CUP_F_VEL + 2], S[CUP_F_LHS], nullptr, nullptr,
                                                                     h);
@@ -751,6 +757,11 @@ int stencil_run(CupCtx *c, CupStencilId id, const long long *list, long long n) 
     return CUP_ERR_UNSUPPORTED;
   }
   return c->real_bytes == 8 ? stencil_t<double>(c, id, nullptr, n) : stencil_t<float>(c, id, nullptr, n);
+}
+
+int vorticity(CupCtx *c) {
+  CUP_TRY(stencil_run(c, CUP_ST_VORT, nullptr, c->nblk));
+  return scale_blk3(c, c->state[CUP_F_TMP], c->state[CUP_F_TMP + 1], c->state[CUP_F_TMP + 2]);
 }
 
 int advdiff(CupCtx *c) {

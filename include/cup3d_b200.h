@@ -171,6 +171,17 @@ int cup_obstacle_tmpv(CupCtx *ctx);
  * control (sta_dt) needs only this scalar, so F_VEL can stay on the device. */
 int cup_umax(CupCtx *ctx, double *umax);
 
+/* ---- mesh_adapt's tagging input (main.c:4012-4019) ----
+ * vorticity() (main.c:5786): k_vort sweep F_VEL -> F_TMP (with its coarse-fine flux correction)
+ * scaled by 1/h^3 per block. */
+int cup_vorticity(CupCtx *ctx);
+/* mesh_tag_blk's norm (main.c:3683): per local block, max over cells of |(f0, f0+1, f0+2)|_2.
+ * linf_all[b]: all cells; linf_fluid[b]: cells with F_CHI <= 0.9, i.e. what the norm is after
+ * k_gradchi (main.c:3649) zeroed the cells inside bodies.  The OTHER effect of k_gradchi, the
+ * 1e10 marker of blocks whose extended chi neighbourhood contains 1e-5 < chi < 0.9, depends on F_CHI
+ * alone and stays on the host (F_CHI is produced there by fish_build).  NULL = not wanted. */
+int cup_block_linf(CupCtx *ctx, int f0, double *linf_all, double *linf_fluid);
+
 /* One rank per GPU.  nccl_id = the 128 bytes of an ncclUniqueId created on
  * rank 0 and distributed by the caller (torch.distributed / MPI_Bcast). */
 int cup_comm_init(CupCtx *ctx, int rank, int nranks, const void *nccl_id, size_t id_bytes);

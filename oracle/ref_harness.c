@@ -103,9 +103,9 @@ API void ref_pois_solve(void) { pois_solve(); }
 API void ref_advdiff(void) { advdiff(); }
 API void ref_projection(void) { projection(); }
 
-/* 0 lhs, 1 mg, 2 advdiff, 3 prhs, 4 divp, 5 gradp, 6 vort, 7 q */
+/* 0 lhs, 1 mg, 2 advdiff, 3 prhs, 4 divp, 5 gradp, 6 vort, 7 q, 8 gradchi */
 API int ref_stencil(int id) {
-  struct Stencil *tab[] = {&st_lhs, &st_mg, &st_advdiff, &st_prhs, &st_divp, &st_gradp, &st_vort, &st_q};
+  struct Stencil *tab[] = {&st_lhs, &st_mg, &st_advdiff, &st_prhs, &st_divp, &st_gradp, &st_vort, &st_q, &st_gradchi};
   if (id < 0 || id >= (int)(sizeof tab / sizeof *tab))
     return 1;
   stencil_apply(tab[id]);
@@ -155,6 +155,9 @@ API double ref_time_stencil(int id, int w, int n) {
     ref_stencil(id);
   return now() - t0;
 }
+
+/* vorticity() (main.c:5786): k_vort sweep, then 1/h^3 per block */
+API void ref_vorticity(void) { vorticity(); }
 
 /* sta_umax (main.c:5918): max over cells of max_a |u_a + uinf_a| */
 API double ref_umax(void) { return sta_umax(); }

@@ -16,7 +16,7 @@ LIB = os.path.join(REFDIR, "libcup3d_ref.so")
 BS3 = 512
 F_N = 9
 F_CHI, F_PRES, F_VEL, F_TMP, F_LHS = 0, 1, 2, 5, 8
-STENCILS = {"lhs": 0, "mg": 1, "advdiff": 2, "prhs": 3, "divp": 4, "gradp": 5, "vort": 6, "q": 7}
+STENCILS = {"lhs": 0, "mg": 1, "advdiff": 2, "prhs": 3, "divp": 4, "gradp": 5, "vort": 6, "q": 7, "gradchi": 8}
 
 _lib = None
 dp = C.POINTER(C.c_double)
@@ -138,6 +138,10 @@ def advdiff():
 
 def projection():
     _lib.ref_projection()
+
+
+def vorticity():
+    _lib.ref_vorticity()
 
 
 def umax():

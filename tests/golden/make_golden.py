@@ -134,13 +134,26 @@ def worker(case):
     if tier != "big":
         keep = {"lhs": (R.F_LHS, 1), "advdiff": (R.F_TMP, 3), "prhs": (R.F_LHS, 1), "divp": (R.F_TMP, 1),
                 "gradp": (R.F_TMP, 3)}
-        if case not in ADAPT:
-            keep.update({"vort": (R.F_TMP, 3), "q": (R.F_LHS, 1)})
+        keep.update({"vort": (R.F_TMP, 3), "q": (R.F_LHS, 1)})
         for name, (f0, nc) in keep.items():
             R.set_scalars(dt=dt, nu=nu, uinf=uinf, step=5, mean_constraint=2)
             R.state_set(st)
             R.stencil(name)
             g["st_" + name] = R.state_get()[:, f0:f0 + nc]
+        # mesh_adapt's tagging input (main.c:4017-4019): vorticity(), then k_gradchi marks blocks at the
+        # chi interface (1e10) and zeroes the vorticity inside bodies; mesh_tag_blk takes the block Linf
+        R.set_scalars(dt=dt, nu=nu, uinf=uinf, step=5, mean_constraint=2)
+        R.state_set(st)
+        R.vorticity()
+        w = R.state_get()[:, R.F_TMP:R.F_TMP + 3]
+        g["tag_linf_all"] = np.abs(np.sqrt((w * w).sum(1))).max(1)
+        g["tag_linf_fluid"] = np.where(st[:, R.F_CHI] > 0.9, 0.0, np.abs(np.sqrt((w * w).sum(1)))).max(1)
+        R.stencil("gradchi")
+        w = R.state_get()[:, R.F_TMP:R.F_TMP + 3]
+        g["tag_marked"] = (w[:, 0, (3 * 8 + 3) * 8 + 3] == 1e10)
+        g["tag_linf"] = np.abs(np.sqrt((w * w).sum(1))).max(1)
+        # where k_gradchi did not mark the block, its zeroing is exactly the chi <= 0.9 mask
+        assert np.array_equal(g["tag_linf"][~g["tag_marked"]], g["tag_linf_fluid"][~g["tag_marked"]])
         R.set_scalars(dt=dt, nu=nu, uinf=uinf, step=5, mean_constraint=2)
         R.state_set(st)
         R.advdiff()

@@ -136,8 +136,19 @@ def worker(case):
     s5 = R.state_get()
     g["proj"] = s5[obu, R.F_PRES:R.F_PRES + 4]
     g["proj_sums"] = checksums(s5[:, R.F_PRES:R.F_PRES + 4])
+    # mesh_adapt's tagging input on the projected state (main.c:4017-4019)
+    R.vorticity()
+    w = R.state_get()[:, R.F_TMP:R.F_TMP + 3]
+    mag = np.abs(np.sqrt((w * w).sum(1)))
+    g["tag_linf_all"] = mag.max(1)
+    g["tag_linf_fluid"] = np.where(chi_field > 0.9, 0.0, mag).max(1)
+    R.stencil("gradchi")
+    w = R.state_get()[:, R.F_TMP:R.F_TMP + 3]
+    g["tag_marked"] = (w[:, 0, (3 * 8 + 3) * 8 + 3] == 1e10)
+    g["tag_linf"] = np.abs(np.sqrt((w * w).sum(1))).max(1)
+    assert np.array_equal(g["tag_linf"][~g["tag_marked"]], g["tag_linf_fluid"][~g["tag_marked"]])
     np.savez_compressed(os.path.join(HERE, case + ".npz"), **g)
-    print(case, "nblk", n, "levels", np.bincount(ib[:, 0]), "nfish", nf, "nob", [len(o[0]) for o in obs], "dt", dt,
+    print(case, "marked", int(g["tag_marked"].sum()), "nblk", n, "levels", np.bincount(ib[:, 0]), "nfish", nf, "nob", [len(o[0]) for o in obs], "dt", dt,
           "uinf", sc["uinf"], "|vel|", [float(np.abs(m[1]).max()) for m in mot],
           "|omega|", [float(np.abs(m[2]).max()) for m in mot])
 

@@ -88,9 +88,10 @@ def test_amr_pois_solve(built):
 
 
 @pytest.mark.parametrize("st,sid,f0,nc", [("prhs", capi.ST_PRHS, 8, 1), ("divp", capi.ST_DIVP, 5, 1),
-                                          ("gradp", capi.ST_GRADP, 5, 3), ("advdiff", capi.ST_ADVDIFF, 5, 3)])
+                                          ("gradp", capi.ST_GRADP, 5, 3), ("advdiff", capi.ST_ADVDIFF, 5, 3),
+                                          ("vort", capi.ST_VORT, 5, 3), ("q", capi.ST_Q, 8, 1)])
 def test_amr_projection_sweeps(built, st, sid, f0, nc):
-    """k_prhs / k_divp / k_gradp with their flux correction on a 2-level mesh"""
+    """k_prhs / k_divp / k_gradp / k_vort with their flux correction (and k_q) on a 2-level mesh"""
     c = case("amr2")
     ctx = make_ctx(c)
     s0 = c.state0()
@@ -127,4 +128,19 @@ def test_amr_advdiff_rk3(built):
     out = np.zeros_like(s0)
     ctx.state_d2h(out)
     assert relerr(out[:, 2:5], c.g["advdiff"][:, 0:3]) < 1e-12
+    ctx.close()
+
+
+def test_amr_vorticity_block_norms(built):
+    """vorticity() + mesh_tag_blk's per-block norm, without and with k_gradchi's zeroing (chi > 0.9)"""
+    c = case("amr2")
+    ctx = make_ctx(c)
+    ctx.state_h2d(c.state0())
+    ctx.vorticity()
+    la, lf = ctx.block_linf()
+    assert np.max(np.abs(la - c.g["tag_linf_all"]) / c.g["tag_linf_all"]) < 1e-12
+    assert np.max(np.abs(lf - c.g["tag_linf_fluid"])) < 1e-12 * np.max(c.g["tag_linf_all"])
+    # blocks the reference's k_gradchi did not mark: the fluid norm IS mesh_tag_blk's Linf
+    um = ~c.g["tag_marked"]
+    assert np.max(np.abs(lf[um] - c.g["tag_linf"][um])) < 1e-12 * np.max(c.g["tag_linf_all"])
     ctx.close()

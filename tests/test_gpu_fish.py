@@ -61,6 +61,15 @@ def test_fish_step(built, name):
     esp = relerr(checksums(s5[:, 1:2]), c.g["proj_sums"][:, 0:1])
     esv = relerr(checksums(s5[:, 2:5]), c.g["proj_sums"][:, 1:4])
     assert ep < 1e-7 and ev < 1e-9 and esp < 1e-7 and esv < 1e-9, (ep, ev, esp, esv, info.iterations)
+    # mesh_adapt's tagging input on the projected state: vorticity() and the per-block norms; where the
+    # reference's k_gradchi did not mark the block, the fluid norm is mesh_tag_blk's Linf
+    ctx.vorticity()
+    la, lf = ctx.block_linf()
+    scale = np.max(c.g["tag_linf_all"])
+    assert np.max(np.abs(la - c.g["tag_linf_all"])) < 1e-7 * scale
+    assert np.max(np.abs(lf - c.g["tag_linf_fluid"])) < 1e-7 * scale
+    um = ~c.g["tag_marked"]
+    assert um.sum() > 0.5 * c.n and np.max(np.abs(lf[um] - c.g["tag_linf"][um])) < 1e-7 * scale
     ctx.close()
 
 

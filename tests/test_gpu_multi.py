@@ -95,7 +95,7 @@ def worker_step(rank, world, nid, name, q):
     out = {}
     s0 = np.ascontiguousarray(c.state0()[mine])
     for st, sid in (("advdiff", capi.ST_ADVDIFF), ("prhs", capi.ST_PRHS), ("divp", capi.ST_DIVP),
-                    ("gradp", capi.ST_GRADP)):
+                    ("gradp", capi.ST_GRADP), ("vort", capi.ST_VORT), ("q", capi.ST_Q)):
         ctx.state_h2d(s0)
         ctx.stencil_apply(sid)
         r = np.zeros_like(s0)
@@ -142,6 +142,8 @@ def test_two_rank_time_step_pieces(built, name):
     assert relerr(full["st_prhs"][:, 8:9], c.g["st_prhs"]) < 1e-12
     assert relerr(full["st_divp"][:, 5:6], c.g["st_divp"]) < 1e-12
     assert relerr(full["st_gradp"][:, 5:8], c.g["st_gradp"]) < 1e-12
+    assert relerr(full["st_vort"][:, 5:8], c.g["st_vort"]) < 1e-12
+    assert relerr(full["st_q"][:, 8:9], c.g["st_q"]) < 1e-12
     assert relerr(full["advdiff"][:, 2:5], c.g["advdiff"][:, 0:3]) < 1e-12
     assert relerr(full["proj"][:, 1], c.g["proj_step5"][:, 0]) < 1e-7
     assert relerr(full["proj"][:, 2:5], c.g["proj_step5"][:, 1:4]) < 1e-9

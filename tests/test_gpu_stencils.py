@@ -87,3 +87,16 @@ def test_umax(built, name):
     ctx.state_h2d(c.state0())
     assert abs(ctx.umax() - float(c.g["umax"])) <= 1e-15 * float(c.g["umax"])
     ctx.close()
+
+
+@pytest.mark.parametrize("name", STENCIL_CASES)
+def test_vorticity_block_norms(built, name):
+    """vorticity() (k_vort, 1/h^3) and mesh_tag_blk's per-block norm (main.c:3683), all cells / chi <= 0.9"""
+    c = case(name)
+    ctx = make_ctx(c)
+    ctx.state_h2d(c.state0())
+    ctx.vorticity()
+    la, lf = ctx.block_linf()
+    assert np.max(np.abs(la - c.g["tag_linf_all"]) / c.g["tag_linf_all"]) < 1e-12
+    assert np.max(np.abs(lf - c.g["tag_linf_fluid"])) < 1e-12 * np.max(c.g["tag_linf_all"])
+    ctx.close()
