@@ -211,7 +211,7 @@ int block_linf(CupCtx *c, int f0, double *h_all, double *h_fluid) {
     set_error("block_linf: field %d", f0);
     return CUP_ERR_ARG;
   }
-  double *d = (double *)c->tmp_stage;  // nblk*512 doubles of scratch; 2*nblk used
+  double *d = (double *)c->tmp_out;  // leaf-sized scratch of doubles (host-pointer entry points); 2*nblk used
   const int g = (int)std::min<long long>((c->nblk + 7) / 8, (long long)c->num_sms * 8);
   if (c->real_bytes == 8)
     k_blk_linf<double><<<g, 256, 0, c->stream>>>((const double *)c->state[f0], (const double *)c->state[f0 + 1],
