@@ -148,10 +148,10 @@ int umax(CupCtx *c, double *out) {
 // vorticity()'s scaling (main.c:5789-5796): the three F_TMP components times 1/h^3 of the block
 template <typename Real>
 __global__ void __launch_bounds__(256) k_scale_blk3(Real *__restrict__ a0, Real *__restrict__ a1,
-                                                    Real *__restrict__ a2, const Real *__restrict__ ih3,
+                                                    Real *__restrict__ a2, const Real *__restrict__ h3,
                                                     long long nblk) {
   for (long long b = blockIdx.x; b < nblk; b += gridDim.x) {
-    const Real f = ih3[b];
+    const Real f = (Real)1.0 / h3[b];
     for (int j = threadIdx.x; j < 512; j += blockDim.x) {
       a0[b * 512 + j] *= f;
       a1[b * 512 + j] *= f;

@@ -153,7 +153,7 @@ struct CupCtx {
   // leaf-sized temporaries used by the host-pointer entry points and drivers
   void *tmp_in = nullptr, *tmp_out = nullptr, *tmp_stage = nullptr;
   void *d_W = nullptr;          // FDM eigenvalue table, lane-major [8][64]
-  void *d_hw = nullptr;         // per-leaf 1/h^3 (pois.hw, main.c:4886)
+  void *d_hw = nullptr;         // per-leaf h^3 (pois.hw, main.c:4886, is its reciprocal)
   double *d_scal = nullptr;     // device scalars (reductions); always double
   double *h_scal = nullptr;     // pinned mirror
   cup::Krylov *kr = nullptr;
