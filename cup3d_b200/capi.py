@@ -73,6 +73,7 @@ SYMBOLS = {
     "cup_projection_udef_ready": (_i, [_vp, _i]),
     "cup_vorticity": (_i, [_vp]),
     "cup_block_linf": (_i, [_vp, _i, _dp, _dp]),
+    "cup_io_pack": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "cup_obstacle_upload": (_i, [_vp, _i, _i, _ip, _dp, _dp]),
     "cup_obstacle_motion": (_i, [_vp, _i, _dp, _dp, _dp]),
     "cup_obstacle_clear": (_i, [_vp]),
@@ -316,6 +317,15 @@ class Context:
     def vorticity(self):
         """vorticity() (main.c:5786): F_VEL -> F_TMP, scaled by 1/h^3"""
         check(self.L.cup_vorticity(self.h))
+
+    def io_pack(self):
+        """io_dump's arrays (main.c:1525-1535): float32 chi [n,512], vorticity [n,512,3], Q [n,512]"""
+        fp = C.POINTER(C.c_float)
+        attr = np.zeros((self.nblk, BS3), np.float32)
+        vort = np.zeros((self.nblk, BS3, 3), np.float32)
+        q = np.zeros((self.nblk, BS3), np.float32)
+        check(self.L.cup_io_pack(self.h, attr.ctypes.data_as(fp), vort.ctypes.data_as(fp), q.ctypes.data_as(fp)))
+        return attr, vort, q
 
     def block_linf(self, f0=F_TMP):
         """-> (linf_all [nblk], linf_fluid [nblk]): mesh_tag_blk's norm, without / with k_gradchi's zeroing"""

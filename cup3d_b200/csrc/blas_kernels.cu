@@ -235,6 +235,49 @@ int block_linf(CupCtx *c, int f0, double *h_all, double *h_fluid) {
   return CUP_OK;
 }
 
+// io_dump's packing loop (main.c:1525-1535): float32 chi, interleaved vorticity, Q
+template <typename Real>
+__global__ void __launch_bounds__(256) k_io_pack(const Real *__restrict__ chi, const Real *__restrict__ w0,
+                                                 const Real *__restrict__ w1, const Real *__restrict__ w2,
+                                                 const Real *__restrict__ qq, long long n, float *__restrict__ attr,
+                                                 float *__restrict__ vort, float *__restrict__ q) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    attr[i] = (float)chi[i];
+    vort[3 * i] = (float)w0[i];
+    vort[3 * i + 1] = (float)w1[i];
+    vort[3 * i + 2] = (float)w2[i];
+    q[i] = (float)qq[i];
+  }
+}
+
+int io_pack(CupCtx *c, float *h_attr, float *h_vort, float *h_q) {
+  const long long n = c->nblk * 512;
+  if (!c->io_buf)
+    CUP_CUDA(cudaMalloc(&c->io_buf, (size_t)n * 5 * sizeof(float)));
+  float *attr = (float *)c->io_buf, *q = attr + n, *vort = attr + 2 * n;
+  const int g = (int)std::min<long long>((n + 255) / 256, (long long)c->num_sms * 8);
+  if (c->real_bytes == 8)
+    k_io_pack<double><<<g, 256, 0, c->stream>>>((const double *)c->state[CUP_F_CHI], (const double *)c->state[CUP_F_TMP],
+                                                (const double *)c->state[CUP_F_TMP + 1],
+                                                (const double *)c->state[CUP_F_TMP + 2],
+                                                (const double *)c->state[CUP_F_LHS], n, attr, vort, q);
+  else
+    k_io_pack<float><<<g, 256, 0, c->stream>>>((const float *)c->state[CUP_F_CHI], (const float *)c->state[CUP_F_TMP],
+                                               (const float *)c->state[CUP_F_TMP + 1],
+                                               (const float *)c->state[CUP_F_TMP + 2],
+                                               (const float *)c->state[CUP_F_LHS], n, attr, vort, q);
+  c->launches++;
+  CUP_CUDA(cudaGetLastError());
+  if (h_attr)
+    CUP_CUDA(cudaMemcpyAsync(h_attr, attr, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (h_q)
+    CUP_CUDA(cudaMemcpyAsync(h_q, q, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (h_vort)
+    CUP_CUDA(cudaMemcpyAsync(h_vort, vort, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CUP_CUDA(cudaStreamSynchronize(c->stream));
+  return CUP_OK;
+}
+
 int fetch_scalars(CupCtx *c, int first, int n) {
   CUP_CUDA(cudaMemcpyAsync(c->h_scal + first, c->d_scal + first, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost,
                            c->stream));

@@ -40,6 +40,8 @@ static int alloc_state(CupCtx *c) {
   cudaFree(c->tmp_out);
   cudaFree(c->p_old);
   cudaFree(c->tmp_stage);
+  cudaFree(c->io_buf);
+  c->io_buf = nullptr;
   c->tmp_in = c->tmp_out = c->p_old = c->tmp_stage = nullptr;
   // staging for host flat vectors: always room for doubles
   CUP_CUDA(cudaMalloc(&c->tmp_in, (size_t)c->nblk * 512 * 8));
@@ -137,6 +139,7 @@ int cup_destroy(CupCtx *c) {
   cudaFree(c->tmp_out);
   cudaFree(c->p_old);
   cudaFree(c->tmp_stage);
+  cudaFree(c->io_buf);
   cudaFree(c->d_W);
   cudaFree(c->d_hw);
   cudaFree(c->d_scal);
@@ -271,6 +274,16 @@ int cup_pois_solve(CupCtx *c, CupSolveInfo *info) { return pois_solve(c, info); 
 int cup_umax(CupCtx *c, double *out) { return umax(c, out); }
 int cup_advdiff(CupCtx *c) { return advdiff(c); }
 int cup_vorticity(CupCtx *c) { return vorticity(c); }
+int cup_io_pack(CupCtx *c, float *attr, float *vort, float *q) {
+  if (c->nblk == 0) {
+    set_error("cup_io_pack: no mesh uploaded");
+    return CUP_ERR_STATE;
+  }
+  // io_dump (main.c:1441-1442): vorticity(); qcrit();
+  CUP_TRY(vorticity(c));
+  CUP_TRY(stencil_run(c, CUP_ST_Q, nullptr, c->nblk));
+  return io_pack(c, attr, vort, q);
+}
 int cup_block_linf(CupCtx *c, int f0, double *linf_all, double *linf_fluid) {
   return block_linf(c, f0, linf_all, linf_fluid);
 }

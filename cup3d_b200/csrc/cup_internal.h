@@ -163,6 +163,7 @@ struct CupCtx {
   void *tma_cache = nullptr;    // tensor-map cache (smooth_tma.cu)
   bool no_flux_correction = false;  // st_mg on the leaves (stencil_apply(CUP_ST_MG)): k_mg has no flux faces
   void *obst = nullptr;         // cup::Obstacles (obstacle.cu)
+  void *io_buf = nullptr;       // io_dump packing: 5 floats per cell (allocated on first use)
   bool keep_tmp_udef = false;   // projection(): F_TMP already holds fish_tmpv()'s udef
 };
 
@@ -187,6 +188,7 @@ int wdot(CupCtx *c, const void *a, const void *b, int scal_idx);  // -> d_scal[i
 int fetch_scalars(CupCtx *c, int first, int n);                   // d_scal -> h_scal, synchronises
 int umax(CupCtx *c, double *out);                                 // sta_umax over all ranks
 int scale_blk3(CupCtx *c, void *a0, void *a1, void *a2);          // a_q[b] *= 1/h_b^3
+int io_pack(CupCtx *c, float *h_attr, float *h_vort, float *h_q);  // F_CHI, F_TMP, F_LHS -> float32 host arrays
 int block_linf(CupCtx *c, int f0, double *h_all, double *h_fluid);  // per-block |.|_inf of 3 components
 
 // solver.cu

@@ -182,6 +182,13 @@ int cup_vorticity(CupCtx *ctx);
  * alone and stays on the host (F_CHI is produced there by fish_build).  NULL = not wanted. */
 int cup_block_linf(CupCtx *ctx, int f0, double *linf_all, double *linf_fluid);
 
+/* io_dump's field part (main.c:1441-1442, :1525-1535): vorticity(); qcrit();
+ * then float32 packing on the device -- attr[nblk*512] = chi, vort[nblk*512][3] (interleaved),
+ * q[nblk*512] in block-index order, exactly the arrays io_write() receives.  5 floats per cell
+ * cross PCIe instead of 5 doubles.  F_TMP / F_LHS hold vorticity / Q afterwards, as in the
+ * reference.  NULL = not wanted.  Synchronous. */
+int cup_io_pack(CupCtx *ctx, float *attr, float *vort, float *q);
+
 /* One rank per GPU.  nccl_id = the 128 bytes of an ncclUniqueId created on
  * rank 0 and distributed by the caller (torch.distributed / MPI_Bcast). */
 int cup_comm_init(CupCtx *ctx, int rank, int nranks, const void *nccl_id, size_t id_bytes);

@@ -100,3 +100,24 @@ def test_vorticity_block_norms(built, name):
     assert np.max(np.abs(la - c.g["tag_linf_all"]) / c.g["tag_linf_all"]) < 1e-12
     assert np.max(np.abs(lf - c.g["tag_linf_fluid"])) < 1e-12 * np.max(c.g["tag_linf_all"])
     ctx.close()
+
+
+@pytest.mark.parametrize("name", STENCIL_CASES + ["amr2"])
+def test_io_pack(built, name):
+    """io_dump's field arrays (main.c:1441-1442, :1525-1535): vorticity(); qcrit(); float32 packing.
+    Expected = the reference's k_vort / k_q sweeps, scaled and converted exactly as the reference does."""
+    c = case(name)
+    ctx = make_ctx(c)
+    s0 = c.state0()
+    ctx.state_h2d(s0)
+    attr, vort, q = ctx.io_pack()
+    h = c.rb[:, 0]
+    fac = (1.0 / (h * h * h))[:, None, None]
+    ev = np.moveaxis(c.g["st_vort"] * fac, 1, 2).astype(np.float32)       # [n,512,3]
+    assert np.array_equal(attr, s0[:, 0].astype(np.float32))
+    # float32 of two doubles that agree to 1e-12 can differ by one float ulp at a rounding boundary
+    assert np.max(np.abs(vort - ev)) <= 2e-7 * np.max(np.abs(ev))
+    assert np.mean(vort != ev) < 1e-3
+    eq = c.g["st_q"][:, 0].astype(np.float32)
+    assert np.max(np.abs(q - eq)) <= 2e-7 * np.max(np.abs(eq)) and np.mean(q != eq) < 1e-3
+    ctx.close()
