@@ -13,4 +13,7 @@ int tma_slab_maps(CupCtx *c, const void *leaf, CUtensorMap out[2]);
 template <typename Real>
 int advdiff_tma_launch(CupCtx *c, LevelView lv, const int *d_sub, int nsub, const void *d_hblk, double dtnu_dt,
                        double dtnu_nu, double fac_a, double fac_d);
+// k_prhs with TMA-staged fields and ghost faces (prhs_tma.cu); uniform leaf level, fac = h^2/(2 dt)
+template <typename Real>
+int prhs_tma_launch(CupCtx *c, LevelView lv, double fac);
 }  // namespace cup

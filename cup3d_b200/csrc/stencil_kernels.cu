@@ -469,6 +469,16 @@ bool adv_tma() {
   return v != 0;
 }
 
+// CUP_PRHS_IMPL=tma selects the TMA-staged k_prhs (prhs_tma.cu); default: plain loads
+bool prhs_tma() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("CUP_PRHS_IMPL");
+    v = (e && !strcmp(e, "tma")) ? 1 : 0;
+  }
+  return v != 0;
+}
+
 const Level *leaf_level(CupCtx *c) {
   int top = c->top;
   while (top > 0 && c->lv[top].gnact == 0)
@@ -614,6 +624,8 @@ int stencil_t(CupCtx *c, CupStencilId id, const int *d_sub, long long nsub) {
   }
   case CUP_ST_PRHS: {
     const double fac = 0.5 * hd * hd / dt;
+    if (prhs_tma())
+      return prhs_tma_launch<Real>(c, lv, fac);
     static bool carve = false;  // 8 CTAs x 21.5 KB need the large shared-memory configuration
     if (!carve) {
       carve = true;
