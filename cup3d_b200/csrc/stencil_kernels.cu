@@ -469,12 +469,12 @@ bool adv_tma() {
   return v != 0;
 }
 
-// CUP_PRHS_IMPL=tma selects the TMA-staged k_prhs (prhs_tma.cu); default: plain loads
+// k_prhs: TMA-staged (prhs_tma.cu) by default; CUP_PRHS_IMPL=ldg selects the plain-load kernel
 bool prhs_tma() {
   static int v = -1;
   if (v < 0) {
     const char *e = getenv("CUP_PRHS_IMPL");
-    v = (e && !strcmp(e, "tma")) ? 1 : 0;
+    v = !(e && !strcmp(e, "ldg"));
   }
   return v != 0;
 }
@@ -624,7 +624,8 @@ int stencil_t(CupCtx *c, CupStencilId id, const int *d_sub, long long nsub) {
   }
   case CUP_ST_PRHS: {
     const double fac = 0.5 * hd * hd / dt;
-    if (prhs_tma())
+    // (its received-face path has not run on two GPUs yet: multi-rank contexts keep the plain loads)
+    if (prhs_tma() && c->nranks == 1)
       return prhs_tma_launch<Real>(c, lv, fac);
     static bool carve = false;  // 8 CTAs x 21.5 KB need the large shared-memory configuration
     if (!carve) {
