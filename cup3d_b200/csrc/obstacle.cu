@@ -269,18 +269,23 @@ int obstacle_upload(CupCtx *c, int body, int nob, const int *blk, const double *
     geo[4 * o + 3] = k.origin[2];
   }
   if (nob > b.cap) {
+    b.cap = 0;  // a failed allocation below must not leave a stale capacity behind
+    b.nob = 0;
     CUP_TRY(grow((void **)&b.d_blk, (size_t)nob * sizeof(int)));
     CUP_TRY(grow((void **)&b.d_geo, (size_t)nob * 4 * sizeof(double)));
     CUP_TRY(grow(&b.d_chi, (size_t)nob * 512 * c->real_bytes));
     CUP_TRY(grow(&b.d_udef, (size_t)nob * 1536 * c->real_bytes));
     b.cap = nob;
+    b.nob = nob;
   }
   const size_t need = (size_t)nob * 2048;
   if (need > ob->stage_cap) {
+    ob->stage_cap = 0;
     CUP_TRY(grow((void **)&ob->d_stage, need * sizeof(double)));
     ob->stage_cap = need;
   }
   if ((size_t)nob * CUP_M_N > ob->part_cap) {
+    ob->part_cap = 0;
     CUP_TRY(grow((void **)&ob->d_part, (size_t)nob * CUP_M_N * sizeof(double)));
     ob->part_cap = (size_t)nob * CUP_M_N;
   }
