@@ -1,0 +1,183 @@
+"""GPU: size-independent properties at the sizes BASELINE.json names (512^3 for the Poisson V-cycle,
+256^3 for the sweeps of the time step), where no CPU golden exists.  Every property was first
+checked on the reference itself at 64^3 / 128^3 (it holds there to rounding: linearity 2e-16,
+symmetry 7e-15, adjointness 4e-17, k_divp vs k_lhs 5e-15), so a violation here is a defect of the
+device path, not of the mathematics:
+
+  * the V-cycle is a linear map of its right-hand side (zero initial guess, linear smoother,
+    restriction, prolongation and bottom solve): M(2a - 3b) = 2 M(a) - 3 M(b)
+  * pois_op without mean constraint annihilates constants exactly and is symmetric
+  * x += M(b - A x) contracts the residual by a grid-independent factor per cycle; at 128^3 the
+    history must equal the reference's own known answers (generated from
+    /root/reference during the survey)
+  * k_divp and k_lhs are the same stencil with different summation order
+  * with free-slip walls the central divergence of k_prhs and the central gradient of k_gradp are
+    negative adjoints of each other: sum p div(u) = - sum u . grad(p)
+  * k_advdiff of a velocity that is constant on the grid (values exact in binary) is exactly zero
+    away from the walls
+"""
+import numpy as np
+import pytest
+
+from util import relerr
+from cup3d_b200 import capi, mesh
+
+pytestmark = pytest.mark.gpu
+
+# reference-generated known answers: ||r||/||b|| after cycles 1..5, cosine rhs
+HIST_128 = [1.786780e+00, 2.010526e-01, 3.573689e-02, 5.819499e-03, 1.004914e-03]
+
+
+def uniform_ctx(level, mc=2):
+    import cup3d_b200
+    ib, rb = mesh.uniform_blocks(level)
+    ctx = cup3d_b200.Context(0, 8)
+    ctx.mesh_upload(ib, rb, (1, 1, 1), level + 1)
+    ctx.set_params(dt=1e-3, nu=1e-3, uinf=(0.0, 0.0, 0.0), step=5, mean_constraint=mc, ptol=1e-6, ptol_rel=1e-4)
+    return ctx, ib, rb
+
+
+def cosine_rhs(ib, rb):
+    X, Y, Z = mesh.cell_centers(ib, rb)
+    h = rb[0, 0]
+    return np.ascontiguousarray((h ** 3 * np.cos(np.pi * X) * np.cos(2 * np.pi * Y) * np.cos(3 * np.pi * Z))
+                                .reshape(len(ib), 512))
+
+
+def point_sources(ib, rb):
+    """bench.py's right-hand side: +1 / -1 in the first cell of the blocks at (1/4,1/4,1/4), (3/4,3/4,3/4)"""
+    a = np.zeros((len(ib), 512))
+    for p, v in ((0.25, 1.0), (0.75, -1.0)):
+        i = int(np.argmin((rb[:, 1] - p) ** 2 + (rb[:, 2] - p) ** 2 + (rb[:, 3] - p) ** 2))
+        a[i, 0] = v
+    return a
+
+
+def history(ctx, b, cycles):
+    x = np.zeros_like(b)
+    nb = np.sqrt(np.vdot(b, b))
+    hist = []
+    for _ in range(cycles):
+        x += ctx.mg_vcycle(b - ctx.pois_op(x))
+        r = b - ctx.pois_op(x)
+        hist.append(float(np.sqrt(np.vdot(r, r)) / nb))
+    return hist
+
+
+def test_vcycle_history_128_known_answers(built):
+    ctx, ib, rb = uniform_ctx(4)
+    hist = history(ctx, cosine_rhs(ib, rb), 5)
+    ctx.close()
+    assert np.allclose(hist, HIST_128, rtol=2e-6, atol=0), hist
+
+
+@pytest.fixture(scope="module")
+def big(built):
+    ctx, ib, rb = uniform_ctx(6)          # 512^3: 262144 blocks, 7 multigrid levels
+    yield ctx, ib, rb
+    ctx.close()
+
+
+def test_vcycle_linearity_512(big):
+    ctx, ib, rb = big
+    ctx.set_params(mean_constraint=2)
+    a, b = point_sources(ib, rb), cosine_rhs(ib, rb)
+    Ma = ctx.mg_vcycle(a)
+    Mb = ctx.mg_vcycle(b)
+    c = 2.0 * a - 3.0 * b
+    Mc = ctx.mg_vcycle(c)
+    e = relerr(Mc, 2.0 * Ma - 3.0 * Mb)
+    assert e < 1e-10, e
+    assert np.all(np.isfinite(Ma)) and np.abs(Ma).max() > 0 and np.abs(Mb).max() > 0
+
+
+def test_pois_op_nullspace_and_symmetry_512(big):
+    ctx, ib, rb = big
+    ctx.set_params(mean_constraint=0)
+    n = len(ib)
+    one = np.ones((n, 512))
+    assert np.abs(ctx.pois_op(one)).max() <= 1e-13
+    rng = np.random.default_rng(11)
+    u = rng.standard_normal((n, 512))
+    X, Y, Z = mesh.cell_centers(ib, rb)
+    v = np.ascontiguousarray(np.sin(3 * X + Y).reshape(n, 512))
+    del X, Y, Z
+    Au, Av = ctx.pois_op(u), ctx.pois_op(v)
+    s1, s2 = float(np.vdot(u, Av)), float(np.vdot(Au, v))
+    assert abs(s1 - s2) <= 1e-10 * max(abs(s1), abs(s2)), (s1, s2)
+    ctx.set_params(mean_constraint=2)
+
+
+def test_vcycle_contraction_512(big):
+    ctx, ib, rb = big
+    ctx.set_params(mean_constraint=2)
+    hist = history(ctx, cosine_rhs(ib, rb), 4)
+    # reference: 0.117 / 0.179 / 0.166 at 64^3, 0.113 / 0.178 / 0.163 at 128^3
+    for k in range(1, 4):
+        assert hist[k] < 0.3 * hist[k - 1], hist
+
+
+@pytest.fixture(scope="module")
+def mid(built):
+    ctx, ib, rb = uniform_ctx(5, mc=0)    # 256^3: 32768 blocks
+    yield ctx, ib, rb
+    ctx.close()
+
+
+def sweep_state(ib, rb):
+    n = len(ib)
+    X, Y, Z = mesh.cell_centers(ib, rb)
+    rng = np.random.default_rng(5)
+    st = np.zeros((n, 9, 512))
+    st[:, 1] = (np.cos(np.pi * X) * np.cos(np.pi * Y) * np.cos(2 * np.pi * Z)).reshape(n, 512)
+    st[:, 1] += 0.01 * rng.standard_normal((n, 512))
+    st[:, 2] = (np.sin(2 * np.pi * X) * np.cos(2 * np.pi * Y)).reshape(n, 512)
+    st[:, 3] = (-np.cos(2 * np.pi * X) * np.sin(2 * np.pi * Y)).reshape(n, 512)
+    st[:, 4] = (0.1 * np.sin(2 * np.pi * Z)).reshape(n, 512)
+    st[:, 2:5] += 0.01 * rng.standard_normal((n, 3, 512))
+    return st
+
+
+def test_divp_is_lhs_and_div_grad_adjoint_256(mid):
+    ctx, ib, rb = mid
+    st = sweep_state(ib, rb)
+    out = np.zeros_like(st)
+    h, dt = rb[0, 0], 1e-3
+    ctx.state_h2d(st)
+    ctx.stencil_apply(capi.ST_DIVP)
+    ctx.state_d2h(out, 5, 1)
+    divp = out[:, 5].copy()
+    ctx.stencil_apply(capi.ST_LHS)
+    ctx.state_d2h(out, 8, 1)
+    assert relerr(divp, out[:, 8]) < 1e-12
+    # <p, D u> = -<G p, u> with zero-gradient p and free-slip u at the walls (chi = 0, udef = 0)
+    ctx.state_h2d(st)
+    ctx.stencil_apply(capi.ST_PRHS)
+    ctx.state_d2h(out, 8, 1)
+    D = out[:, 8] / (0.5 * h * h / dt)
+    ctx.state_h2d(st)
+    ctx.stencil_apply(capi.ST_GRADP)
+    ctx.state_d2h(out, 5, 3)
+    G = out[:, 5:8] / (-0.5 * dt * h * h)
+    s1 = float(np.vdot(st[:, 1], D))
+    s2 = float(np.vdot(st[:, 2:5], G))
+    scale = float(np.abs(st[:, 1] * D).sum())
+    assert abs(s1 + s2) <= 1e-11 * scale, (s1, s2, scale)
+
+
+def test_advdiff_of_constant_flow_256(mid):
+    ctx, ib, rb = mid
+    n = len(ib)
+    st = np.zeros((n, 9, 512))
+    for q, c in enumerate((0.5, 0.25, -0.125)):   # exact in binary: every stencil product is exact
+        st[:, 2 + q] = c
+    ctx.state_h2d(st)
+    ctx.stencil_apply(capi.ST_ADVDIFF)
+    out = np.zeros_like(st)
+    ctx.state_d2h(out, 5, 3)
+    nb = 1 << int(ib[0, 0])       # blocks per direction on this (single) level
+    inner = np.all((ib[:, 1:4] > 0) & (ib[:, 1:4] < nb - 1), axis=1)
+    assert inner.sum() == (nb - 2) ** 3
+    assert not np.any(out[inner, 5:8])                      # exactly zero away from the walls
+    wall = out[~inner, 5:8]
+    assert np.all(np.isfinite(wall)) and np.any(wall != 0)  # the free-slip sign flip shears the flow there
