@@ -120,7 +120,15 @@ def cpu_reference_run(level, warmup, steps, timeout=900):
     """time the reference's CPU V-cycle in a subprocess (its state is process-global)"""
     cmd = [sys.executable, os.path.join(ROOT, "oracle", "cpu_baseline.py"), "--level", str(level), "--warmup",
            str(warmup), "--steps", str(steps)]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    env = dict(os.environ)
+    # torchrun exports OMP_NUM_THREADS=1 to every worker when the user has not set it; the CPU arm must
+    # use all the host threads it can (it picks the best count itself), so that default is dropped.
+    # CUP_REF_THREADS pins a count explicitly.
+    if "TORCHELASTIC_RUN_ID" in env and env.get("OMP_NUM_THREADS") == "1":
+        env.pop("OMP_NUM_THREADS")
+    if env.get("CUP_REF_THREADS"):
+        env["OMP_NUM_THREADS"] = env["CUP_REF_THREADS"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout, env=env)
     for line in r.stdout.splitlines()[::-1]:
         if line.startswith("{"):
             return json.loads(line)
