@@ -7,7 +7,8 @@ import pytest
 
 from util import ALL_CASES, STENCIL_CASES, case, relerr
 
-ST = {"lhs": (0, 8, 1), "advdiff": (2, 5, 3), "prhs": (3, 8, 1), "divp": (4, 5, 1), "gradp": (5, 5, 3)}
+ST = {"lhs": (0, 8, 1), "advdiff": (2, 5, 3), "prhs": (3, 8, 1), "divp": (4, 5, 1), "gradp": (5, 5, 3),
+      "vort": (6, 5, 3), "q": (7, 8, 1)}
 
 
 @pytest.fixture(scope="module")
