@@ -64,8 +64,8 @@ typedef enum {
   CUP_ST_PRHS = 3,    /* st_prhs    F_VEL,F_TMP,F_CHI -> F_LHS */
   CUP_ST_DIVP = 4,    /* st_divp    F_PRES -> F_TMP[0] */
   CUP_ST_GRADP = 5,   /* st_gradp   F_PRES -> F_TMP[0..2] */
-  CUP_ST_VORT = 6,    /* st_vort    F_VEL  -> F_TMP[0..2] (h^3-weighted vorticity; single-level meshes) */
-  CUP_ST_Q = 7        /* st_q       F_VEL  -> F_LHS (Q criterion; single-level meshes) */
+  CUP_ST_VORT = 6,    /* st_vort    F_VEL  -> F_TMP[0..2] (h^3-weighted vorticity, with its flux correction) */
+  CUP_ST_Q = 7        /* st_q       F_VEL  -> F_LHS (Q criterion) */
 } CupStencilId;
 
 /* run-time scalars the kernels read from the reference's sim/sta globals */
