@@ -104,7 +104,9 @@ def test_pois_op_nullspace_and_symmetry_512(big):
     del X, Y, Z
     Au, Av = ctx.pois_op(u), ctx.pois_op(v)
     s1, s2 = float(np.vdot(u, Av)), float(np.vdot(Au, v))
-    assert abs(s1 - s2) <= 1e-10 * max(abs(s1), abs(s2)), (s1, s2)
+    # the sums cancel heavily (random u against a smooth v): compare on the scale of their terms
+    scale = float(np.abs(u * Av).sum())
+    assert abs(s1 - s2) <= 1e-11 * scale, (s1, s2, scale)
     ctx.set_params(mean_constraint=2)
 
 

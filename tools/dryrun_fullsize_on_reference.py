@@ -5,7 +5,8 @@ tolerance of that file is exercised without a GPU.  One test per process (the re
 in file-statics).  TEST INFRASTRUCTURE; needs oracle/_ref (make -C oracle ref).
 
     python tools/dryrun_fullsize_on_reference.py            # all tests at 64^3 (128^3 for the known answers)
-    python tools/dryrun_fullsize_on_reference.py TEST LEVEL
+    python tools/dryrun_fullsize_on_reference.py TEST LEVEL  # e.g. test_vcycle_linearity_512 6 = the true
+                                                             # size (about 25 GB of host memory, minutes)
 """
 import os
 import subprocess
