@@ -158,6 +158,42 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def sweep_rates(ctx, torch, capi, N, b, z, stream):
+    """ms per sweep (CUDA events on the library's stream, 5 launches after 2 warm-ups) and GB/s at the
+    algorithmic traffic of SURVEY 8(d); the state is filled with uniform random numbers on the device"""
+    import ctypes
+    rt = ctypes.cdll.LoadLibrary("libcudart.so.12")
+    rng = torch.Generator(device="cuda").manual_seed(1)
+    t = torch.empty(N, dtype=torch.float64, device="cuda")
+    for f in range(9):
+        t.uniform_(-1, 1, generator=rng)
+        torch.cuda.synchronize()
+        rc = rt.cudaMemcpy(ctypes.c_void_p(ctx.state_dev(f)), ctypes.c_void_p(t.data_ptr()), ctypes.c_size_t(N * 8), 3)
+        if rc != 0:
+            raise RuntimeError("cudaMemcpy into the state failed: %d" % rc)
+    del t
+    ctx.set_params(dt=1e-3, nu=1e-3, uinf=(0.1, 0.0, 0.0), step=5)
+    reals = {"advdiff": 9, "prhs": 8, "divp": 2, "gradp": 4, "pois_op": 2}
+    calls = {"advdiff": lambda: ctx.stencil_apply(capi.ST_ADVDIFF), "prhs": lambda: ctx.stencil_apply(capi.ST_PRHS),
+             "divp": lambda: ctx.stencil_apply(capi.ST_DIVP), "gradp": lambda: ctx.stencil_apply(capi.ST_GRADP),
+             "pois_op": lambda: ctx.pois_op_dev(b, z)}
+    out = {}
+    for name, fn in calls.items():
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(5):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        out[name] = {"ms": round(ms, 4), "Gcells_per_s": round(N / ms / 1e6, 2),
+                     "GBs_at_algorithmic": round(N * 8 * reals[name] / ms / 1e6, 1)}
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
@@ -270,6 +306,14 @@ def run_ours(args, rank, world, local_rank):
         except Exception as ex:  # the oracle always exists; report why it did not run
             cpu = {"value": None, "unit": "cell-updates/s", "cores": 0, "kind": "reference",
                    "sample": "failed: %s" % str(ex)[:200]}
+    # secondary numbers SURVEY 8(d) asks for: per-sweep rates of the time-step stencils and of pois_op on
+    # the same 512^3 grid (after everything above was measured; a failure here cannot touch the line)
+    sweeps = None
+    if world == 1 and not args.no_sweeps:
+        try:
+            sweeps = sweep_rates(ctx, torch, capi, N, b, z, stream)
+        except Exception as ex:
+            sweeps = {"error": str(ex)[:200]}
     line = {
         "metric": "poisson_vcycle_cell_updates_per_s", "value": value, "unit": "cell-updates/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -292,9 +336,13 @@ def run_ours(args, rank, world, local_rank):
                 "d2h_bytes_per_step": gcells * 8, "ms_per_step": t_e2e * 1e3},
         "gpu_launches": launches,
         "clocks": clocks,
+        "sweeps": sweeps,
     }
     print(json.dumps(line), flush=True)
-    ctx.close()
+    try:
+        ctx.close()
+    except Exception:
+        pass
     if dist is not None:
         dist.destroy_process_group()
 
@@ -308,6 +356,7 @@ def main():
     ap.add_argument("--level", type=int, default=6, help="uniform level: grid = (8<<level)^3; 6 = 512^3")
     ap.add_argument("--cpu-level", type=int, default=5, help="grid of the bounded CPU sample (5 = 256^3)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sweeps", action="store_true", help="skip the per-sweep secondary timings")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
