@@ -4,15 +4,15 @@ size: the context of the test module is replaced by a reference-backed stand-in,
 tolerance of that file is exercised without a GPU.  One test per process (the reference keeps its mesh
 in file-statics).  TEST INFRASTRUCTURE; needs oracle/_ref (make -C oracle ref).
 
-    python tools/dryrun_fullsize_on_reference.py            # all tests at 64^3 (128^3 for the known answers)
-    python tools/dryrun_fullsize_on_reference.py TEST LEVEL  # e.g. test_vcycle_linearity_512 6 = the true
+    python tests/dryrun_fullsize_on_reference.py            # all tests at 64^3 (128^3 for the known answers)
+    python tests/dryrun_fullsize_on_reference.py TEST LEVEL  # e.g. test_vcycle_linearity_512 6 = the true
                                                              # size (about 25 GB of host memory, minutes)
 """
 import os
 import subprocess
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tests/.. = repo root
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")]
 
 PLAN = [("test_vcycle_history_128_known_answers", 4), ("test_vcycle_linearity_512", 3),
