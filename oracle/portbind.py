@@ -31,6 +31,8 @@ def lib():
         L.orc_advdiff.argtypes = [C.c_void_p, dp, C.c_double, C.c_double, dp]
         L.orc_projection.argtypes = [C.c_void_p, dp, C.c_double, C.c_double, dp, C.c_int, C.c_int, C.c_double,
                                      C.c_double]
+        L.orc_projection_keep.argtypes = [C.c_void_p, dp, C.c_double, C.c_double, dp, C.c_int, C.c_int, C.c_double,
+                                          C.c_double, C.c_int]
         L.orc_time_vcycle.restype = C.c_double
         L.orc_time_vcycle.argtypes = [C.c_void_p, dp, dp, C.c_int, C.c_int]
         _lib = L
@@ -92,9 +94,10 @@ class Oracle:
         u = np.asarray(uinf, np.float64)
         lib().orc_advdiff(self.h, _p(state), dt, nu, _p(u))
 
-    def projection(self, state, dt, nu, uinf, step, mc, ptol, ptol_rel):
+    def projection(self, state, dt, nu, uinf, step, mc, ptol, ptol_rel, keep_tmp=False):
+        """keep_tmp: F_TMP already holds fish_tmpv()'s udef (it is not zeroed first)"""
         u = np.asarray(uinf, np.float64)
-        return lib().orc_projection(self.h, _p(state), dt, nu, _p(u), step, mc, ptol, ptol_rel)
+        return lib().orc_projection_keep(self.h, _p(state), dt, nu, _p(u), step, mc, ptol, ptol_rel, int(keep_tmp))
 
     def time_vcycle(self, x, warmup, n):
         x = np.ascontiguousarray(x, np.float64)

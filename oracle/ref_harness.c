@@ -253,3 +253,37 @@ API void ref_fish_mom(int k, double *M) {
       M[q] += o->mom[q];
   }
 }
+
+/* ---- the host halves of fish_vel / fish_pen, for a caller whose per-cell halves run elsewhere
+ * (tests/coupled.py: the integration recipe of INTEGRATION.md, step by step) ---- */
+
+/* what fish_vel does with the reduced moments M (main.c:5328-5340): hand them to the 6x6
+ * rigid-body solve of fish k */
+API void ref_fish_solve_from(int k, const double *M) {
+  struct Fish *f = &sta.fish[k];
+  int d, q;
+  f->pen_m = M[M_GfX];
+  for (d = 0; d < 3; d++) {
+    f->pen_cm[d] = M[M_GpX + d];
+    f->pen_lmom[d] = M[M_GuX + d];
+    f->pen_amom[d] = M[M_GaX + d];
+  }
+  for (q = 0; q < 6; q++)
+    f->pen_j[q] = M[M_Gj0 + q];
+  fish_solve(f);
+}
+/* fish_pen = fish_hit (collisions, host) + the per-block penalisation loop (main.c:5651-5662) */
+API void ref_fish_hit(void) {
+  if (sim.nfish > 0)
+    fish_hit();
+}
+API void ref_fish_pen_blocks(void) {
+  long long i;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (i = 0; i < sta.nblk; ++i) {
+    int k;
+    for (k = 0; k < sim.nfish; k++)
+      fish_pen_blk(i, &sta.fish[k]);
+  }
+}
+API int ref_mesh_changed(void) { return sta.mesh_changed; }

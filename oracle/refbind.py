@@ -223,3 +223,17 @@ def fish_mom(k):
     M = np.zeros(int(_lib.ref_m_n()))
     _lib.ref_fish_mom(k, _p(M))
     return M
+
+
+def fish_solve_from(k, M):
+    """the tail of fish_vel for fish k: moments -> fish_solve"""
+    M = np.ascontiguousarray(M, np.float64)
+    _lib.ref_fish_solve_from(k, _p(M))
+
+
+def fish_hit():
+    _lib.ref_fish_hit()
+
+
+def fish_pen_blocks():
+    _lib.ref_fish_pen_blocks()
