@@ -116,10 +116,23 @@ def point_sources(ib, rb):
     return out
 
 
-def cpu_reference_run(level, warmup, steps, timeout=900):
-    """time the reference's CPU V-cycle in a subprocess (its state is process-global)"""
+def free_ram_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                return int(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
+def cpu_reference_run(level, warmup, steps, timeout=1500, dump=None):
+    """time the reference's CPU V-cycle in a subprocess (its state is process-global); dump: also write the
+    V-cycle output of the point-source right-hand side to that .npy (the parity check reads it)"""
     cmd = [sys.executable, os.path.join(ROOT, "oracle", "cpu_baseline.py"), "--level", str(level), "--warmup",
            str(warmup), "--steps", str(steps)]
+    if dump:
+        cmd += ["--dump", dump]
     env = dict(os.environ)
     # torchrun exports OMP_NUM_THREADS=1 to every worker when the user has not set it; the CPU arm must
     # use all the host threads it can (it picks the best count itself), so that default is dropped.
@@ -138,8 +151,12 @@ def cpu_reference_run(level, warmup, steps, timeout=900):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    lvl = args.cpu_level
-    res = cpu_reference_run(lvl, args.warmup, args.steps)
+    # the configuration itself (512^3: ~20 GB of host RAM, about a minute of the reference's mesh_init) when the
+    # host has the memory, else a bounded 256^3 sample of the same workload; --cpu-level forces one
+    lvl = args.cpu_level if args.cpu_level >= 0 else (args.level if free_ram_gb() >= 48 else 5)
+    steps = min(args.steps, 10) if lvl >= 6 else args.steps
+    res = cpu_reference_run(lvl, min(args.warmup, 2), steps)
+    args = argparse.Namespace(**dict(vars(args), steps=steps))
     cells = (8 << lvl) ** 3
     line = {
         "impl": "reference", "metric": "poisson_vcycle_cell_updates_per_s", "value": res["cell_updates_per_s"],
@@ -147,7 +164,9 @@ def run_reference(args, rank, world):
         "ms_per_step": res["ms_per_cycle"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "512^3 uniform Poisson V-cycle (bpd 1, levelStart 6, levelMax 7), fp64, point-source "
-                               "pair; CPU arm timed on a bounded %d^3 sample of the same workload" % (8 << lvl)},
+                               "pair; CPU arm timed on %s" % ("the full 512^3 grid" if lvl >= 6 else
+                                                              "a bounded %d^3 sample of the same workload" % (8 << lvl)),
+                   "cpu_grid": 8 << lvl, "same_config": lvl >= 6},
         "cpu_baseline": {"value": res["cell_updates_per_s"], "unit": "cell-updates/s", "cores": res["threads"],
                          "kind": res["kind"], "sample": "%d V-cycles of the %d^3 grid (%d cells), %s" %
                          (args.steps, 8 << lvl, cells, res["what"])},
@@ -194,6 +213,67 @@ def sweep_rates(ctx, torch, capi, N, b, z, stream):
     return out
 
 
+def parity_vs_reference(ctx, torch, dist, capi, mesh, args, rank, world):
+    """The SAME point-source V-cycle on the grid of the CPU sample (256^3), on all N ranks, against the
+    reference run live on the host (oracle/_ref in a subprocess on rank 0): max |z - z_ref| / max |z_ref|.
+    This is the driver-visible correctness evidence for every N (decomposition may only change rounding).
+    -> (parity dict, cpu_baseline dict or None)"""
+    import tempfile
+    import numpy as np
+    Lp = args.cpu_level if args.cpu_level >= 0 else 5
+    gib, grb = mesh.uniform_blocks(Lp)
+    owner = capi.split_owner(len(gib), world)
+    mine = np.nonzero(owner == rank)[0]
+    cpu, zref, err = None, None, None
+    if rank == 0:
+        d = tempfile.mkdtemp(prefix="cup_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        path = os.path.join(d, "zref.npy")
+        try:
+            full = world == 1 and not args.no_cpu
+            r = cpu_reference_run(Lp, 1, 3 if full else 1, dump=path)
+            zref = np.load(path)
+            if full:
+                cpu = {"value": r["cell_updates_per_s"], "unit": "cell-updates/s", "cores": r["threads"],
+                       "kind": r["kind"],
+                       "sample": "3 V-cycles of a %d^3 grid (same block-structured workload, bounded), %s" %
+                                 (8 << Lp, r["what"])}
+        except Exception as ex:
+            err = str(ex)[:300]
+        finally:
+            import shutil
+            shutil.rmtree(d, ignore_errors=True)
+    ok = torch.tensor([0 if (rank == 0 and zref is None) else 1], device="cuda")
+    if dist is not None:
+        dist.broadcast(ok, src=0)
+    if int(ok.item()) == 0:
+        return {"rel_err": None, "error": err or "reference run failed"}, cpu
+    zr = torch.empty(len(gib) * 512, dtype=torch.float64, device="cuda")
+    if rank == 0:
+        zr.copy_(torch.from_numpy(zref.reshape(-1)))
+    if dist is not None:
+        dist.broadcast(zr, src=0)
+    ctx.mesh_upload(gib[mine], grb[mine], (1, 1, 1), Lp + 1)
+    ctx.set_params(mean_constraint=2)
+    n = len(mine)
+    b = torch.zeros(n * 512, dtype=torch.float64, device="cuda")
+    for g, val in zip(point_sources(gib, grb), (1.0, -1.0)):
+        if owner[g] == rank:
+            b[int(g - mine[0]) * 512] = val
+    z = torch.empty_like(b)
+    for _ in range(2):  # the second call replays the captured CUDA graph: both paths must agree with the reference
+        ctx.mg_vcycle_dev(b, z)
+        torch.cuda.synchronize()
+        ctx.synchronize()
+    lo = int(mine[0]) * 512
+    diff = (z - zr[lo:lo + n * 512]).abs().max().reshape(1)
+    if dist is not None:
+        dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+    ref_max = float(zr.abs().max().item())
+    rel = float(diff.item()) / ref_max
+    return {"rel_err": rel, "grid": 8 << Lp, "tolerance": 1e-10, "ref_max": ref_max,
+            "against": "oracle/_ref (unmodified reference main.c) run live on the host, same RHS"}, cpu
+
+
 def run_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
@@ -218,6 +298,9 @@ def run_ours(args, rank, world, local_rank):
         box = [capi.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         ctx.comm_init(rank, world, box[0])
+    parity, cpu = ({"rel_err": None, "error": "skipped (--no-parity)"}, None)
+    if not args.no_parity:
+        parity, cpu = parity_vs_reference(ctx, torch, dist, capi, mesh, args, rank, world)
     ctx.mesh_upload(ib, rb, (1, 1, 1), L + 1)
     ctx.set_params(mean_constraint=2)
     n = len(ib)
@@ -269,6 +352,16 @@ def run_ours(args, rank, world, local_rank):
     sm_ms = ctx.time_smooth(L, 40)
     clocks = clk.stop()
     checksum = float(z.abs().sum().item())
+    # result fingerprint, comparable across N by the driver: pois_dot(z, z) over all ranks and four fixed cells
+    zz = ctx.pois_dot_dev(z, z)
+    G = len(gib)
+    samp = torch.zeros(4, dtype=torch.float64, device="cuda")
+    for k, g in enumerate((0, G // 3, G // 2 + 17, G - 1)):
+        if owner[g] == rank:
+            samp[k] = z[int(g - mine[0]) * 512 + 77]
+    if dist is not None:
+        dist.all_reduce(samp)
+    fingerprint = {"pois_dot_zz": zz, "cells": [float(v) for v in samp.tolist()]}
 
     # end to end through the host-pointer C ABI: pinned host in/out, H2D + V-cycle + D2H per step
     hb = torch.zeros(N, dtype=torch.float64).pin_memory()
@@ -295,17 +388,6 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = measured_peak()
     smooth_gbs = N * B_PER_CELL_SMOOTH / (sm_ms * 1e-3) / 1e9
     traffic = ncu_traffic()
-    cpu = None
-    if not args.no_cpu and world == 1:
-        try:
-            r = cpu_reference_run(args.cpu_level, 1, 3)
-            cpu = {"value": r["cell_updates_per_s"], "unit": "cell-updates/s", "cores": r["threads"],
-                   "kind": r["kind"],
-                   "sample": "3 V-cycles of a %d^3 grid (same block-structured workload, bounded), %s" %
-                             (8 << args.cpu_level, r["what"])}
-        except Exception as ex:  # the oracle always exists; report why it did not run
-            cpu = {"value": None, "unit": "cell-updates/s", "cores": 0, "kind": "reference",
-                   "sample": "failed: %s" % str(ex)[:200]}
     # secondary numbers SURVEY 8(d) asks for: per-sweep rates of the time-step stencils and of pois_op on
     # the same 512^3 grid (after everything above was measured; a failure here cannot touch the line)
     sweeps = None
@@ -325,12 +407,19 @@ def run_ours(args, rank, world, local_rank):
                    "parallelism": "%d rank(s), one per GPU, contiguous Hilbert ranges of the block list; ghost faces "
                                   "pushed into peer windows over NVLink by the sweep kernels (NCCL for setup and "
                                   "allreduce)" % world},
-        "hbm_gbs_vcycle": cells * B_PER_CELL_VCYCLE * args.steps / (ms * 1e-3) / 1e9,
-        "roofline": {"bound": "hbm", "kernel": "k_smooth_tma<double> (finest-level smoother)", "achieved": smooth_gbs,
-                     "peak": peak, "unit": "GB/s", "frac": smooth_gbs / peak,
-                     "traffic": traffic["bytes_per_launch"] if traffic else None, "peak_source": peak_src,
+        "hbm_gbs_vcycle_per_gpu": cells * B_PER_CELL_VCYCLE * args.steps / (ms * 1e-3) / 1e9 / world,
+        "roofline": {"bound": "hbm", "kernel": "k_smooth_tma<double> (finest-level smoother, this rank's blocks)",
+                     "achieved": smooth_gbs, "peak": peak, "unit": "GB/s", "frac": smooth_gbs / peak,
+                     "traffic": (traffic["bytes_per_launch"] * (N / float(traffic.get("cells_per_launch", 512 ** 3)))
+                                 if traffic else None),
+                     "traffic_source": ("ncu --set full capture at N=1 (profiles/), scaled by this rank's share of "
+                                        "the cells" if traffic else None),
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": N * B_PER_CELL_SMOOTH, "ms_per_launch": sm_ms,
-                     "vcycle_frac_at_171B_per_cell": cells * B_PER_CELL_VCYCLE * args.steps / (ms * 1e-3) / 1e9 / peak},
+                     "vcycle_frac_per_gpu_at_171B_per_cell":
+                         cells * B_PER_CELL_VCYCLE * args.steps / (ms * 1e-3) / 1e9 / (peak * world)},
+        "parity": parity,
+        "fingerprint": fingerprint,
         "cpu_baseline": cpu,
         "e2e": {"value": cells / t_e2e, "unit": "cell-updates/s", "h2d_bytes_per_step": gcells * 8,
                 "d2h_bytes_per_step": gcells * 8, "ms_per_step": t_e2e * 1e3},
@@ -345,6 +434,10 @@ def run_ours(args, rank, world, local_rank):
         pass
     if dist is not None:
         dist.destroy_process_group()
+    if parity.get("rel_err") is not None and parity["rel_err"] > 1e-10:
+        sys.stderr.write("bench.py: PARITY FAILURE: V-cycle differs from the reference by %.3e (> 1e-10)\n" %
+                         parity["rel_err"])
+        sys.exit(3)
 
 
 def main():
@@ -354,8 +447,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--level", type=int, default=6, help="uniform level: grid = (8<<level)^3; 6 = 512^3")
-    ap.add_argument("--cpu-level", type=int, default=5, help="grid of the bounded CPU sample (5 = 256^3)")
+    ap.add_argument("--cpu-level", type=int, default=-1,
+                    help="grid of the CPU runs: 5 = 256^3, 6 = 512^3 (default: 5 for the parity / cpu_baseline leg of "
+                         "ours; for --impl reference 6 when the host has >= 48 GB free, else 5)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the live parity check against the reference")
     ap.add_argument("--no-sweeps", action="store_true", help="skip the per-sweep secondary timings")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -83,6 +83,7 @@ SYMBOLS = {
     "cup_umax": (_i, [_vp, _dp]),
     "cup_comm_init": (_i, [_vp, _i, _i, _vp, C.c_size_t]),
     "cup_nccl_unique_id": (_i, [_vp, C.c_size_t]),
+    "cup_comm_init_host": (_i, [_vp, _i, _i, _vp, _vp]),
     "cup_plan_build": (_i, [C.POINTER(CupBlk), _ll, C.POINTER(_i), _i, _i, C.POINTER(_i), _i, _i,
                        C.POINTER(CupPlan)]),
     "cup_plan_free": (None, [C.POINTER(CupPlan)]),
@@ -91,6 +92,8 @@ SYMBOLS = {
     "cup_mg_smooth_dev": (_i, [_vp, _i, _i, _vp, _vp]),
     "cup_mg_array": (_vp, [_vp, _i]),
 }
+
+ALLGATHER_FN = C.CFUNCTYPE(_i, _vp, _vp, _vp, C.c_size_t)  # CupAllgatherFn
 
 _lib = None
 
@@ -172,6 +175,22 @@ def _ptr(a):
     return a
 
 
+def gloo_allgather(group=None):
+    """allgather(bytes) -> [bytes] over a torch.distributed (gloo / CPU tensors) process group: a host
+    collective for Context.comm_init_host (what MPI_Allgather is for the reference)."""
+    import torch
+    import torch.distributed as dist
+
+    def ag(payload):
+        n = dist.get_world_size(group)
+        t = torch.frombuffer(bytearray(payload), dtype=torch.uint8)
+        out = [torch.empty_like(t) for _ in range(n)]
+        dist.all_gather(out, t, group=group)
+        return [bytes(o.numpy().tobytes()) for o in out]
+
+    return ag
+
+
 def nccl_unique_id():
     buf = (C.c_char * 128)()
     check(lib().cup_nccl_unique_id(buf, 128))
@@ -217,6 +236,22 @@ class Context:
         buf = (C.c_char * 128).from_buffer_copy(id_bytes) if id_bytes is not None else None
         check(self.L.cup_comm_init(self.h, rank, nranks, buf, 128 if id_bytes is not None else 0))
 
+    def comm_init_host(self, rank, nranks, allgather):
+        """cup_comm_init_host: bootstrap by a host collective.  allgather(send: bytes) -> list of nranks
+        bytes objects (e.g. built on torch.distributed / mpi4py); the reference passes MPI_Allgather."""
+        def cb(user, send, recv, nbytes):
+            try:
+                parts = allgather(C.string_at(send, nbytes))
+                assert len(parts) == nranks and all(len(p) == nbytes for p in parts)
+                C.memmove(recv, b"".join(parts), nbytes * nranks)
+                return 0
+            except Exception as ex:  # reported through cup_last_error as CUP_ERR_COMM
+                import sys
+                sys.stderr.write("cup3d_b200: allgather callback failed: %r\n" % (ex,))
+                return 1
+        self._ag_cb = ALLGATHER_FN(cb)  # keep the trampoline alive as long as the context
+        check(self.L.cup_comm_init_host(self.h, rank, nranks, C.cast(self._ag_cb, _vp), None))
+
     def mesh_upload(self, ib, rb, bpd, level_max):
         arr = blocks_to_struct(np.asarray(ib), np.asarray(rb))
         b = (C.c_int * 3)(*bpd)
@@ -249,6 +284,14 @@ class Context:
 
     def stencil_apply(self, sid):
         check(self.L.cup_stencil_apply(self.h, sid))
+
+    def stencil_run(self, sid, blocks=None, n=None):
+        """stencil_run(st, list, n) (main.c:3631): listed local blocks, or the first n when blocks is None"""
+        if blocks is None:
+            check(self.L.cup_stencil_run(self.h, sid, None, self.nblk if n is None else n))
+        else:
+            arr = np.ascontiguousarray(blocks, np.int64)
+            check(self.L.cup_stencil_run(self.h, sid, arr.ctypes.data_as(C.POINTER(_ll)), len(arr)))
 
     def pois_op(self, x, out=None):
         out = np.empty_like(x) if out is None else out

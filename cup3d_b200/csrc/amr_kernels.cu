@@ -265,7 +265,8 @@ __global__ void __launch_bounds__(TPB) k_pres_amr(LevelView lv, const Real *__re
   const int t = threadIdx.x, x = t & 7, y = t >> 3, a = t & 7, c = t >> 3;
   SlotVec<Real> pv{const_cast<Real *>(p), nullptr, 0x7fffffff};
   Real *outs[3] = {o0, o1, o2};
-  for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
+  for (int wi = blockIdx.x; wi < lv_count(lv); wi += gridDim.x) {
+    const int b = lv_item(lv, wi);
     const size_t own = (size_t)lv.act[b] * 512;
     const int *nbr6 = lv.nbr + (size_t)b * 6;
     const int *ext24 = lv.ext + (size_t)b * 24;
@@ -354,7 +355,8 @@ __global__ void __launch_bounds__(TPB) k_prhs_amr(LevelView lv, const Real *__re
   __shared__ Real patch[2][6][16];
   const int t = threadIdx.x, x = t & 7, y = t >> 3, a = t & 7, c = t >> 3;
   const Real *comp[6] = {v0, v1, v2, d0, d1, d2};
-  for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
+  for (int wi = blockIdx.x; wi < lv_count(lv); wi += gridDim.x) {
+    const int b = lv_item(lv, wi);
     const size_t own = (size_t)lv.act[b] * 512;
     const int *nbr6 = lv.nbr + (size_t)b * 6;
     const int *ext24 = lv.ext + (size_t)b * 24;
@@ -483,7 +485,8 @@ __global__ void __launch_bounds__(TPB) k_velgrad_amr(LevelView lv, const Real *_
   const int t = threadIdx.x, x = t & 7, y = t >> 3, a = t & 7, c = t >> 3;
   const Real *vel[3] = {v0, v1, v2};
   Real *outs[3] = {o0, o1, o2};
-  for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
+  for (int wi = blockIdx.x; wi < lv_count(lv); wi += gridDim.x) {
+    const int b = lv_item(lv, wi);
     const size_t own = (size_t)lv.act[b] * 512;
     const int *nbr6 = lv.nbr + (size_t)b * 6;
     const int *ext24 = lv.ext + (size_t)b * 24;

@@ -282,7 +282,7 @@ int fetch_scalars(CupCtx *c, int first, int n) {
   CUP_CUDA(cudaMemcpyAsync(c->h_scal + first, c->d_scal + first, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost,
                            c->stream));
   CUP_CUDA(cudaStreamSynchronize(c->stream));
-  return CUP_OK;
+  return comm_check_error(c);  // a reduction that timed out on a peer must not be trusted
 }
 
 int axpy(CupCtx *c, void *y, const void *x, long long n, double alpha, int scal_idx, double sign) {

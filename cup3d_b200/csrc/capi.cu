@@ -64,6 +64,31 @@ static int vec_h2d(CupCtx *c, void *d_dst, const double *h_src, long long n) {
   return CUP_OK;
 }
 
+// Every entry point that touches a context runs on the context's device whatever the caller's
+// current device is, and restores the caller's device on return (one process may hold contexts on
+// several devices).
+struct DevGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DevGuard(const CupCtx *c) {
+    if (!c)
+      return;
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != c->device)
+      switched = cudaSetDevice(c->device) == cudaSuccess;
+  }
+  ~DevGuard() {
+    if (switched)
+      cudaSetDevice(prev);
+  }
+};
+
+#define CUP_ENTER(c)                         \
+  if (!(c)) {                                \
+    cup::set_error("%s: null context", __func__); \
+    return CUP_ERR_ARG;                      \
+  }                                          \
+  cup::DevGuard guard_(c)
+
 }  // namespace cup
 
 using namespace cup;
@@ -105,12 +130,23 @@ int cup_create(CupCtx **out, int device, int real_bytes) {
   c->prm.ptol = 1e-6;
   c->prm.ptol_rel = 1e-4;
   c->prm.nu = 1e-3;
-  CUP_CUDA(cudaMalloc((void **)&c->d_scal, SCAL_N * sizeof(double)));
-  CUP_CUDA(cudaMemset(c->d_scal, 0, SCAL_N * sizeof(double)));
-  CUP_CUDA(cudaMallocHost((void **)&c->h_scal, SCAL_N * sizeof(double)));
   // the NULL stream cannot be captured into a CUDA graph: work goes to an own BLOCKING stream
   // (implicitly ordered against legacy-default-stream work of the caller) unless one is set
-  CUP_CUDA(cudaStreamCreate(&c->own_stream));
+  cudaError_t e1 = cudaMalloc((void **)&c->d_scal, SCAL_N * sizeof(double));
+  if (e1 == cudaSuccess)
+    e1 = cudaMemset(c->d_scal, 0, SCAL_N * sizeof(double));
+  if (e1 == cudaSuccess)
+    e1 = cudaMallocHost((void **)&c->h_scal, SCAL_N * sizeof(double));
+  if (e1 == cudaSuccess)
+    e1 = cudaStreamCreate(&c->own_stream);
+  if (e1 != cudaSuccess) {
+    set_error("cup_create: %s", cudaGetErrorString(e1));
+    cudaFree(c->d_scal);
+    if (c->h_scal)
+      cudaFreeHost(c->h_scal);
+    delete c;
+    return CUP_ERR_CUDA;
+  }
   c->stream = c->own_stream;
   *out = c;
   return CUP_OK;
@@ -144,17 +180,21 @@ int cup_destroy(CupCtx *c) {
   cudaFree(c->d_hw);
   cudaFree(c->d_scal);
   cudaFreeHost(c->h_scal);
+  if (c->h_err)
+    cudaFreeHost(c->h_err);
   cudaStreamDestroy(c->own_stream);
   delete c;
   return CUP_OK;
 }
 
 int cup_set_stream(CupCtx *c, void *stream) {
+  CUP_ENTER(c);
   c->stream = stream ? (cudaStream_t)stream : c->own_stream;
   return CUP_OK;
 }
 
 int cup_set_params(CupCtx *c, const CupParams *p) {
+  CUP_ENTER(c);
   if (!p) {
     set_error("cup_set_params: null");
     return CUP_ERR_ARG;
@@ -164,16 +204,17 @@ int cup_set_params(CupCtx *c, const CupParams *p) {
 }
 
 int cup_synchronize(CupCtx *c) {
+  CUP_ENTER(c);
   CUP_CUDA(cudaStreamSynchronize(c->stream));
-  return CUP_OK;
+  return comm_check_error(c);
 }
 
-int cup_mesh_upload(CupCtx *c, const CupBlk *blk, long long n, const int bpd[3], int level_max) {
-  CUP_CUDA(cudaSetDevice(c->device));
+static int mesh_upload_impl(CupCtx *c, const CupBlk *blk, long long n, const int bpd[3], int level_max) {
   CUP_CUDA(cudaStreamSynchronize(c->stream));
   free_krylov(c);
   free_obstacles(c);
   free_graph_cache(c);
+  free_tma_cache(c);  // descriptors are keyed by pointers that are about to be freed
   comm_free_level_buffers(c);
   // tree_sync (main.c:2928): all ranks learn all blocks; owner = contributing rank
   std::vector<CupBlk> gblk;
@@ -186,6 +227,24 @@ int cup_mesh_upload(CupCtx *c, const CupBlk *blk, long long n, const int bpd[3],
   return CUP_OK;
 }
 
+int cup_mesh_upload(CupCtx *c, const CupBlk *blk, long long n, const int bpd[3], int level_max) {
+  CUP_ENTER(c);
+  if (!blk || !bpd || n <= 0) {
+    set_error("cup_mesh_upload: blk/bpd null or n = %lld", n);
+    return CUP_ERR_ARG;
+  }
+  const int rc = mesh_upload_impl(c, blk, n, bpd, level_max);
+  if (rc != CUP_OK) {
+    // never leave a half-built mesh behind: later calls must fail with CUP_ERR_STATE, not launch
+    // kernels on null tables
+    const std::string keep = cup_last_error();
+    comm_free_level_buffers(c);
+    free_mesh(c);
+    set_error("%s", keep.c_str());
+  }
+  return rc;
+}
+
 long long cup_nblk(const CupCtx *c) { return c->nblk; }
 long long cup_nslot(const CupCtx *c) { return c->nslot; }
 int cup_mg_levels(const CupCtx *c) { return c->top + 1; }
@@ -194,6 +253,7 @@ long long cup_mg_nact(const CupCtx *c, int level) {
 }
 
 int cup_state_h2d(CupCtx *c, const double *h_fld, int f0, int nc) {
+  CUP_ENTER(c);
   if (f0 < 0 || nc < 1 || f0 + nc > CUP_F_N || c->nblk == 0) {
     set_error("cup_state_h2d: bad field range %d+%d", f0, nc);
     return CUP_ERR_ARG;
@@ -214,6 +274,7 @@ int cup_state_h2d(CupCtx *c, const double *h_fld, int f0, int nc) {
 }
 
 int cup_state_d2h(CupCtx *c, double *h_fld, int f0, int nc) {
+  CUP_ENTER(c);
   if (f0 < 0 || nc < 1 || f0 + nc > CUP_F_N || c->nblk == 0) {
     set_error("cup_state_d2h: bad field range %d+%d", f0, nc);
     return CUP_ERR_ARG;
@@ -238,10 +299,17 @@ int cup_state_d2h(CupCtx *c, double *h_fld, int f0, int nc) {
 
 void *cup_state_dev(CupCtx *c, int f) { return (f < 0 || f >= CUP_F_N) ? nullptr : c->state[f]; }
 
-int cup_pois_op_dev(CupCtx *c, const void *d_in, void *d_out) { return pois_op_dev(c, d_in, d_out); }
-int cup_mg_vcycle_dev(CupCtx *c, const void *d_in, void *d_out) { return mg_vcycle_dev(c, d_in, d_out); }
+int cup_pois_op_dev(CupCtx *c, const void *d_in, void *d_out) {
+  CUP_ENTER(c);
+  return pois_op_dev(c, d_in, d_out);
+}
+int cup_mg_vcycle_dev(CupCtx *c, const void *d_in, void *d_out) {
+  CUP_ENTER(c);
+  return mg_vcycle_dev(c, d_in, d_out);
+}
 
 static int host_op(CupCtx *c, const double *h_in, double *h_out, int which) {
+  CUP_ENTER(c);
   if (c->nblk == 0) {
     set_error("no mesh uploaded");
     return CUP_ERR_STATE;
@@ -257,24 +325,38 @@ static int host_op(CupCtx *c, const double *h_in, double *h_out, int which) {
   }
   CUP_CUDA(cudaMemcpyAsync(h_out, dout, (size_t)N * 8, cudaMemcpyDeviceToHost, c->stream));
   CUP_CUDA(cudaStreamSynchronize(c->stream));
-  return CUP_OK;
+  return comm_check_error(c);
 }
 
 int cup_pois_op(CupCtx *c, const double *h_in, double *h_out) { return host_op(c, h_in, h_out, 0); }
 int cup_mg_vcycle(CupCtx *c, const double *h_in, double *h_out) { return host_op(c, h_in, h_out, 1); }
 
 int cup_pois_dot_dev(CupCtx *c, const void *a, const void *b, double *result) {
+  CUP_ENTER(c);
   CUP_TRY(wdot(c, a, b, 4));
   CUP_TRY(fetch_scalars(c, 4, 1));
   *result = c->h_scal[4];
   return CUP_OK;
 }
 
-int cup_pois_solve(CupCtx *c, CupSolveInfo *info) { return pois_solve(c, info); }
-int cup_umax(CupCtx *c, double *out) { return umax(c, out); }
-int cup_advdiff(CupCtx *c) { return advdiff(c); }
-int cup_vorticity(CupCtx *c) { return vorticity(c); }
+int cup_pois_solve(CupCtx *c, CupSolveInfo *info) {
+  CUP_ENTER(c);
+  return pois_solve(c, info);
+}
+int cup_umax(CupCtx *c, double *out) {
+  CUP_ENTER(c);
+  return umax(c, out);
+}
+int cup_advdiff(CupCtx *c) {
+  CUP_ENTER(c);
+  return advdiff(c);
+}
+int cup_vorticity(CupCtx *c) {
+  CUP_ENTER(c);
+  return vorticity(c);
+}
 int cup_io_pack(CupCtx *c, float *attr, float *vort, float *q) {
+  CUP_ENTER(c);
   if (c->nblk == 0) {
     set_error("cup_io_pack: no mesh uploaded");
     return CUP_ERR_STATE;
@@ -285,38 +367,64 @@ int cup_io_pack(CupCtx *c, float *attr, float *vort, float *q) {
   return io_pack(c, attr, vort, q);
 }
 int cup_block_linf(CupCtx *c, int f0, double *linf_all, double *linf_fluid) {
+  CUP_ENTER(c);
   return block_linf(c, f0, linf_all, linf_fluid);
 }
-int cup_projection(CupCtx *c, CupSolveInfo *info) { return projection(c, info); }
+int cup_projection(CupCtx *c, CupSolveInfo *info) {
+  CUP_ENTER(c);
+  return projection(c, info);
+}
 int cup_projection_udef_ready(CupCtx *c, int flag) {
+  CUP_ENTER(c);
   c->keep_tmp_udef = flag != 0;
   return CUP_OK;
 }
 int cup_obstacle_upload(CupCtx *c, int body, int nob, const int *blk, const double *chi, const double *udef) {
+  CUP_ENTER(c);
   return obstacle_upload(c, body, nob, blk, chi, udef);
 }
 int cup_obstacle_motion(CupCtx *c, int body, const double com[3], const double vel[3], const double omega[3]) {
+  CUP_ENTER(c);
   return obstacle_motion(c, body, com, vel, omega);
 }
-int cup_obstacle_clear(CupCtx *c) { return obstacle_clear(c); }
+int cup_obstacle_clear(CupCtx *c) {
+  CUP_ENTER(c);
+  return obstacle_clear(c);
+}
 int cup_obstacle_moments(CupCtx *c, int body, double *M) {
+  CUP_ENTER(c);
   if (!M) {
     set_error("cup_obstacle_moments: M is NULL");
     return CUP_ERR_ARG;
   }
   return obstacle_moments(c, body, M);
 }
-int cup_obstacle_penalize(CupCtx *c) { return obstacle_penalize(c); }
-int cup_obstacle_tmpv(CupCtx *c) { return obstacle_tmpv(c); }
-int cup_stencil_apply(CupCtx *c, CupStencilId id) { return stencil_run(c, id, nullptr, c->nblk); }
+int cup_obstacle_penalize(CupCtx *c) {
+  CUP_ENTER(c);
+  return obstacle_penalize(c);
+}
+int cup_obstacle_tmpv(CupCtx *c) {
+  CUP_ENTER(c);
+  return obstacle_tmpv(c);
+}
+int cup_stencil_apply(CupCtx *c, CupStencilId id) {
+  CUP_ENTER(c);
+  return stencil_run(c, id, nullptr, c->nblk);
+}
 int cup_stencil_run(CupCtx *c, CupStencilId id, const long long *list, long long n) {
+  CUP_ENTER(c);
   return stencil_run(c, id, list, n);
 }
 
 int cup_comm_init(CupCtx *c, int rank, int nranks, const void *id, size_t id_bytes) {
+  CUP_ENTER(c);
   return comm_init(c, rank, nranks, id, id_bytes);
 }
 int cup_nccl_unique_id(void *out, size_t bytes) { return comm_unique_id(out, bytes); }
+int cup_comm_init_host(CupCtx *c, int rank, int nranks, CupAllgatherFn allgather, void *user) {
+  CUP_ENTER(c);
+  return comm_init_host(c, rank, nranks, allgather, user);
+}
 
 static int *dup_ints(const std::vector<int> &v) {
   int *p = (int *)malloc((v.size() + 1) * sizeof(int));
@@ -377,8 +485,12 @@ void cup_plan_free(CupPlan *p) {
 }
 
 long long cup_kernel_launches(const CupCtx *c) { return c->launches; }
-int cup_time_smooth(CupCtx *c, int level, int reps, float *ms) { return time_smooth(c, level, reps, ms); }
+int cup_time_smooth(CupCtx *c, int level, int reps, float *ms) {
+  CUP_ENTER(c);
+  return time_smooth(c, level, reps, ms);
+}
 int cup_mg_smooth_dev(CupCtx *c, int level, int n, void *d_u, const void *d_f) {
+  CUP_ENTER(c);
   return mg_smooth_slots(c, level, n, d_u, d_f);
 }
 void *cup_mg_array(CupCtx *c, int which) {

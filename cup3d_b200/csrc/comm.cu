@@ -12,6 +12,7 @@
 #include <nccl.h>
 
 #include "comm.cuh"
+#include "comm_dev.cuh"
 #include "cup_internal.h"
 #include "mg_device.cuh"
 #include "smooth_tma.cuh"
@@ -70,15 +71,21 @@ static int load_nccl() {
   return CUP_OK;
 }
 
+enum { RED_MAX = 32 };  // values per window all-reduce (GMRES: j + 2 <= 32; fish moments: 29)
+
 struct Comm {
-  ncclComm_t nccl = nullptr;
+  ncclComm_t nccl = nullptr;           // NCCL bootstrap (cup_comm_init); null with a host bootstrap
+  CupAllgatherFn host_ag = nullptr;    // host bootstrap (cup_comm_init_host)
+  void *host_user = nullptr;
   // ---- one-sided mode: every rank exposes one receive window through CUDA IPC ----
   bool p2p = false;
-  char *win = nullptr;                 // [flags | per-level receive areas]
-  size_t flag_bytes = 0;
+  char *win = nullptr;                 // [flags | all-reduce area | per-level receive areas]
+  size_t flag_bytes = 0;               // bytes in front of the per-level areas
   std::vector<char *> peer_win;        // mapped base of every rank's window (own = win)
   char **d_peer_win = nullptr;
-  unsigned long long *d_seq = nullptr; // [levels][3] exchange counters of THIS rank (face, restrict, prolong)
+  unsigned long long *d_seq = nullptr; // [levels][3] exchange counters of THIS rank (face, restrict, prolong) + [1] all-reduce
+  size_t red_flag_index = 0;           // index (in 8-byte words) of the [nranks] all-reduce flag words
+  size_t red_data_off = 0;             // byte offset of the all-reduce data [2][nranks][RED_MAX] doubles
 };
 
 #define CUP_NCCL(call)                                                                      \
@@ -134,6 +141,30 @@ int comm_init(CupCtx *c, int rank, int nranks, const void *idp, size_t id_bytes)
   return CUP_OK;
 }
 
+int comm_init_host(CupCtx *c, int rank, int nranks, CupAllgatherFn fn, void *user) {
+  if (nranks < 1 || rank < 0 || rank >= nranks) {
+    set_error("cup_comm_init_host: rank %d of %d", rank, nranks);
+    return CUP_ERR_ARG;
+  }
+  if (c->nblk != 0) {
+    set_error("cup_comm_init_host must precede cup_mesh_upload");
+    return CUP_ERR_STATE;
+  }
+  if (nranks > 1 && !fn) {
+    set_error("cup_comm_init_host: allgather callback required");
+    return CUP_ERR_ARG;
+  }
+  c->rank = rank;
+  c->nranks = nranks;
+  if (nranks == 1)
+    return CUP_OK;
+  Comm *cm = new Comm;
+  cm->host_ag = fn;
+  cm->host_user = user;
+  c->comm = cm;
+  return CUP_OK;
+}
+
 void comm_free(CupCtx *c) {
   Comm *cm = (Comm *)c->comm;
   if (!cm)
@@ -144,6 +175,39 @@ void comm_free(CupCtx *c) {
   c->comm = nullptr;
 }
 
+// every rank contributes `bytes` bytes; recv = nranks * bytes in rank order (host memory)
+static int allgather_bytes(CupCtx *c, const void *send, void *recv, size_t bytes) {
+  Comm *cm = (Comm *)c->comm;
+  const int R = c->nranks;
+  if (cm->host_ag) {
+    const int rc = cm->host_ag(cm->host_user, send, recv, bytes);
+    if (rc != 0) {
+      set_error("host allgather callback failed: %d", rc);
+      return CUP_ERR_COMM;
+    }
+    return CUP_OK;
+  }
+  char *d;
+  CUP_CUDA(cudaMalloc((void **)&d, bytes * (size_t)(R + 1)));
+  CUP_CUDA(cudaMemcpyAsync(d + bytes * R, send, bytes, cudaMemcpyHostToDevice, c->stream));
+  CUP_NCCL(g_nccl.AllGather(d + bytes * R, d, bytes, ncclChar, cm->nccl, c->stream));
+  CUP_CUDA(cudaMemcpyAsync(recv, d, bytes * (size_t)R, cudaMemcpyDeviceToHost, c->stream));
+  CUP_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d);
+  return CUP_OK;
+}
+
+int comm_check_error(CupCtx *c) {
+  if (c->h_err && *(volatile int *)c->h_err != 0) {
+    const int code = *(volatile int *)c->h_err;
+    *(volatile int *)c->h_err = 0;
+    set_error("rank %d: a peer did not post in time (exchange code %d: level %d, kind %d) -- peer lost or ranks "
+              "out of step", c->rank, code, (code - 1) / 4, (code - 1) % 4);
+    return CUP_ERR_COMM;
+  }
+  return CUP_OK;
+}
+
 // tree_sync: every rank contributes its blocks; result = global list in rank order + owner per block
 int comm_gather_blocks(CupCtx *c, const CupBlk *blk, long long n, std::vector<CupBlk> &gblk,
                        std::vector<int> &owner) {
@@ -152,30 +216,18 @@ int comm_gather_blocks(CupCtx *c, const CupBlk *blk, long long n, std::vector<Cu
     owner.assign((size_t)n, 0);
     return CUP_OK;
   }
-  Comm *cm = (Comm *)c->comm;
   const int R = c->nranks;
-  long long *d_cnt;
-  CUP_CUDA(cudaMalloc((void **)&d_cnt, (size_t)(R + 1) * sizeof(long long)));
-  CUP_CUDA(cudaMemcpyAsync(d_cnt + R, &n, sizeof n, cudaMemcpyHostToDevice, c->stream));
-  CUP_NCCL(g_nccl.AllGather(d_cnt + R, d_cnt, sizeof(long long), ncclChar, cm->nccl, c->stream));
   std::vector<long long> cnt((size_t)R);
-  CUP_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)R * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
-  CUP_CUDA(cudaStreamSynchronize(c->stream));
-  cudaFree(d_cnt);
+  CUP_TRY(allgather_bytes(c, &n, cnt.data(), sizeof(long long)));
   long long mx = 0, tot = 0;
   for (int r = 0; r < R; r++) {
     mx = cnt[r] > mx ? cnt[r] : mx;
     tot += cnt[r];
   }
   const size_t chunk = (size_t)mx * sizeof(CupBlk);
-  char *d;
-  CUP_CUDA(cudaMalloc((void **)&d, chunk * (size_t)(R + 1)));
-  CUP_CUDA(cudaMemcpyAsync(d + chunk * R, blk, (size_t)n * sizeof(CupBlk), cudaMemcpyHostToDevice, c->stream));
-  CUP_NCCL(g_nccl.AllGather(d + chunk * R, d, chunk, ncclChar, cm->nccl, c->stream));
-  std::vector<char> h(chunk * (size_t)R);
-  CUP_CUDA(cudaMemcpyAsync(h.data(), d, h.size(), cudaMemcpyDeviceToHost, c->stream));
-  CUP_CUDA(cudaStreamSynchronize(c->stream));
-  cudaFree(d);
+  std::vector<char> mine(chunk, 0), h(chunk * (size_t)R);
+  memcpy(mine.data(), blk, (size_t)n * sizeof(CupBlk));
+  CUP_TRY(allgather_bytes(c, mine.data(), h.data(), chunk));
   gblk.clear();
   owner.clear();
   gblk.reserve((size_t)tot);
@@ -189,13 +241,80 @@ int comm_gather_blocks(CupCtx *c, const CupBlk *blk, long long n, std::vector<Cu
   return CUP_OK;
 }
 
-int comm_allreduce(CupCtx *c, int first, int n) {
+// All-reduce of a few device scalars through the peer windows: every rank stores its values into
+// every rank's window (parity-double-buffered), publishes a flag, waits for the others' flags and
+// reduces in RANK ORDER -- the result is bitwise identical on all ranks and independent of timing.
+// One small kernel, no NCCL kernel, replayable from a CUDA graph.
+__global__ void __launch_bounds__(256) k_allreduce_win(double *vals, int n, int is_max, unsigned long long *seq,
+                                                       char *const *peer_win, int me, int R, size_t flag_index,
+                                                       size_t data_off, int *err) {
+  __shared__ unsigned long long s_seq;
+  const int t = threadIdx.x;
+  if (t == 0)
+    s_seq = *(volatile unsigned long long *)seq + 1;
+  __syncthreads();
+  const unsigned long long s = s_seq;
+  const size_t par = (size_t)(s & 1);
+  for (int idx = t; idx < n * R; idx += blockDim.x) {
+    const int p = idx / n, j = idx - p * n;
+    volatile double *dst = (volatile double *)(peer_win[p] + data_off) + ((par * R + me) * RED_MAX + j);
+    *dst = vals[j];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t < R && t != me) {
+    volatile unsigned long long *f = (volatile unsigned long long *)peer_win[t] + flag_index + me;
+    *f = s;
+    const volatile unsigned long long *mine = (const volatile unsigned long long *)peer_win[me] + flag_index + t;
+    int spins = 0;
+    while (*mine < s) {
+      __nanosleep(100);
+      if (++spins > COMM_SPIN_MAX) {
+        *(volatile int *)err = 4000;
+        break;
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t < n) {
+    const double *src = (const double *)(peer_win[me] + data_off) + (par * R) * RED_MAX + t;
+    double acc = __ldcg(src);
+    for (int r = 1; r < R; r++) {
+      const double v = __ldcg(src + (size_t)r * RED_MAX);
+      acc = is_max ? (acc < v ? v : acc) : acc + v;
+    }
+    vals[t] = acc;
+  }
+  if (t == 0)
+    *(volatile unsigned long long *)seq = s;
+}
+
+static int allreduce_impl(CupCtx *c, int first, int n, bool is_max) {
   if (c->nranks == 1)
     return CUP_OK;
   Comm *cm = (Comm *)c->comm;
-  CUP_NCCL(g_nccl.AllReduce(c->d_scal + first, c->d_scal + first, (size_t)n, ncclDouble, ncclSum, cm->nccl, c->stream));
+  if (cm->p2p) {
+    for (int o = 0; o < n; o += RED_MAX) {
+      const int m = n - o < RED_MAX ? n - o : RED_MAX;
+      k_allreduce_win<<<1, 256, 0, c->stream>>>(c->d_scal + first + o, m, is_max ? 1 : 0,
+                                                cm->d_seq + (size_t)(c->top + 1) * 3, cm->d_peer_win, c->rank,
+                                                c->nranks, cm->red_flag_index, cm->red_data_off, c->h_err);
+      c->launches++;
+    }
+    CUP_CUDA(cudaGetLastError());
+    return CUP_OK;
+  }
+  if (!cm->nccl) {
+    set_error("all-reduce without peer windows needs the NCCL bootstrap (cup_comm_init)");
+    return CUP_ERR_STATE;
+  }
+  CUP_NCCL(g_nccl.AllReduce(c->d_scal + first, c->d_scal + first, (size_t)n, ncclDouble, is_max ? ncclMax : ncclSum,
+                            cm->nccl, c->stream));
   return CUP_OK;
 }
+
+int comm_allreduce(CupCtx *c, int first, int n) { return allreduce_impl(c, first, n, false); }
 
 // ===========================================================================
 // Exchanges.  Two transports behind one post/wait interface:
@@ -213,13 +332,7 @@ int comm_allreduce(CupCtx *c, int first, int n) {
 // ===========================================================================
 enum { K_FACE = 0, K_RES = 1, K_PRO = 2 };
 
-int comm_allreduce_max(CupCtx *c, int first, int n) {
-  if (c->nranks == 1)
-    return CUP_OK;
-  Comm *cm = (Comm *)c->comm;
-  CUP_NCCL(g_nccl.AllReduce(c->d_scal + first, c->d_scal + first, (size_t)n, ncclDouble, ncclMax, cm->nccl, c->stream));
-  return CUP_OK;
-}
+int comm_allreduce_max(CupCtx *c, int first, int n) { return allreduce_impl(c, first, n, true); }
 
 // grouped point-to-point exchange: entries of `entry_bytes` bytes, peer-major on both sides
 static int exchange(CupCtx *c, const void *sbuf, const std::vector<int> &scnt, void *rbuf,
@@ -251,9 +364,10 @@ template <typename Real>
 __global__ void __launch_bounds__(64) k_pack_faces(const int *__restrict__ sslot, const int *__restrict__ splane,
                                                    int n, SlotVec<Real> u, Real *const *__restrict__ dst0,
                                                    Real *const *__restrict__ dst1,
-                                                   const unsigned long long *__restrict__ seq) {
+                                                   const unsigned long long *__restrict__ seq, PostDesc post) {
   const int t = threadIdx.x, a = t & 7, cc = t >> 3;
-  const bool odd = seq ? ((*seq + 1) & 1) : false;  // the exchange being posted is number *seq + 1
+  // the exchange being posted is number *seq + 1 (the last CTA to retire bumps it, so every CTA reads the old value)
+  const bool odd = seq ? ((*(const volatile unsigned long long *)seq + 1) & 1) : false;
   for (int e = blockIdx.x; e < n; e += gridDim.x) {
     const Real *b = u.at(sslot[e]);
     const int p = splane[e], q = (p & 1) ? 7 : 0;
@@ -266,6 +380,7 @@ __global__ void __launch_bounds__(64) k_pack_faces(const int *__restrict__ sslot
       idx = (q << 6) + t;
     (odd ? dst1 : dst0)[e][t] = b[idx];
   }
+  comm_post_at_exit(post);
 }
 
 // ghost slabs of the stencil sweeps: for each face entry, `ncomp` components x `nlayer` planes
@@ -274,9 +389,9 @@ template <typename Real>
 __global__ void __launch_bounds__(64) k_pack_slabs(const int *__restrict__ sslot, const int *__restrict__ splane,
                                                    int n, SlabSrc<Real> src, int ncomp, int nlayer,
                                                    Real *const *__restrict__ dst0, Real *const *__restrict__ dst1,
-                                                   const unsigned long long *__restrict__ seq) {
+                                                   const unsigned long long *__restrict__ seq, PostDesc post) {
   const int t = threadIdx.x, a = t & 7, cc = t >> 3;
-  const bool odd = seq ? ((*seq + 1) & 1) : false;
+  const bool odd = seq ? ((*(const volatile unsigned long long *)seq + 1) & 1) : false;
   for (int e = blockIdx.x; e < n; e += gridDim.x) {
     const size_t base = (size_t)sslot[e] * 512;
     const int p = splane[e];
@@ -287,31 +402,36 @@ __global__ void __launch_bounds__(64) k_pack_slabs(const int *__restrict__ sslot
         d[(q * nlayer + l) * 64 + t] = src.c[q][base + face_idx(p, n0, a, cc)];
       }
   }
+  comm_post_at_exit(post);
 }
 
 // mg_put (main.c:4722): received 64 r + 64 u of a remote child -> the parent's octant
 template <typename Real>
 __global__ void __launch_bounds__(64) k_put(const int *__restrict__ rslot, const int *__restrict__ roct, int n,
-                                            const Real *__restrict__ in, SlotVec<Real> f, SlotVec<Real> u) {
+                                            const Real *__restrict__ in, SlotVec<Real> f, SlotVec<Real> u,
+                                            WaitDesc wait) {
   const int t = threadIdx.x, cx = t & 3, cy = (t >> 2) & 3, cz = t >> 4;
+  comm_wait_cta(wait);  // the children's owners posted them (k_down's exit)
   for (int e = blockIdx.x; e < n; e += gridDim.x) {
     const int o = roct[e], ps = rslot[e];
     const int pidx = ((4 * (o >> 2) + cz) << 6) + ((4 * ((o >> 1) & 1) + cy) << 3) + 4 * (o & 1) + cx;
-    f.at(ps)[pidx] = in[(size_t)e * 128 + t];
-    u.at(ps)[pidx] = in[(size_t)e * 128 + 64 + t];
+    f.at(ps)[pidx] = ld_recv(in + (size_t)e * 128 + t);
+    u.at(ps)[pidx] = ld_recv(in + (size_t)e * 128 + 64 + t);
   }
 }
 
 // mg_get (main.c:4771): u_c - us of the parent's octant, for a remote child
 template <typename Real>
 __global__ void __launch_bounds__(64) k_get(const int *__restrict__ rslot, const int *__restrict__ roct, int n,
-                                            SlotVec<Real> u, SlotVec<Real> us, Real *const *__restrict__ dst) {
+                                            SlotVec<Real> u, SlotVec<Real> us, Real *const *__restrict__ dst,
+                                            PostDesc post) {
   const int t = threadIdx.x, cx = t & 3, cy = (t >> 2) & 3, cz = t >> 4;
   for (int e = blockIdx.x; e < n; e += gridDim.x) {
     const int o = roct[e], ps = rslot[e];
     const int pidx = ((4 * (o >> 2) + cz) << 6) + ((4 * ((o >> 1) & 1) + cy) << 3) + 4 * (o & 1) + cx;
     dst[e][t] = u.at(ps)[pidx] - us.at(ps)[pidx];
   }
+  comm_post_at_exit(post);
 }
 
 // bump this rank's sequence number for (level, kind) and publish it to the peers' flag words
@@ -331,19 +451,9 @@ __global__ void __launch_bounds__(64) k_signal(unsigned long long *seq, char *co
 }
 
 // wait until every listed peer has published at least this rank's current sequence number
-__global__ void __launch_bounds__(64) k_wait(const unsigned long long *seq, const unsigned long long *my_flags,
-                                             const int *peers, int np) {
-  const unsigned long long want = *seq;
-  for (int i = threadIdx.x; i < np; i += blockDim.x) {
-    const volatile unsigned long long *f = my_flags + peers[i];
-    long long spins = 0;
-    while (*f < want) {
-      __nanosleep(64);
-      if (++spins > (1LL << 26))  // several seconds: a lost peer is an error, not a hang
-        __trap();
-    }
-  }
-  __threadfence_system();
+__global__ void __launch_bounds__(64) k_wait(WaitDesc w) {
+  // several seconds without an answer: a lost peer is an ERROR reported to the host, not a hang or a trap
+  comm_wait_cta(w);
 }
 
 static inline int cgrid(const CupCtx *c, int n) {
@@ -379,15 +489,17 @@ static std::vector<int> peers_of(const std::vector<int> &cnt) {
 void comm_free_level_buffers(CupCtx *c) {
   Comm *cm = (Comm *)c->comm;
   if (cm && cm->p2p) {
-    // nobody may still be writing into a window that is about to disappear
+    // nobody may still be writing into a window that is about to disappear: local work done, then a barrier
     cudaStreamSynchronize(c->stream);
-    double *d = c->d_scal + SCAL_N - 1;
-    g_nccl.AllReduce(d, d, 1, ncclDouble, ncclSum, cm->nccl, c->stream);
-    cudaStreamSynchronize(c->stream);
+    char one = 0;
+    std::vector<char> all((size_t)c->nranks);
+    allgather_bytes(c, &one, all.data(), 1);
     for (int p = 0; p < c->nranks; p++)
       if (p != c->rank && cm->peer_win.size() > (size_t)p && cm->peer_win[p])
         cudaIpcCloseMemHandle(cm->peer_win[p]);
     cm->peer_win.clear();
+    // ... and nobody may still have this rank's window mapped when it is freed
+    allgather_bytes(c, &one, all.data(), 1);
     cudaFree(cm->win);
     cudaFree(cm->d_peer_win);
     cudaFree(cm->d_seq);
@@ -433,18 +545,22 @@ static bool want_p2p() {
   return !(e && atoi(e) == 0);
 }
 
-// open every rank's receive window; false if CUDA IPC is not usable here
+// open every rank's receive window; *ok = false if CUDA IPC is not usable here
 static int open_windows(CupCtx *c, bool *ok) {
   Comm *cm = (Comm *)c->comm;
   const int R = c->nranks;
   const size_t rb = (size_t)c->real_bytes;
   *ok = false;
-  cm->flag_bytes = (((size_t)(c->top + 1) * 3 * R * sizeof(unsigned long long)) + 255) / 256 * 256;
+  // [level][kind][rank] exchange flags | [rank] all-reduce flags | all-reduce data [2][R][RED_MAX]
+  const size_t nflag = (size_t)(c->top + 1) * 3 * R;
+  cm->red_flag_index = nflag;
+  cm->red_data_off = ((nflag + (size_t)R) * sizeof(unsigned long long) + 255) / 256 * 256;
+  cm->flag_bytes = (cm->red_data_off + (size_t)2 * R * RED_MAX * sizeof(double) + 255) / 256 * 256;
   const size_t bytes = cm->flag_bytes + (size_t)c->win_reals[c->rank] * rb + 256;
   CUP_CUDA(cudaMalloc((void **)&cm->win, bytes));
   CUP_CUDA(cudaMemset(cm->win, 0, bytes));
   CUP_CUDA(cudaDeviceSynchronize());
-  // all-gather the IPC handles (and a usable flag) through NCCL
+  // all-gather the IPC handles (and a usable flag)
   struct Msg {
     cudaIpcMemHandle_t h;
     int ok, pad[15];
@@ -453,20 +569,13 @@ static int open_windows(CupCtx *c, bool *ok) {
   memset(&mine, 0, sizeof mine);
   mine.ok = cudaIpcGetMemHandle(&mine.h, cm->win) == cudaSuccess;
   cudaGetLastError();
-  char *d;
-  CUP_CUDA(cudaMalloc((void **)&d, sizeof(Msg) * (size_t)(R + 1)));
-  CUP_CUDA(cudaMemcpyAsync(d + sizeof(Msg) * R, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
-  CUP_NCCL(g_nccl.AllGather(d + sizeof(Msg) * R, d, sizeof(Msg), ncclChar, cm->nccl, c->stream));
   std::vector<Msg> all((size_t)R);
-  CUP_CUDA(cudaMemcpyAsync(all.data(), d, sizeof(Msg) * (size_t)R, cudaMemcpyDeviceToHost, c->stream));
-  CUP_CUDA(cudaStreamSynchronize(c->stream));
-  cudaFree(d);
+  CUP_TRY(allgather_bytes(c, &mine, all.data(), sizeof(Msg)));
   bool good = true;
   for (int p = 0; p < R; p++)
     good = good && all[p].ok;
   cm->peer_win.assign((size_t)R, nullptr);
   cm->peer_win[c->rank] = cm->win;
-  int opened = 1;
   if (good)
     for (int p = 0; p < R; p++) {
       if (p == c->rank)
@@ -478,15 +587,15 @@ static int open_windows(CupCtx *c, bool *ok) {
         break;
       }
       cm->peer_win[p] = (char *)ptr;
-      opened++;
     }
   // everyone must agree on the transport
-  double flag = good ? 0.0 : 1.0, *dflag = c->d_scal + SCAL_N - 1;
-  CUP_CUDA(cudaMemcpyAsync(dflag, &flag, sizeof flag, cudaMemcpyHostToDevice, c->stream));
-  CUP_NCCL(g_nccl.AllReduce(dflag, dflag, 1, ncclDouble, ncclSum, cm->nccl, c->stream));
-  CUP_CUDA(cudaMemcpyAsync(&flag, dflag, sizeof flag, cudaMemcpyDeviceToHost, c->stream));
-  CUP_CUDA(cudaStreamSynchronize(c->stream));
-  if (flag != 0.0) {
+  char flag = good ? 0 : 1;
+  std::vector<char> flags((size_t)R);
+  CUP_TRY(allgather_bytes(c, &flag, flags.data(), 1));
+  bool all_good = true;
+  for (int p = 0; p < R; p++)
+    all_good = all_good && flags[p] == 0;
+  if (!all_good) {
     for (int p = 0; p < R; p++)
       if (p != c->rank && cm->peer_win[p])
         cudaIpcCloseMemHandle(cm->peer_win[p]);
@@ -496,8 +605,9 @@ static int open_windows(CupCtx *c, bool *ok) {
     return CUP_OK;
   }
   CUP_TRY(up(&cm->d_peer_win, cm->peer_win));
-  CUP_CUDA(cudaMalloc((void **)&cm->d_seq, (size_t)(c->top + 1) * 3 * sizeof(unsigned long long)));
-  CUP_CUDA(cudaMemset(cm->d_seq, 0, (size_t)(c->top + 1) * 3 * sizeof(unsigned long long)));
+  const size_t nseq = (size_t)(c->top + 1) * 3 + 1;
+  CUP_CUDA(cudaMalloc((void **)&cm->d_seq, nseq * sizeof(unsigned long long)));
+  CUP_CUDA(cudaMemset(cm->d_seq, 0, nseq * sizeof(unsigned long long)));
   *ok = true;
   return CUP_OK;
 }
@@ -509,9 +619,22 @@ int comm_alloc_level_buffers(CupCtx *c) {
   if (c->nranks == 1)
     return CUP_OK;
   Comm *cm = (Comm *)c->comm;
+  if (!cm) {
+    set_error("rank %d of %d: cup_comm_init / cup_comm_init_host was not called", c->rank, c->nranks);
+    return CUP_ERR_STATE;
+  }
+  if (!c->h_err) {
+    CUP_CUDA(cudaHostAlloc((void **)&c->h_err, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+    *c->h_err = 0;
+  }
   bool p2p = false;
   if (want_p2p())
     CUP_TRY(open_windows(c, &p2p));
+  if (!p2p && !cm->nccl) {
+    set_error("the host-bootstrapped transport needs CUDA IPC peer windows between all ranks (not available here%s)",
+              want_p2p() ? "" : ": CUP_P2P=0");
+    return CUP_ERR_UNSUPPORTED;
+  }
   cm->p2p = p2p;
   const int me = c->rank;
   for (auto &v : c->lv) {
@@ -592,6 +715,10 @@ int comm_alloc_level_buffers(CupCtx *c) {
       CUP_TRY(up(&v.d_speers[k], v.speers[k]));
       CUP_TRY(up(&v.d_rpeers[k], v.rpeers[k]));
     }
+    if (p2p) {
+      CUP_CUDA(cudaMalloc((void **)&v.d_counters, 8 * sizeof(unsigned int)));
+      CUP_CUDA(cudaMemset(v.d_counters, 0, 8 * sizeof(unsigned int)));
+    }
     if (p2p && !v.bnd.empty()) {
       std::map<std::pair<int, int>, int> ent;
       for (size_t e = 0; e < ns; e++)
@@ -605,8 +732,6 @@ int comm_alloc_level_buffers(CupCtx *c) {
       v.order.insert(v.order.end(), v.inner.begin(), v.inner.end());
       CUP_TRY(up(&v.d_bsend, v.bsend));
       CUP_TRY(up(&v.d_order, v.order));
-      CUP_CUDA(cudaMalloc((void **)&v.d_counters, 2 * sizeof(unsigned int)));
-      CUP_CUDA(cudaMemset(v.d_counters, 0, 2 * sizeof(unsigned int)));
     }
     v.p2p = p2p;
     v.rface_stride = p2p ? (long long)nr * 64 : 0;
@@ -615,7 +740,39 @@ int comm_alloc_level_buffers(CupCtx *c) {
   return CUP_OK;
 }
 
-static int post(CupCtx *c, Level &v, int kind) {
+// ---- descriptors for kernels that wait / post themselves (one-sided transport only) ----
+enum { CNT_PACK = 2, CNT_DOWN = 3, CNT_GET = 4, CNT_UP = 5, CNT_SLAB = 6 };
+
+static WaitDesc make_wait(CupCtx *c, const Level &v, int kind) {
+  WaitDesc w;
+  Comm *cm = (Comm *)c->comm;
+  if (!cm || !v.p2p || v.rpeers[kind].empty())
+    return w;
+  w.seq = cm->d_seq + (size_t)v.L * 3 + kind;
+  w.flags = (const unsigned long long *)cm->win + ((size_t)v.L * 3 + kind) * c->nranks;
+  w.peers = v.d_rpeers[kind];
+  w.np = (int)v.rpeers[kind].size();
+  w.err = c->h_err;
+  w.code = 1 + v.L * 4 + kind;
+  return w;
+}
+
+static PostDesc make_post(CupCtx *c, const Level &v, int kind, int counter) {
+  PostDesc p;
+  Comm *cm = (Comm *)c->comm;
+  if (!cm || !v.p2p)
+    return p;
+  p.seq = cm->d_seq + (size_t)v.L * 3 + kind;
+  p.peer_win = cm->d_peer_win;
+  p.peers = v.d_speers[kind];
+  p.np = (int)v.speers[kind].size();
+  p.flag_index = ((size_t)v.L * 3 + kind) * c->nranks + c->rank;
+  p.counter = v.d_counters + counter;
+  return p;
+}
+
+// bump the sequence number of an exchange this rank takes part in without sending anything
+static int post_empty(CupCtx *c, Level &v, int kind) {
   Comm *cm = (Comm *)c->comm;
   const size_t fidx = ((size_t)v.L * 3 + kind) * c->nranks + c->rank;
   k_signal<<<1, 64, 0, c->stream>>>(cm->d_seq + (size_t)v.L * 3 + kind, cm->d_peer_win, v.d_speers[kind],
@@ -625,14 +782,16 @@ static int post(CupCtx *c, Level &v, int kind) {
 }
 
 static int wait(CupCtx *c, Level &v, int kind) {
-  Comm *cm = (Comm *)c->comm;
-  if (v.rpeers[kind].empty())
+  const WaitDesc w = make_wait(c, v, kind);
+  if (!w.seq)
     return CUP_OK;
-  const unsigned long long *flags = (const unsigned long long *)cm->win + ((size_t)v.L * 3 + kind) * c->nranks;
-  k_wait<<<1, 64, 0, c->stream>>>(cm->d_seq + (size_t)v.L * 3 + kind, flags, v.d_rpeers[kind],
-                                  (int)v.rpeers[kind].size());
+  k_wait<<<1, 64, 0, c->stream>>>(w);
   c->launches++;
   return CUP_OK;
+}
+
+static bool level_has_faces(const CupCtx *c, const Level &v) {
+  return c->nranks > 1 && (!v.face_sslot.empty() || v.nface_recv > 0);
 }
 
 bool comm_fused_desc(CupCtx *c, Level &v, FusedComm *out) {
@@ -652,11 +811,20 @@ bool comm_fused_desc(CupCtx *c, Level &v, FusedComm *out) {
   out->flag_index = ((size_t)v.L * 3 + K_FACE) * c->nranks + c->rank;
   out->counters = v.d_counters;
   out->nbnd = (int)v.bnd.size();
+  out->err = c->h_err;
+  out->code = 1 + v.L * 4 + K_FACE;
   return true;
 }
 
-static bool level_has_faces(const CupCtx *c, const Level &v) {
-  return c->nranks > 1 && (!v.face_sslot.empty() || v.nface_recv > 0);
+// what a kernel that consumes / produces an exchange itself needs (empty descriptors elsewhere)
+WaitDesc comm_wait_desc(CupCtx *c, Level &v, int kind) { return make_wait(c, v, kind); }
+PostDesc comm_post_desc(CupCtx *c, Level &v, int kind) {
+  // only kinds whose producer is a single kernel: restriction (k_down) and the faces after k_up
+  if (kind == K_RES && sum(v.res_scnt) == 0)
+    return PostDesc{};
+  if (kind == K_FACE && !level_has_faces(c, v))
+    return PostDesc{};
+  return make_post(c, v, kind, kind == K_RES ? CNT_DOWN : CNT_UP);
 }
 
 // publish the ghost faces of `u` (this rank's boundary blocks of level v) to their consumers
@@ -666,14 +834,16 @@ int halo_post(CupCtx *c, Level &v, SlotVec<Real> u) {
     return CUP_OK;
   const int ns = (int)v.face_sslot.size();
   if (ns) {
+    // one-sided: the pack kernel stores into the peers' windows and its last CTA publishes
     k_pack_faces<Real><<<cgrid(c, ns), 64, 0, c->stream>>>(v.d_face_sslot, v.d_face_splane, ns, u,
                                                            (Real *const *)v.d_fptr0, (Real *const *)v.d_fptr1,
-                                                           (const unsigned long long *)v.d_seq);
+                                                           (const unsigned long long *)v.d_seq,
+                                                           make_post(c, v, K_FACE, CNT_PACK));
     c->launches++;
+  } else if (v.p2p) {
+    CUP_TRY(post_empty(c, v, K_FACE));
   }
-  if (v.p2p)
-    CUP_TRY(post(c, v, K_FACE));
-  else
+  if (!v.p2p)
     CUP_TRY(exchange(c, v.d_fsend, v.face_scnt, v.d_frecv, v.face_rcnt, 64 * sizeof(Real)));
   CUP_CUDA(cudaGetLastError());
   return CUP_OK;
@@ -693,49 +863,54 @@ int slab_exchange(CupCtx *c, Level &v, const SlabSrc<Real> &src, int ncomp, int 
   if (ns) {
     k_pack_slabs<Real><<<cgrid(c, ns), 64, 0, c->stream>>>(v.d_face_sslot, v.d_face_splane, ns, src, ncomp, nlayer,
                                                            (Real *const *)v.d_sptr0, (Real *const *)v.d_sptr1,
-                                                           (const unsigned long long *)v.d_seq);
+                                                           (const unsigned long long *)v.d_seq,
+                                                           make_post(c, v, K_FACE, CNT_SLAB));
     c->launches++;
+  } else if (v.p2p) {
+    CUP_TRY(post_empty(c, v, K_FACE));
   }
-  if (v.p2p) {
-    CUP_TRY(post(c, v, K_FACE));
+  if (v.p2p)
     CUP_TRY(wait(c, v, K_FACE));
-  } else {
+  else
     CUP_TRY(exchange(c, v.d_ssend, v.face_scnt, v.d_srecv, v.face_rcnt, 64 * SLAB_PLANES * sizeof(Real)));
-  }
   CUP_CUDA(cudaGetLastError());
   return CUP_OK;
 }
 
-// the faces posted last are complete in this rank's receive area
+// the faces posted last are complete in this rank's receive area (stand-alone wait kernel: for
+// consumers that do not wait themselves)
 int halo_wait(CupCtx *c, Level &v) {
   if (!level_has_faces(c, v) || !v.p2p)
     return CUP_OK;
   return wait(c, v, K_FACE);
 }
 
-// after k_down stored the children with remote parents through v.d_rptr
+// after k_down stored the children with remote parents through v.d_rptr.  `posted`: the kernel
+// published the exchange itself (comm_post_desc(K_RES) was non-empty)
 template <typename Real>
-int restrict_exchange(CupCtx *c, Level &v, SlotVec<Real> f, SlotVec<Real> u) {
+int restrict_exchange(CupCtx *c, Level &v, SlotVec<Real> f, SlotVec<Real> u, bool posted) {
   if (c->nranks == 1)
     return CUP_OK;
   const int cr = sum(v.res_rcnt), cs = sum(v.res_scnt);
   if (cr == 0 && cs == 0)
     return CUP_OK;
   if (v.p2p) {
-    CUP_TRY(post(c, v, K_RES));
-    CUP_TRY(wait(c, v, K_RES));
+    if (!posted)
+      CUP_TRY(post_empty(c, v, K_RES));  // also the plain signal when k_down ran without a descriptor
   } else {
     CUP_TRY(exchange(c, v.d_rsend, v.res_scnt, v.d_rrecv, v.res_rcnt, 128 * sizeof(Real)));
   }
   if (cr) {
-    k_put<Real><<<cgrid(c, cr), 64, 0, c->stream>>>(v.d_res_rslot, v.d_res_roct, cr, (const Real *)v.d_rrecv, f, u);
+    k_put<Real><<<cgrid(c, cr), 64, 0, c->stream>>>(v.d_res_rslot, v.d_res_roct, cr, (const Real *)v.d_rrecv, f, u,
+                                                    make_wait(c, v, K_RES));
     c->launches++;
   }
   CUP_CUDA(cudaGetLastError());
   return CUP_OK;
 }
 
-// before k_up: parents' owners send u_c - us to remote children; lands in v.d_precv
+// before k_up: parents' owners send u_c - us to remote children; lands in v.d_precv.  In one-sided
+// mode the consumer (k_up) waits itself with comm_wait_desc(K_PRO).
 template <typename Real>
 int prolong_exchange(CupCtx *c, Level &v, SlotVec<Real> u, SlotVec<Real> us) {
   if (c->nranks == 1)
@@ -744,15 +919,14 @@ int prolong_exchange(CupCtx *c, Level &v, SlotVec<Real> u, SlotVec<Real> us) {
   if (cr == 0 && cs == 0)
     return CUP_OK;
   if (cr) {
-    k_get<Real><<<cgrid(c, cr), 64, 0, c->stream>>>(v.d_res_rslot, v.d_res_roct, cr, u, us, (Real *const *)v.d_pptr);
+    k_get<Real><<<cgrid(c, cr), 64, 0, c->stream>>>(v.d_res_rslot, v.d_res_roct, cr, u, us, (Real *const *)v.d_pptr,
+                                                    make_post(c, v, K_PRO, CNT_GET));
     c->launches++;
+  } else if (v.p2p) {
+    CUP_TRY(post_empty(c, v, K_PRO));
   }
-  if (v.p2p) {
-    CUP_TRY(post(c, v, K_PRO));
-    CUP_TRY(wait(c, v, K_PRO));
-  } else {
+  if (!v.p2p)
     CUP_TRY(exchange(c, v.d_rrecv, v.res_rcnt, v.d_precv, v.res_scnt, 64 * sizeof(Real)));
-  }
   CUP_CUDA(cudaGetLastError());
   return CUP_OK;
 }
@@ -761,8 +935,8 @@ template int slab_exchange<double>(CupCtx *, Level &, const SlabSrc<double> &, i
 template int slab_exchange<float>(CupCtx *, Level &, const SlabSrc<float> &, int, int);
 template int halo_post<double>(CupCtx *, Level &, SlotVec<double>);
 template int halo_post<float>(CupCtx *, Level &, SlotVec<float>);
-template int restrict_exchange<double>(CupCtx *, Level &, SlotVec<double>, SlotVec<double>);
-template int restrict_exchange<float>(CupCtx *, Level &, SlotVec<float>, SlotVec<float>);
+template int restrict_exchange<double>(CupCtx *, Level &, SlotVec<double>, SlotVec<double>, bool);
+template int restrict_exchange<float>(CupCtx *, Level &, SlotVec<float>, SlotVec<float>, bool);
 template int prolong_exchange<double>(CupCtx *, Level &, SlotVec<double>, SlotVec<double>);
 template int prolong_exchange<float>(CupCtx *, Level &, SlotVec<float>, SlotVec<float>);
 

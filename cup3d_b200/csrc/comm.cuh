@@ -2,6 +2,7 @@
 #pragma once
 #include <vector>
 
+#include "comm_dev.cuh"
 #include "cup_internal.h"
 #include "mg_device.cuh"
 namespace cup {
@@ -30,8 +31,14 @@ struct SlabSrc {
 };
 template <typename Real>
 int slab_exchange(CupCtx *c, Level &v, const SlabSrc<Real> &src, int ncomp, int nlayer);
+// `posted`: k_down published the exchange itself (it ran with comm_post_desc(c, v, COMM_RES))
 template <typename Real>
-int restrict_exchange(CupCtx *c, Level &v, SlotVec<Real> f, SlotVec<Real> u);
+int restrict_exchange(CupCtx *c, Level &v, SlotVec<Real> f, SlotVec<Real> u, bool posted = false);
+// one-sided transport: descriptors for kernels that wait for / publish an exchange themselves
+// (empty descriptors -- null seq -- on one rank, in NCCL mode, or when there is nothing to do)
+enum { COMM_FACE = 0, COMM_RES = 1, COMM_PRO = 2 };
+WaitDesc comm_wait_desc(CupCtx *c, Level &v, int kind);
+PostDesc comm_post_desc(CupCtx *c, Level &v, int kind);
 template <typename Real>
 int prolong_exchange(CupCtx *c, Level &v, SlotVec<Real> u, SlotVec<Real> us);
 }  // namespace cup

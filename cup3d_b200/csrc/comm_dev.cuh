@@ -1,0 +1,137 @@
+// comm_dev.cuh -- device side of the one-sided (peer window) transport (comm.cu).
+//
+// Every exchange kind of every multigrid level has a SEQUENCE NUMBER in this rank's device memory
+// (how many times this rank has posted it) and one FLAG WORD per peer in this rank's receive
+// window (how many times that peer has posted it).  Both sides of an exchange post equally often,
+// so "the data of my n-th post's counterpart has arrived" == "flag[peer] >= n".
+//
+//   producer kernel: all CTAs store into the peers' windows, then comm_post_at_exit():
+//                    the LAST CTA to retire bumps the sequence number and writes it into the
+//                    peers' flag words -- no separate signal kernel;
+//   consumer kernel: one thread runs comm_wait() before the first read of received data --
+//                    no separate wait kernel.
+//
+// A wait that does not complete within COMM_SPIN_MAX polls (several seconds: a peer died or the
+// protocol is broken) records a code in a host-visible error word and RETURNS; the host reports
+// it as CUP_ERR_COMM at the next synchronisation instead of the context being poisoned by a trap.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace cup {
+
+enum { COMM_SPIN_MAX = 1 << 25 };
+
+struct WaitDesc {
+  const unsigned long long *seq = nullptr;    // this rank's sequence number; null: nothing to wait for
+  const unsigned long long *flags = nullptr;  // [nranks] flag words of this (level, kind) in the own window
+  const int *peers = nullptr;                 // ranks to wait for
+  int np = 0;
+  int *err = nullptr;                         // mapped host word
+  int code = 0;                               // what to record on a timeout
+};
+
+struct PostDesc {
+  unsigned long long *seq = nullptr;  // null: nothing to post
+  char *const *peer_win = nullptr;    // base of every rank's window
+  const int *peers = nullptr;         // ranks to notify
+  int np = 0;
+  size_t flag_index = 0;              // index of this rank's flag word inside a peer's window
+  unsigned int *counter = nullptr;    // CTAs retired (re-armed by the last one)
+};
+
+// order generic-proxy reads/writes (the flag acquire) before async-proxy (TMA) reads of the data
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// ONE thread: wait until every listed peer has posted at least `want` times
+__device__ __forceinline__ void comm_wait_for(const WaitDesc &w, unsigned long long want) {
+  for (int i = 0; i < w.np; i++) {
+    const volatile unsigned long long *f = w.flags + w.peers[i];
+    int spins = 0;
+    while (*f < want) {
+      __nanosleep(100);
+      if (++spins > COMM_SPIN_MAX) {
+        if (w.err)
+          *(volatile int *)w.err = w.code ? w.code : 1;  // mapped host memory: a plain store, no PCIe atomic
+        break;
+      }
+    }
+  }
+  __threadfence_system();
+  fence_proxy_async();
+}
+
+// whole CTA, at the top of a consumer kernel (before any read of received data)
+__device__ __forceinline__ void comm_wait_cta(const WaitDesc &w) {
+  if (w.seq == nullptr)
+    return;
+  if (threadIdx.x == 0)
+    comm_wait_for(w, *(const volatile unsigned long long *)w.seq);
+  __syncthreads();
+}
+
+// whole CTA, after its last store of posted data (every CTA of the grid must call it)
+__device__ __forceinline__ void comm_post_at_exit(const PostDesc &p) {
+  if (p.seq == nullptr)
+    return;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int old = atomicAdd(p.counter, 1u);
+    if (old == gridDim.x - 1) {
+      *p.counter = 0;
+      const unsigned long long s = *(volatile unsigned long long *)p.seq + 1;
+      __threadfence_system();
+      for (int i = 0; i < p.np; i++) {
+        volatile unsigned long long *f = (volatile unsigned long long *)p.peer_win[p.peers[i]] + p.flag_index;
+        *f = s;
+      }
+      *(volatile unsigned long long *)p.seq = s;
+      __threadfence();
+    }
+  }
+}
+
+// Store the boundary planes of a block's NEW values (thread t = x + 8y holds the z-line v[0..7])
+// into the neighbours' owners' windows: bs[f] = send entry of plane f or -1, fp = per-entry
+// destination of the exchange being posted.  Plane element order as load_halo expects.
+template <typename Real>
+__device__ __forceinline__ void push_faces(const int *__restrict__ bs, void *const *__restrict__ fp,
+                                           const Real (&v)[8], int t, int x, int y) {
+  const int e0 = bs[0], e1 = bs[1], e2 = bs[2], e3 = bs[3], e4 = bs[4], e5 = bs[5];
+  if (e4 >= 0)
+    ((Real *)fp[e4])[t] = v[0];
+  if (e5 >= 0)
+    ((Real *)fp[e5])[t] = v[7];
+  if (e2 >= 0 && y == 0) {
+    Real *d = (Real *)fp[e2];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      d[k * 8 + x] = v[k];
+  }
+  if (e3 >= 0 && y == 7) {
+    Real *d = (Real *)fp[e3];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      d[k * 8 + x] = v[k];
+  }
+  if (e0 >= 0 && x == 0) {
+    Real *d = (Real *)fp[e0];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      d[k * 8 + y] = v[k];
+  }
+  if (e1 >= 0 && x == 7) {
+    Real *d = (Real *)fp[e1];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      d[k * 8 + y] = v[k];
+  }
+}
+
+// read of data another GPU stored into this rank's window: never through a possibly stale L1 line
+template <typename Real>
+__device__ __forceinline__ Real ld_recv(const Real *p) {
+  return __ldcg(p);
+}
+
+}  // namespace cup

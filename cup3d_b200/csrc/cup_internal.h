@@ -98,7 +98,8 @@ struct Level {
   // fused sweep + exchange (smooth_tma.cu): work order = boundary blocks first, then interior
   std::vector<int> order, bsend;           // [nact] act indices; [nact][6] send entry of (block, plane) or -1
   int *d_order = nullptr, *d_bsend = nullptr;
-  unsigned int *d_counters = nullptr;      // [2] retired boundary blocks / CTAs
+  unsigned int *d_counters = nullptr;      // [8]: [0] retired boundary blocks, [1] retired CTAs (fused sweep);
+                                           // [2..7] retired CTAs of the other posting kernels (comm_dev.cuh)
   // fused prolongation (UpFuse, smooth_tma.cuh): [nact][7] parent index/octant of own + face neighbours
   std::vector<int> upinfo;
   int *d_upinfo = nullptr;
@@ -139,6 +140,7 @@ struct CupCtx {
   int rank = 0, nranks = 1;
   std::vector<long long> win_reals;  // [nranks] receive-window sizes (Reals)
   void *comm = nullptr;            // cup::Comm (comm.cu)
+  int *h_err = nullptr;            // pinned + mapped: nonzero after a peer-flag wait timed out (comm_dev.cuh)
   int top = -1;
   int bpd[3] = {1, 1, 1};
   int level_max = 1;
@@ -165,6 +167,12 @@ struct CupCtx {
   void *obst = nullptr;         // cup::Obstacles (obstacle.cu)
   void *io_buf = nullptr;       // io_dump packing: 5 floats per cell (allocated on first use)
   bool keep_tmp_udef = false;   // projection(): F_TMP already holds fish_tmpv()'s udef
+  // stencil_run(st, list, n) (main.c:3631): the caller's block list on the device while a listed
+  // sweep runs; d_list holds 2*nblk ints (the list, and its split into regular / interface blocks)
+  int *d_list = nullptr;
+  const int *run_sub = nullptr;
+  int run_nsub = -1;            // < 0: no list, sweep every block
+  std::vector<int> run_list;    // host copy of the current list
 };
 
 namespace cup {
@@ -211,6 +219,8 @@ void free_obstacles(CupCtx *c);
 
 // comm.cu
 int comm_init(CupCtx *c, int rank, int nranks, const void *id, size_t id_bytes);
+int comm_init_host(CupCtx *c, int rank, int nranks, CupAllgatherFn fn, void *user);
+int comm_check_error(CupCtx *c);  // after a stream synchronisation: CUP_ERR_COMM if a wait timed out
 int comm_unique_id(void *out, size_t bytes);
 
 enum { SCAL_N = 256, SLAB_PLANES = 9 };  // 3 components x 3 layers (k_advdiff) is the largest slab

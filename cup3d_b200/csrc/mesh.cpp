@@ -591,6 +591,10 @@ void free_mesh(CupCtx *c) {
     cudaFree(v.d_hvals);
     v = Level();
   }
+  cudaFree(c->d_list);
+  c->d_list = nullptr;
+  c->run_sub = nullptr;
+  c->run_nsub = -1;
   c->blk.clear();
   c->nblk = c->nslot = 0;
   c->top = -1;

@@ -50,7 +50,14 @@ struct LevelView {
   // ghost slabs received from other ranks (stencil sweeps): [face][SLAB planes][64], double buffered
   const void *rslab;
   long long rslab_stride;
+  // optional work list (stencil_run(st, list, n), main.c:3631): the sweep visits act[] indices
+  // sub[0..nsub) (or 0..nsub-1 when sub is null); nsub < 0: all nact blocks
+  const int *sub = nullptr;
+  int nsub = -1;
 };
+
+__device__ __forceinline__ int lv_count(const LevelView &lv) { return lv.nsub >= 0 ? lv.nsub : lv.nact; }
+__device__ __forceinline__ int lv_item(const LevelView &lv, int i) { return lv.sub ? lv.sub[i] : i; }
 
 enum { kSlabPlanes = 9 };
 template <typename Real>
@@ -174,7 +181,7 @@ __device__ __forceinline__ void load_halo(const SlotVec<Real> &u, const Real *ow
   for (int f = 0; f < 6; f++) {
     const int nb = nbr6[f];
     if (nb <= kRemote0) {  // packed by the owner in exactly this (a, c) order
-      halo[f][t] = rface[(size_t)(kRemote0 - nb) * 64 + t];
+      halo[f][t] = __ldcg(rface + (size_t)(kRemote0 - nb) * 64 + t);  // stored by another GPU: not through L1
       continue;
     }
     const Real *src = nb >= 0 ? u.at(nb) : own;

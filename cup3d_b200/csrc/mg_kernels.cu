@@ -19,6 +19,7 @@
 #include "stencil7_tma.cuh"
 #include "amr_kernels.cuh"
 #include "comm.cuh"
+#include "comm_dev.cuh"
 
 namespace cup {
 
@@ -101,11 +102,12 @@ __global__ void __launch_bounds__(TPB, MINB) k_smooth(LevelView lv, SlotVec<Real
 template <typename Real>
 __global__ void __launch_bounds__(TPB) k_down(LevelView lv, const int *__restrict__ pslot,
                                               const int *__restrict__ oct, SlotVec<Real> u, SlotVec<Real> f, Real h,
-                                              Real *const *__restrict__ rptr) {
+                                              Real *const *__restrict__ rptr, WaitDesc wait, PostDesc post) {
   __shared__ Real tu[512];
   __shared__ Real tr[512];
   __shared__ Real halo[6][64];
   const int t = threadIdx.x, x = t & 7, y = t >> 3;
+  comm_wait_cta(wait);
   for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
     const int slot = lv.act[b];
     const Real *ub = u.at(slot);
@@ -146,6 +148,7 @@ __global__ void __launch_bounds__(TPB) k_down(LevelView lv, const int *__restric
     }
     __syncthreads();
   }
+  comm_post_at_exit(post);
 }
 
 // ---------------------------------------------------------------------------
@@ -156,11 +159,12 @@ __global__ void __launch_bounds__(TPB) k_down(LevelView lv, const int *__restric
 template <typename Real, bool TAU>
 __global__ void __launch_bounds__(TPB) k_apply(LevelView lv, const int *__restrict__ sub, int nsub, SlotVec<Real> u,
                                                SlotVec<Real> out, SlotVec<Real> us, Real h,
-                                               const double *__restrict__ shift, Real h3) {
+                                               const double *__restrict__ shift, Real h3, WaitDesc wait) {
   __shared__ Real tu[512];
   __shared__ Real halo[6][64];
   const int t = threadIdx.x, x = t & 7, y = t >> 3;
   const Real add = shift ? (Real)(*shift) * h3 : (Real)0;
+  comm_wait_cta(wait);
   for (int i = blockIdx.x; i < nsub; i += gridDim.x) {
     const int b = sub ? sub[i] : i;
     const int slot = lv.act[b];
@@ -194,10 +198,24 @@ __global__ void __launch_bounds__(TPB) k_apply(LevelView lv, const int *__restri
 // ---------------------------------------------------------------------------
 // Prolongation (mg_up/mg_get/mg_add, :4771-4807): u_f += (u_c - us) of the
 // parent cell, piecewise-constant injection.
+// One-sided transport: the kernel waits for the corrections of remote parents itself, stores the
+// new boundary planes of u straight into the neighbours' owners' windows (as the fused sweep
+// does) and its last CTA publishes them -- no pack / signal / wait kernels around it.
+struct UpComm {
+  const int *bsend = nullptr;                        // [nact][6] face-send entry or -1 (null: no face push)
+  void *const *fptr0 = nullptr, *const *fptr1 = nullptr;
+  const unsigned long long *face_seq = nullptr;      // parity of the exchange being posted
+};
+
 template <typename Real>
 __global__ void __launch_bounds__(TPB) k_up(LevelView lv, const int *__restrict__ pslot, const int *__restrict__ oct,
-                                            SlotVec<Real> u, SlotVec<Real> us, const Real *__restrict__ precv) {
+                                            SlotVec<Real> u, SlotVec<Real> us, const Real *__restrict__ precv,
+                                            WaitDesc wait, UpComm uc, PostDesc post) {
   const int t = threadIdx.x, x = t & 7, y = t >> 3;
+  comm_wait_cta(wait);
+  void *const *fp = nullptr;
+  if (uc.bsend)
+    fp = ((*(const volatile unsigned long long *)uc.face_seq + 1) & 1) ? uc.fptr1 : uc.fptr0;
   for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
     const int slot = lv.act[b], ps = pslot[b], o = oct[b];
     Real *ub = u.at(slot);
@@ -213,12 +231,18 @@ __global__ void __launch_bounds__(TPB) k_up(LevelView lv, const int *__restrict_
       const Real *q = precv + (size_t)(kRemote0 - ps) * 64;
 #pragma unroll
       for (int kz = 0; kz < 4; kz++)
-        d[kz] = q[(kz * 4 + (y >> 1)) * 4 + (x >> 1)];
+        d[kz] = ld_recv(q + (kz * 4 + (y >> 1)) * 4 + (x >> 1));
     }
+    Real v[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++)
-      ub[k * 64 + t] += d[k >> 1];
+    for (int k = 0; k < 8; k++) {
+      v[k] = ub[k * 64 + t] + d[k >> 1];
+      ub[k * 64 + t] = v[k];
+    }
+    if (fp)
+      push_faces<Real>(uc.bsend + (size_t)b * 6, fp, v, t, x, y);
   }
+  comm_post_at_exit(post);
 }
 
 // ---------------------------------------------------------------------------
@@ -579,7 +603,12 @@ int vcycle_t(CupCtx *c, const Real *d_in, Real *d_out) {
     // levels start from the restricted u (FAS).
     CUP_TRY(smooth_level<Real>(c, v, MG_PRE, a, L == top, nullptr));
     g_tr.mark(c, "L" + std::to_string(L) + " pre");
-    CUP_TRY(halo_wait(c, v));  // faces of u0 were posted by the last sweep
+    // faces of u0 were posted by the last sweep.  One-sided transport on a uniform level: k_down waits for
+    // them itself and publishes the children of remote parents when its last CTA retires
+    const WaitDesc dwait = v.uniform ? comm_wait_desc(c, v, COMM_FACE) : WaitDesc{};
+    const PostDesc dpost = v.uniform ? comm_post_desc(c, v, COMM_RES) : PostDesc{};
+    if (!dwait.seq)
+      CUP_TRY(halo_wait(c, v));
     if (!v.act.empty()) {
       const int grid = grid_for(c, (long long)v.act.size(), 12);
       if (!v.uniform && smooth_use_tma() && amr_split() && !v.reg.empty()) {
@@ -593,17 +622,20 @@ int vcycle_t(CupCtx *c, const Real *d_in, Real *d_out) {
       } else if (!v.uniform)
         CUP_TRY(down_amr_launch<Real>(c, view(v), v.d_pslot, v.d_oct, a.u0, a.f, (Real)v.h));
       else if (smooth_use_tma())
-        CUP_TRY(down_tma_launch<Real>(c, view(v), v.d_pslot, v.d_oct, a.u0, a.f, (Real)v.h, v.d_rptr));
+        CUP_TRY(down_tma_launch<Real>(c, view(v), v.d_pslot, v.d_oct, a.u0, a.f, (Real)v.h, v.d_rptr, nullptr, -1,
+                                      &dwait, &dpost));
       else
         k_down<Real><<<grid, TPB, 0, c->stream>>>(view(v), v.d_pslot, v.d_oct, a.u0, a.f, (Real)v.h,
-                                                   (Real *const *)v.d_rptr);
+                                                   (Real *const *)v.d_rptr, dwait, dpost);
       c->launches++;
     }
     g_tr.mark(c, "L" + std::to_string(L) + " down");
-    CUP_TRY(restrict_exchange<Real>(c, v, a.f, a.u0));
+    CUP_TRY(restrict_exchange<Real>(c, v, a.f, a.u0, dpost.seq != nullptr && !v.act.empty()));
     Level &w = c->lv[L - 1];
     CUP_TRY(halo_post<Real>(c, w, a.u0));  // restricted u: consumed by tau and by the first sweep of level L-1
-    CUP_TRY(halo_wait(c, w));
+    const WaitDesc twait = (w.uniform && !w.par.empty()) ? comm_wait_desc(c, w, COMM_FACE) : WaitDesc{};
+    if (!twait.seq)
+      CUP_TRY(halo_wait(c, w));
     if (!w.par.empty()) {
       const int gridw = grid_for(c, (long long)w.par.size(), 12);
       if (!w.uniform && smooth_use_tma() && amr_split()) {
@@ -620,10 +652,10 @@ int vcycle_t(CupCtx *c, const Real *d_in, Real *d_out) {
                                        nullptr, 1));
       else if (smooth_use_tma())
         CUP_TRY(apply_tma_launch<Real>(c, view(w), w.d_par, (int)w.par.size(), a.u0, a.f, a.us, (Real)w.h, nullptr,
-                                       (Real)0, true));
+                                       (Real)0, true, &twait));
       else
         k_apply<Real, true><<<gridw, TPB, 0, c->stream>>>(view(w), w.d_par, (int)w.par.size(), a.u0, a.f, a.us,
-                                                           (Real)w.h, nullptr, (Real)0);
+                                                           (Real)w.h, nullptr, (Real)0, twait);
       c->launches++;
     }
     g_tr.mark(c, "L" + std::to_string(L) + " res+tau");
@@ -671,12 +703,28 @@ bottom_done:
       continue;
     }
     CUP_TRY(prolong_exchange<Real>(c, v, a.u0, a.us));
-    if (!v.act.empty()) {
-      const int grid = grid_for(c, (long long)v.act.size(), 16);
-      k_up<Real><<<grid, TPB, 0, c->stream>>>(view(v), v.d_pslot, v.d_oct, a.u0, a.us, (const Real *)v.d_precv);
-      c->launches++;
+    {
+      // one-sided transport: k_up waits for the corrections itself, pushes its new boundary planes and publishes
+      const WaitDesc uwait = comm_wait_desc(c, v, COMM_PRO);
+      FusedComm fc;
+      UpComm uc;
+      PostDesc upost;
+      if (!v.act.empty() && v.uniform && fused_ok() && comm_fused_desc(c, v, &fc)) {
+        uc.bsend = fc.bsend;
+        uc.fptr0 = fc.fptr0;
+        uc.fptr1 = fc.fptr1;
+        uc.face_seq = fc.seq;
+        upost = comm_post_desc(c, v, COMM_FACE);
+      }
+      if (!v.act.empty()) {
+        const int grid = grid_for(c, (long long)v.act.size(), 16);
+        k_up<Real><<<grid, TPB, 0, c->stream>>>(view(v), v.d_pslot, v.d_oct, a.u0, a.us, (const Real *)v.d_precv, uwait,
+                                                 uc, upost);
+        c->launches++;
+      }
+      if (!upost.seq)
+        CUP_TRY(halo_post<Real>(c, v, a.u0));
     }
-    CUP_TRY(halo_post<Real>(c, v, a.u0));
     g_tr.mark(c, "L" + std::to_string(L) + " up");
     CUP_TRY(smooth_level<Real>(c, v, MG_POST, a, false, nullptr));
     g_tr.mark(c, "L" + std::to_string(L) + " post");
@@ -738,14 +786,17 @@ int pois_op_t(CupCtx *c, const Real *d_in, Real *d_out) {
   SlotVec<Real> u{const_cast<Real *>(d_in), nullptr, nleaf}, o{d_out, nullptr, nleaf}, us{nullptr, nullptr, nleaf};
   CUP_TRY(halo_exchange<Real>(c, v, u));
   const Real h = (Real)v.h;
+  // stencil_run(&st_lhs / &st_mg, list, n): only the listed blocks (cup_stencil_run)
+  const int *sub = c->run_nsub >= 0 ? c->run_sub : nullptr;
+  const int nsub = c->run_nsub >= 0 ? c->run_nsub : (int)v.act.size();
   if (!c->leaf_uniform)  // k_lhs + fc_fill on all leaves, per-block h
-    CUP_TRY(apply_amr_launch<Real>(c, view(v), nullptr, (int)v.act.size(), u, o, us, h, v.d_hblk, shift,
+    CUP_TRY(apply_amr_launch<Real>(c, view(v), sub, nsub, u, o, us, h, v.d_hblk, shift,
                                    c->no_flux_correction ? 0 : 2));
   else if (smooth_use_tma())
-    CUP_TRY(apply_tma_launch<Real>(c, view(v), nullptr, (int)v.act.size(), u, o, us, h, shift, h * h * h, false));
+    CUP_TRY(apply_tma_launch<Real>(c, view(v), sub, nsub, u, o, us, h, shift, h * h * h, false));
   else
-    k_apply<Real, false><<<grid_for(c, c->nblk, 16), TPB, 0, c->stream>>>(view(v), nullptr, (int)v.act.size(), u, o,
-                                                                           us, h, shift, h * h * h);
+    k_apply<Real, false><<<grid_for(c, c->nblk, 16), TPB, 0, c->stream>>>(view(v), sub, nsub, u, o, us, h, shift,
+                                                                           h * h * h, WaitDesc{});
   c->launches++;
   if (mc == 1 || mc > 2) {
     const long long pin = c->pin_local;  // pois_pin: block (0,0,0), main.c:4888 (on its owner only)

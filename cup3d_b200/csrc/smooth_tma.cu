@@ -22,6 +22,7 @@
 #include "mg_device.cuh"
 #include "smooth_tma.cuh"
 #include "stencil7_tma.cuh"
+#include "comm_dev.cuh"
 #include "tma.cuh"
 
 namespace cup {
@@ -149,16 +150,15 @@ __global__ void __launch_bounds__(TPB, UPF ? 10 : 12)
   int i = blockIdx.x;
   if (COMM && t == 0 && i < fc.nbnd) {
     // this CTA starts with blocks that read received faces: wait until every peer has published seq0
-    for (int p = 0; p < fc.nrp; p++) {
-      const volatile unsigned long long *f = fc.my_flags + fc.rpeers[p];
-      long long spins = 0;
-      while (*f < seq0) {
-        __nanosleep(32);
-        if (++spins > (1LL << 26))
-          __trap();
-      }
-    }
-    __threadfence_system();
+    // (acquire at system scope, then a proxy fence: the faces are read by the TMA engine)
+    WaitDesc w;
+    w.seq = fc.seq;
+    w.flags = fc.my_flags;
+    w.peers = fc.rpeers;
+    w.np = fc.nrp;
+    w.err = fc.err;
+    w.code = fc.code;
+    comm_wait_for(w, seq0);
   }
   if (t == 0 && i < nsub) {
     const int b0 = sub ? sub[i] : i;
@@ -283,36 +283,7 @@ __global__ void __launch_bounds__(TPB, UPF ? 10 : 12)
     if (COMM && i < fc.nbnd) {
       // push the new boundary planes to the neighbours' owners (plane order as load_halo expects)
       void *const *fp = ((seq0 + 1) & 1) ? fc.fptr1 : fc.fptr0;
-      const int *bs = fc.bsend + (size_t)b * 6;
-      const int e0 = bs[0], e1 = bs[1], e2 = bs[2], e3 = bs[3], e4 = bs[4], e5 = bs[5];
-      if (e4 >= 0)
-        ((Real *)fp[e4])[t] = v[0];
-      if (e5 >= 0)
-        ((Real *)fp[e5])[t] = v[7];
-      if (e2 >= 0 && y == 0) {
-        Real *d = (Real *)fp[e2];
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-          d[k * 8 + x] = v[k];
-      }
-      if (e3 >= 0 && y == 7) {
-        Real *d = (Real *)fp[e3];
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-          d[k * 8 + x] = v[k];
-      }
-      if (e0 >= 0 && x == 0) {
-        Real *d = (Real *)fp[e0];
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-          d[k * 8 + y] = v[k];
-      }
-      if (e1 >= 0 && x == 7) {
-        Real *d = (Real *)fp[e1];
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-          d[k * 8 + y] = v[k];
-      }
+      push_faces<Real>(fc.bsend + (size_t)b * 6, fp, v, t, x, y);
       if (i + G >= fc.nbnd) {
         // that was this CTA's last boundary block: retire them; whoever retires the last one of
         // the whole grid publishes the new sequence number to the peers

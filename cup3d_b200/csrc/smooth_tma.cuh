@@ -23,6 +23,8 @@ struct FusedComm {
   size_t flag_index;                   // index of this rank's flag word in a peer's window
   unsigned int *counters;              // [0] boundary blocks retired, [1] CTAs retired
   int nbnd;
+  int *err;                            // host-visible error word (comm_dev.cuh)
+  int code;
 };
 
 // Fused prolongation (mg_up/mg_up2, main.c:4787-4807): the first post-smoothing sweep of a level

@@ -6,6 +6,7 @@
 // read, one __syncthreads per block.
 #include <cuda.h>
 
+#include "comm_dev.cuh"
 #include "cup_internal.h"
 #include "stencil7_tma.cuh"
 #include "tma_stage.cuh"
@@ -19,7 +20,8 @@ template <typename Real>
 __global__ void __launch_bounds__(TPB, 12)
     k_down_tma(LevelView lv, const int *__restrict__ sub, int nsub, const int *__restrict__ pslot,
                const int *__restrict__ oct, SlotVec<Real> u,
-               SlotVec<Real> f, Real h, Real *const *__restrict__ rptr, const __grid_constant__ CUtensorMap mxl,
+               SlotVec<Real> f, Real h, Real *const *__restrict__ rptr, WaitDesc wait, PostDesc post,
+               const __grid_constant__ CUtensorMap mxl,
                const __grid_constant__ CUtensorMap myl, const __grid_constant__ CUtensorMap mxe,
                const __grid_constant__ CUtensorMap mye) {
   __shared__ Stage<Real> st;
@@ -28,6 +30,9 @@ __global__ void __launch_bounds__(TPB, 12)
   if (t == 0) {
     mbar_init(&st.mbar, 1);
     mbar_fence_init();
+    // the ghost faces of u posted by the last pre-smoothing sweep (one-sided transport)
+    if (wait.seq)
+      comm_wait_for(wait, *(const volatile unsigned long long *)wait.seq);
   }
   __syncthreads();
   int i = blockIdx.x;
@@ -96,13 +101,14 @@ __global__ void __launch_bounds__(TPB, 12)
       }
     }
   }
+  comm_post_at_exit(post);  // children of remote parents are in their owners' windows
 }
 
 // out = A u on the blocks sub[0..nsub) (or all).  TAU: out += A u, us = u (mg_tau).
 template <typename Real, bool TAU>
 __global__ void __launch_bounds__(TPB, 12)
     k_apply_tma(LevelView lv, const int *__restrict__ sub, int nsub, SlotVec<Real> u, SlotVec<Real> out,
-                SlotVec<Real> us, Real h, const double *__restrict__ shift, Real h3,
+                SlotVec<Real> us, Real h, const double *__restrict__ shift, Real h3, WaitDesc wait,
                 const __grid_constant__ CUtensorMap mxl, const __grid_constant__ CUtensorMap myl,
                 const __grid_constant__ CUtensorMap mxe, const __grid_constant__ CUtensorMap mye) {
   __shared__ Stage<Real> st;
@@ -112,6 +118,8 @@ __global__ void __launch_bounds__(TPB, 12)
   if (t == 0) {
     mbar_init(&st.mbar, 1);
     mbar_fence_init();
+    if (wait.seq)
+      comm_wait_for(wait, *(const volatile unsigned long long *)wait.seq);
   }
   __syncthreads();
   int i = blockIdx.x;
@@ -176,37 +184,39 @@ static inline int pgrid(const CupCtx *c, long long n) {
 
 template <typename Real>
 int down_tma_launch(CupCtx *c, LevelView lv, const int *pslot, const int *oct, SlotVec<Real> u, SlotVec<Real> f,
-                    Real h, void *const *rptr, const int *sub, int nsub) {
+                    Real h, void *const *rptr, const int *sub, int nsub, const WaitDesc *wait, const PostDesc *post) {
   CUtensorMap m[4];
   CUP_TRY(tma_face_maps(c, u.leaf, u.extra, m));
   if (nsub < 0)
     nsub = lv.nact;
   k_down_tma<Real><<<pgrid(c, nsub), TPB, 0, c->stream>>>(lv, sub, nsub, pslot, oct, u, f, h, (Real *const *)rptr,
-                                                         m[0], m[1], m[2], m[3]);
+                                                         wait ? *wait : WaitDesc{}, post ? *post : PostDesc{}, m[0],
+                                                         m[1], m[2], m[3]);
   return CUP_OK;
 }
 
 template <typename Real>
 int apply_tma_launch(CupCtx *c, LevelView lv, const int *sub, int nsub, SlotVec<Real> u, SlotVec<Real> out,
-                     SlotVec<Real> us, Real h, const double *shift, Real h3, bool tau) {
+                     SlotVec<Real> us, Real h, const double *shift, Real h3, bool tau, const WaitDesc *wait) {
   CUtensorMap m[4];
   CUP_TRY(tma_face_maps(c, u.leaf, u.extra, m));
+  const WaitDesc w = wait ? *wait : WaitDesc{};
   if (tau)
-    k_apply_tma<Real, true><<<pgrid(c, nsub), TPB, 0, c->stream>>>(lv, sub, nsub, u, out, us, h, shift, h3, m[0], m[1],
-                                                                    m[2], m[3]);
+    k_apply_tma<Real, true><<<pgrid(c, nsub), TPB, 0, c->stream>>>(lv, sub, nsub, u, out, us, h, shift, h3, w, m[0],
+                                                                    m[1], m[2], m[3]);
   else
-    k_apply_tma<Real, false><<<pgrid(c, nsub), TPB, 0, c->stream>>>(lv, sub, nsub, u, out, us, h, shift, h3, m[0],
+    k_apply_tma<Real, false><<<pgrid(c, nsub), TPB, 0, c->stream>>>(lv, sub, nsub, u, out, us, h, shift, h3, w, m[0],
                                                                      m[1], m[2], m[3]);
   return CUP_OK;
 }
 
 template int down_tma_launch<double>(CupCtx *, LevelView, const int *, const int *, SlotVec<double>, SlotVec<double>,
-                                     double, void *const *, const int *, int);
+                                     double, void *const *, const int *, int, const WaitDesc *, const PostDesc *);
 template int down_tma_launch<float>(CupCtx *, LevelView, const int *, const int *, SlotVec<float>, SlotVec<float>,
-                                    float, void *const *, const int *, int);
+                                    float, void *const *, const int *, int, const WaitDesc *, const PostDesc *);
 template int apply_tma_launch<double>(CupCtx *, LevelView, const int *, int, SlotVec<double>, SlotVec<double>,
-                                      SlotVec<double>, double, const double *, double, bool);
+                                      SlotVec<double>, double, const double *, double, bool, const WaitDesc *);
 template int apply_tma_launch<float>(CupCtx *, LevelView, const int *, int, SlotVec<float>, SlotVec<float>,
-                                     SlotVec<float>, float, const double *, float, bool);
+                                     SlotVec<float>, float, const double *, float, bool, const WaitDesc *);
 
 }  // namespace cup

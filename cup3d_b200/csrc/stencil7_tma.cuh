@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 
+#include "comm_dev.cuh"
 #include "mg_device.cuh"
 struct CupCtx;
 namespace cup {
@@ -9,8 +10,10 @@ namespace cup {
 int tma_face_maps(CupCtx *c, const void *leaf, const void *extra, CUtensorMap out[4]);
 template <typename Real>
 int down_tma_launch(CupCtx *c, LevelView lv, const int *pslot, const int *oct, SlotVec<Real> u, SlotVec<Real> f,
-                    Real h, void *const *rptr, const int *sub = nullptr, int nsub = -1);
+                    Real h, void *const *rptr, const int *sub = nullptr, int nsub = -1,
+                    const WaitDesc *wait = nullptr, const PostDesc *post = nullptr);
 template <typename Real>
 int apply_tma_launch(CupCtx *c, LevelView lv, const int *sub, int nsub, SlotVec<Real> u, SlotVec<Real> out,
-                     SlotVec<Real> us, Real h, const double *shift, Real h3, bool tau);
+                     SlotVec<Real> us, Real h, const double *shift, Real h3, bool tau,
+                     const WaitDesc *wait = nullptr);
 }  // namespace cup

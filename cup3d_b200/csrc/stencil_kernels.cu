@@ -199,19 +199,22 @@ __global__ void __launch_bounds__(TPB, 8) k_prhs(LevelView lv, const Real *__res
   // the block index and neighbour list of the NEXT iteration are fetched one iteration ahead, so the
   // field loads of a block do not wait behind a dependent index load (ncu r01: 17.6 warps per issue
   // stalled on the long scoreboard, three dependent DRAM round trips per block)
-  int b = blockIdx.x, slot_n = 0, nn[6] = {0, 0, 0, 0, 0, 0};
-  if (b < lv.nact) {
+  const int nwork = lv_count(lv);
+  int wi = blockIdx.x, slot_n = 0, nn[6] = {0, 0, 0, 0, 0, 0};
+  if (wi < nwork) {
+    const int b = lv_item(lv, wi);
     slot_n = lv.act[b];
 #pragma unroll
     for (int f = 0; f < 6; f++)
       nn[f] = lv.nbr[(size_t)b * 6 + f];
   }
-  for (; b < lv.nact; b += gridDim.x) {
+  for (; wi < nwork; wi += gridDim.x) {
     const size_t own = (size_t)slot_n * 512;
     const int n0 = nn[0], n1 = nn[1], n2 = nn[2], n3 = nn[3], n4 = nn[4], n5 = nn[5];
     {
-      const int bn = b + gridDim.x;
-      if (bn < lv.nact) {
+      const int wn = wi + gridDim.x;
+      if (wn < nwork) {
+        const int bn = lv_item(lv, wn);
         slot_n = lv.act[bn];
 #pragma unroll
         for (int f = 0; f < 6; f++)
@@ -280,7 +283,8 @@ __global__ void __launch_bounds__(TPB) k_pres(LevelView lv, const Real *__restri
   __shared__ Real halo[6][64];
   const int t = threadIdx.x, x = t & 7, y = t >> 3;
   SlotVec<Real> pv{const_cast<Real *>(p), nullptr, 0x7fffffff};
-  for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
+  for (int wi = blockIdx.x; wi < lv_count(lv); wi += gridDim.x) {
+    const int b = lv_item(lv, wi);
     const size_t own = (size_t)lv.act[b] * 512;
     Real uu[8];
 #pragma unroll
@@ -327,7 +331,8 @@ __global__ void __launch_bounds__(TPB) k_velgrad(LevelView lv, const Real *__res
   const int t = threadIdx.x, x = t & 7, y = t >> 3, a = t & 7, c2 = t >> 3;
   const Real *vel[3] = {v0, v1, v2};
   const Real *rsl = lv.rslab ? rslab_of<Real>(lv) : nullptr;
-  for (int b = blockIdx.x; b < lv.nact; b += gridDim.x) {
+  for (int wi = blockIdx.x; wi < lv_count(lv); wi += gridDim.x) {
+    const int b = lv_item(lv, wi);
     const size_t own = (size_t)lv.act[b] * 512;
     const int *nbr6 = lv.nbr + (size_t)b * 6;
 #pragma unroll
@@ -517,24 +522,51 @@ template <typename Real>
 int stencil_amr_t(CupCtx *c, CupStencilId id) {
   const Level &v = c->leafv;
   LevelView lv{v.d_act, v.d_nbr, (int)v.act.size(), nullptr, nullptr, 0, v.d_ext};
+  lv.sub = c->run_sub;
+  lv.nsub = c->run_nsub;
   Real **S = (Real **)c->state;
   const double dt = c->prm.dt;
   switch (id) {
-  case CUP_ST_ADVDIFF:
+  case CUP_ST_ADVDIFF: {
     // blocks whose neighbours are all same-level / wall: the uniform kernel with per-block factors;
-    // interface blocks: the ss = 3 coarse-fine ghost fill
-    if (!v.reg.empty() && adv_tma()) {
-      CUP_TRY(advdiff_tma_launch<Real>(c, lv, v.d_reg, (int)v.reg.size(), v.d_hblk, dt, c->prm.nu, 0.0, 0.0));
-    } else if (!v.reg.empty()) {
-      k_advdiff<Real, 8><<<bgrid(c, (long long)v.reg.size(), 8), TPB, 0, c->stream>>>(
-          lv, v.d_reg, (int)v.reg.size(), (const Real *)v.d_hblk, (Real)dt, (Real)c->prm.nu, S[CUP_F_VEL],
+    // interface blocks: the ss = 3 coarse-fine ghost fill.  With a caller's list: its two halves.
+    const int *d_reg = v.d_reg, *d_irr = v.d_irr;
+    int nreg = (int)v.reg.size(), nirr = (int)v.irr.size();
+    if (c->run_nsub >= 0) {
+      std::vector<char> is_irr(v.act.size(), 0);
+      for (int k : v.irr)
+        is_irr[(size_t)k] = 1;
+      std::vector<int> lr, li;
+      for (int b : c->run_list)
+        (is_irr[(size_t)b] ? li : lr).push_back(b);
+      int *d2 = c->d_list + c->nblk;  // second half of the list scratch
+      if (!lr.empty())
+        CUP_CUDA(cudaMemcpyAsync(d2, lr.data(), lr.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+      if (!li.empty())
+        CUP_CUDA(cudaMemcpyAsync(d2 + lr.size(), li.data(), li.size() * sizeof(int), cudaMemcpyHostToDevice,
+                                 c->stream));
+      CUP_CUDA(cudaStreamSynchronize(c->stream));  // lr / li are stack vectors
+      d_reg = d2;
+      d_irr = d2 + lr.size();
+      nreg = (int)lr.size();
+      nirr = (int)li.size();
+    }
+    LevelView lv0 = lv;  // these kernels take their list as arguments
+    lv0.sub = nullptr;
+    lv0.nsub = -1;
+    if (nreg > 0 && adv_tma()) {
+      CUP_TRY(advdiff_tma_launch<Real>(c, lv0, d_reg, nreg, v.d_hblk, dt, c->prm.nu, 0.0, 0.0));
+    } else if (nreg > 0) {
+      k_advdiff<Real, 8><<<bgrid(c, (long long)nreg, 8), TPB, 0, c->stream>>>(
+          lv0, d_reg, nreg, (const Real *)v.d_hblk, (Real)dt, (Real)c->prm.nu, S[CUP_F_VEL],
           S[CUP_F_VEL + 1], S[CUP_F_VEL + 2], S[CUP_F_TMP], S[CUP_F_TMP + 1], S[CUP_F_TMP + 2], (Real)0, (Real)0,
           (Real)c->prm.uinf[0], (Real)c->prm.uinf[1], (Real)c->prm.uinf[2]);
       c->launches++;
     }
-    if (!v.irr.empty())
-      CUP_TRY(advdiff_amr_launch<Real>(c, v, S, v.d_irr, (int)v.irr.size()));
+    if (nirr > 0)
+      CUP_TRY(advdiff_amr_launch<Real>(c, v, S, d_irr, nirr));
     break;
+  }
   case CUP_ST_PRHS:
     CUP_TRY(prhs_amr_launch<Real>(c, lv, v.d_hblk, S, (Real)(1.0 / dt)));
     break;
@@ -588,11 +620,11 @@ int stencil_t(CupCtx *c, CupStencilId id, const int *d_sub, long long nsub) {
       CUP_TRY(halo_exchange<Real>(c, vm, pv));
     }
   }
-  if (d_sub) {
-    set_error("stencil_run: block sub-lists are only supported for CUP_ST_MG/CUP_ST_LHS");
-    return CUP_ERR_UNSUPPORTED;
-  }
+  (void)d_sub;
   (void)nsub;
+  const bool listed = c->run_nsub >= 0;
+  lv.sub = c->run_sub;
+  lv.nsub = c->run_nsub;
   Real **S = (Real **)c->state;
   const Real h = (Real)v.h;
   const double dt = c->prm.dt, hd = v.h;
@@ -601,12 +633,17 @@ int stencil_t(CupCtx *c, CupStencilId id, const int *d_sub, long long nsub) {
     // fac_a = -dt/h*h^3 ; fac_d = (nu/h)*(dt/h)*h^3   (main.c:4993-4995, coef = 1)
     const double h3 = hd * hd * hd;
     const double fa = -dt / hd * h3 * 1.0, fd = (c->prm.nu / hd) * (dt / hd) * h3 * 1.0;
-    if (adv_tma())
-      return advdiff_tma_launch<Real>(c, lv, nullptr, lv.nact, nullptr, 0.0, 0.0, fa, fd);
+    if (adv_tma()) {
+      LevelView lv0 = lv;  // takes its list as arguments
+      lv0.sub = nullptr;
+      lv0.nsub = -1;
+      return advdiff_tma_launch<Real>(c, lv0, c->run_sub, listed ? c->run_nsub : lv.nact, nullptr, 0.0, 0.0, fa, fd);
+    }
     static int minb = getenv("CUP_ADV_MINB") ? atoi(getenv("CUP_ADV_MINB")) : 8;
 #define ADV_LAUNCH(M)                                                                                              \
   k_advdiff<Real, M><<<bgrid(c, c->nblk, M), TPB, 0, c->stream>>>(                                                 \
-      lv, nullptr, lv.nact, nullptr, (Real)0, (Real)0, S[CUP_F_VEL], S[CUP_F_VEL + 1], S[CUP_F_VEL + 2],          \
+      lv, c->run_sub, listed ? c->run_nsub : lv.nact, nullptr, (Real)0, (Real)0, S[CUP_F_VEL], S[CUP_F_VEL + 1],   \
+      S[CUP_F_VEL + 2],                                                                                            \
       S[CUP_F_TMP], S[CUP_F_TMP + 1], S[CUP_F_TMP + 2], (Real)fa, (Real)fd, (Real)c->prm.uinf[0],                 \
       (Real)c->prm.uinf[1], (Real)c->prm.uinf[2])
     if (minb == 5)
@@ -625,7 +662,7 @@ int stencil_t(CupCtx *c, CupStencilId id, const int *d_sub, long long nsub) {
   case CUP_ST_PRHS: {
     const double fac = 0.5 * hd * hd / dt;
     // (its received-face path has not run on two GPUs yet: multi-rank contexts keep the plain loads)
-    if (prhs_tma() && c->nranks == 1)
+    if (prhs_tma() && c->nranks == 1 && !listed)
       return prhs_tma_launch<Real>(c, lv, fac);
     static bool carve = false;  // 8 CTAs x 21.5 KB need the large shared-memory configuration
     if (!carve) {
@@ -760,16 +797,51 @@ int projection_t(CupCtx *c, CupSolveInfo *info) {
 
 }  // namespace
 
+// stencil_run(st, list, n), main.c:3631-3647: the kernel runs on blocks list[0..n) -- or on the
+// first n blocks when list is NULL -- after the ghost exchange of the whole field.  Blocks not
+// listed keep their output untouched.  The flux correction is applied inside the pass of the
+// listed coarse blocks, i.e. for exactly the blocks whose output is recomputed.
 int stencil_run(CupCtx *c, CupStencilId id, const long long *list, long long n) {
   if (c->nblk == 0) {
     set_error("stencil_run: no mesh uploaded");
     return CUP_ERR_STATE;
   }
-  if (list != nullptr && n != c->nblk) {
-    set_error("stencil_run: block sub-lists are not supported yet (n=%lld of %lld)", n, c->nblk);
-    return CUP_ERR_UNSUPPORTED;
+  if (n < 0 || n > c->nblk) {
+    set_error("stencil_run: n = %lld outside [0, %lld]", n, c->nblk);
+    return CUP_ERR_ARG;
   }
-  return c->real_bytes == 8 ? stencil_t<double>(c, id, nullptr, n) : stencil_t<float>(c, id, nullptr, n);
+  if ((int)id < 0 || (int)id > (int)CUP_ST_Q) {
+    set_error("stencil_run: unknown stencil id %d", (int)id);
+    return CUP_ERR_ARG;
+  }
+  c->run_sub = nullptr;
+  c->run_nsub = -1;
+  if (list != nullptr || n != c->nblk) {
+    c->run_list.resize((size_t)n);
+    std::vector<char> seen((size_t)c->nblk, 0);
+    for (long long k = 0; k < n; k++) {
+      const long long b = list ? list[k] : k;
+      if (b < 0 || b >= c->nblk || seen[(size_t)b]) {
+        set_error("stencil_run: list[%lld] = %lld is %s", k, b, (b < 0 || b >= c->nblk) ? "out of range" : "a duplicate");
+        return CUP_ERR_ARG;
+      }
+      seen[(size_t)b] = 1;
+      c->run_list[(size_t)k] = (int)b;
+    }
+    if (n == 0)
+      return CUP_OK;  // the reference would still exchange ghosts; no output changes
+    if (!c->d_list)
+      CUP_CUDA(cudaMalloc((void **)&c->d_list, (size_t)c->nblk * 2 * sizeof(int)));
+    CUP_CUDA(cudaMemcpyAsync(c->d_list, c->run_list.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice,
+                             c->stream));
+    CUP_CUDA(cudaStreamSynchronize(c->stream));
+    c->run_sub = c->d_list;
+    c->run_nsub = (int)n;
+  }
+  const int rc = c->real_bytes == 8 ? stencil_t<double>(c, id, nullptr, n) : stencil_t<float>(c, id, nullptr, n);
+  c->run_sub = nullptr;
+  c->run_nsub = -1;
+  return rc;
 }
 
 int vorticity(CupCtx *c) {

@@ -46,7 +46,8 @@ typedef enum {
   CUP_ERR_MESH = -3,    /* inconsistent mesh (missing neighbour / sibling) */
   CUP_ERR_STATE = -4,   /* call order (mesh not uploaded, ...) */
   CUP_ERR_NCCL = -5,
-  CUP_ERR_UNSUPPORTED = -6
+  CUP_ERR_UNSUPPORTED = -6,
+  CUP_ERR_COMM = -7     /* a peer rank did not answer in time (one-sided exchange) */
 } CupStatus;
 
 /* struct Blk, main.c:59-63 (Real = double in the reference build) */
@@ -95,14 +96,20 @@ int cup_version(void);
 /* real_bytes: 8 (the reference build, typedef double Real) or 4 */
 int cup_create(CupCtx **ctx, int device, int real_bytes);
 int cup_destroy(CupCtx *ctx);
-/* run all later work on this CUDA stream (cudaStream_t as void*); 0 = default */
+/* run all later work on this CUDA stream (cudaStream_t as void*).  NULL selects the library's own
+ * BLOCKING stream (ordered against the caller's legacy default stream), not the NULL stream: the
+ * NULL stream cannot be captured into the CUDA graphs the V-cycle replays from. */
 int cup_set_stream(CupCtx *ctx, void *stream);
 int cup_set_params(CupCtx *ctx, const CupParams *p);
 int cup_synchronize(CupCtx *ctx);
 
 /* Rebuild hook.  blk = this rank's sta.blk[0..n), bpd = sim.bpdx/y/z,
  * level_max = sim.level_max.  Builds neighbour tables, flux-face plans and
- * the multigrid hierarchy on the device (replaces main.c:3325-3328). */
+ * the multigrid hierarchy on the device (replaces main.c:3325-3328).
+ * CONTRACT: the nine state fields are re-allocated for the new block count and ZEROED -- after
+ * an adaptation the caller uploads sta.fld again with cup_state_h2d (the reference moves block
+ * data inside mesh_adapt on the host, main.c:4012).  Obstacle blocks are dropped as well.  On any
+ * failure the context is left WITHOUT a mesh (later calls return CUP_ERR_STATE). */
 int cup_mesh_upload(CupCtx *ctx, const CupBlk *blk, long long n, const int bpd[3], int level_max);
 long long cup_nblk(const CupCtx *ctx);
 long long cup_nslot(const CupCtx *ctx); /* leaves + synthesised MG parents */
@@ -116,7 +123,12 @@ int cup_state_d2h(CupCtx *ctx, double *h_fld, int f0, int nc);
 /* device pointer of one state component: flat [nblk][512] Reals */
 void *cup_state_dev(CupCtx *ctx, int f);
 
-/* the per-block compute loop */
+/* the per-block compute loop.  cup_stencil_run is stencil_run(st, list, n) (main.c:3631-3647):
+ * ghost exchange of the whole input field, then the kernel on local blocks list[0..n) -- on the
+ * first n blocks when list is NULL.  Blocks that are not listed keep their output.  Entries must
+ * be distinct and inside [0, cup_nblk) (CUP_ERR_ARG otherwise).  cup_stencil_apply == (NULL, nblk).
+ * Every device is guarded: all entry points switch to the context's device and restore the
+ * caller's current device on return. */
 int cup_stencil_apply(CupCtx *ctx, CupStencilId id);
 int cup_stencil_run(CupCtx *ctx, CupStencilId id, const long long *list, long long n);
 
@@ -193,6 +205,18 @@ int cup_io_pack(CupCtx *ctx, float *attr, float *vort, float *q);
  * rank 0 and distributed by the caller (torch.distributed / MPI_Bcast). */
 int cup_comm_init(CupCtx *ctx, int rank, int nranks, const void *nccl_id, size_t id_bytes);
 int cup_nccl_unique_id(void *out, size_t bytes);
+/* The same, bootstrapped by the CALLER's host collective instead of NCCL -- the reference has an
+ * MPI communicator (sim.comm, main.c:2899ff), so its binding is
+ *     static int ag(void *u, const void *s, void *r, size_t n) {
+ *       return MPI_Allgather(s, (int)n, MPI_BYTE, r, (int)n, MPI_BYTE, *(MPI_Comm *)u); }
+ *     cup_comm_init_host(ctx, sim.rank, sim.size, ag, &sim.comm);
+ * allgather(user, send, recv, bytes): every rank contributes `bytes` bytes, recv gets nranks*bytes
+ * in rank order; returns 0 on success.  It is called only inside cup_mesh_upload / cup_destroy
+ * (block lists, CUDA IPC handles, barriers).  All DATA moves GPU-to-GPU through CUDA-IPC peer
+ * windows (NVLink), reductions included, so this mode needs peer access between the ranks'
+ * devices (ranks may also share one device: used by the single-GPU tests). */
+typedef int (*CupAllgatherFn)(void *user, const void *send, void *recv, size_t bytes);
+int cup_comm_init_host(CupCtx *ctx, int rank, int nranks, CupAllgatherFn allgather, void *user);
 
 /* Host-only view of one rank's exchange plan for one multigrid level (no GPU
  * needed; used by the CPU tests that emulate the exchange over gloo).  Built

@@ -26,6 +26,23 @@
 
 static int ref_ready;
 
+/* The binding always passes doubles.  In the Real=float build (oracle/Makefile target ref32: the
+ * reference's `typedef double Real` / `#define MPI_Real` lines switched to float in a temporary
+ * copy at build time, main.c:14-15) vectors are converted at this boundary. */
+static Real *to_real(const double *in, long long n) {
+  Real *p = malloc((size_t)n * sizeof *p);
+  long long i;
+  for (i = 0; i < n; i++)
+    p[i] = (Real)in[i];
+  return p;
+}
+static void from_real(double *out, const Real *p, long long n) {
+  long long i;
+  for (i = 0; i < n; i++)
+    out[i] = (double)p[i];
+}
+API int ref_real_bytes(void) { return (int)sizeof(Real); }
+
 /* argv = the reference's own "-key value" command line (without argv[0]);
  * tabdir = directory holding lab_ss*_t*.bin (the reference opens them in cwd,
  * main.c:3350-3353). */
@@ -81,8 +98,12 @@ API void ref_blocks(int *ib, double *rb) {
 }
 
 /* raw state: sta.fld is [nblk][F_N][512] (main.c:55-58,131-132) */
-API void ref_state_get(double *out) { memcpy(out, sta.fld, (size_t)sta.nblk * BLK_S * sizeof(Real)); }
-API void ref_state_set(const double *in) { memcpy(sta.fld, in, (size_t)sta.nblk * BLK_S * sizeof(Real)); }
+API void ref_state_get(double *out) { from_real(out, sta.fld, sta.nblk * BLK_S); }
+API void ref_state_set(const double *in) {
+  long long i, n = sta.nblk * BLK_S;
+  for (i = 0; i < n; i++)
+    sta.fld[i] = (Real)in[i];
+}
 
 API void ref_set_scalars(double dt, double nu, double uinfx, double uinfy, double uinfz, int step,
                          int mean_constraint, double ptol, double ptol_rel) {
@@ -97,8 +118,22 @@ API void ref_set_scalars(double dt, double nu, double uinfx, double uinfy, doubl
   sim.ptol_rel = ptol_rel;
 }
 
-API void ref_mg_vcycle(double *in, double *out) { mg_vcycle(in, out); }
-API void ref_pois_op(double *in, double *out) { pois_op(in, out); }
+API void ref_mg_vcycle(double *in, double *out) {
+  long long n = sta.nblk * BS3;
+  Real *a = to_real(in, n), *b = malloc((size_t)n * sizeof *b);
+  mg_vcycle(a, b);
+  from_real(out, b, n);
+  free(a);
+  free(b);
+}
+API void ref_pois_op(double *in, double *out) {
+  long long n = sta.nblk * BS3;
+  Real *a = to_real(in, n), *b = malloc((size_t)n * sizeof *b);
+  pois_op(a, b);
+  from_real(out, b, n);
+  free(a);
+  free(b);
+}
 API void ref_pois_solve(void) { pois_solve(); }
 API void ref_advdiff(void) { advdiff(); }
 API void ref_projection(void) { projection(); }
@@ -115,16 +150,25 @@ API int ref_stencil(int id) {
 /* Weighted dot used by the Krylov solver (main.c:4854); builds pois.hw first. */
 API double ref_pois_dot(double *a, double *b) {
   long long N = sta.nblk * BS3, i;
+  Real *ra = to_real(a, N), *rb = to_real(b, N);
+  double r;
   pois_alloc(N);
   for (i = 0; i < sta.nblk; i++)
     pois.hw[i] = 1 / (sta.blk[i].h * sta.blk[i].h * sta.blk[i].h);
-  return pois_dot(a, b, N);
+  r = pois_dot(ra, rb, N);
+  free(ra);
+  free(rb);
+  return r;
 }
 
 /* the block-local FDM inverse (main.c:4368) on one 512-vector */
 API void ref_pre_blk(double *src, double *dst, double invh) {
-  Real a[BS3], b[BS3];
-  pre_blk(src, dst, invh, a, b);
+  Real a[BS3], b[BS3], s[BS3], d[BS3];
+  int i;
+  for (i = 0; i < BS3; i++)
+    s[i] = (Real)src[i];
+  pre_blk(s, d, invh, a, b);
+  from_real(dst, d, BS3);
 }
 
 static double now(void) {
@@ -136,13 +180,19 @@ static double now(void) {
 /* time n V-cycles (after w warm-ups); returns seconds for the n cycles */
 API double ref_time_vcycle(double *in, double *out, int w, int n) {
   int k;
-  double t0;
+  double t0, t1;
+  long long N = sta.nblk * BS3;
+  Real *a = to_real(in, N), *b = malloc((size_t)N * sizeof *b);
   for (k = 0; k < w; k++)
-    mg_vcycle(in, out);
+    mg_vcycle(a, b);
   t0 = now();
   for (k = 0; k < n; k++)
-    mg_vcycle(in, out);
-  return now() - t0;
+    mg_vcycle(a, b);
+  t1 = now();
+  from_real(out, b, N);
+  free(a);
+  free(b);
+  return t1 - t0;
 }
 
 API double ref_time_stencil(int id, int w, int n) {

@@ -13,6 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 REFDIR = os.path.join(HERE, "_ref")
 LIB = os.path.join(REFDIR, "libcup3d_ref.so")
+LIB32 = os.path.join(REFDIR, "libcup3d_ref32.so")  # the same source built with Real = float
 BS3 = 512
 F_N = 9
 F_CHI, F_PRES, F_VEL, F_TMP, F_LHS = 0, 1, 2, 5, 8
@@ -39,11 +40,12 @@ def default_args(**kw):
     return a
 
 
-def init(**kw):
+def init(real_bytes=8, **kw):
     global _lib
     if _lib is not None:
         raise RuntimeError("reference already initialised in this process")
-    lib = C.CDLL(LIB)
+    lib = C.CDLL(LIB if real_bytes == 8 else LIB32)
+    assert lib.ref_real_bytes() == real_bytes
     args = default_args(**kw)
     flat = []
     for k, v in args.items():

@@ -1,6 +1,12 @@
-"""GPU, 2 ranks (needs >= 2 devices; skipped otherwise): the domain-decomposed
-V-cycle / operator / solve must reproduce the reference's single-rank golden
-result -- decomposition may only change reduction order."""
+"""GPU, 2 ranks: the domain-decomposed V-cycle / operator / solve / time-step pieces must reproduce
+the reference's single-rank golden result -- decomposition may only change reduction order
+(SURVEY.md 8c).
+
+Two bootstraps are covered.  "nccl": cup_comm_init with an ncclUniqueId, one rank per GPU (needs
+>= 2 devices, skipped otherwise).  "host": cup_comm_init_host with a host all-gather (gloo here,
+MPI_Allgather in the reference); data moves through CUDA-IPC peer windows only, so the ranks may
+share ONE device -- that is how the exchange kernels run in a single-GPU CI box (the two processes
+are time-sliced by the driver; every flag wait costs a time slice, which is fine for these sizes)."""
 import os
 import sys
 
@@ -13,20 +19,77 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def worker(rank, world, nid, name, coarse, q):
+def connect(rank, world, boot):
+    """-> Context of this rank on its device, communicator initialised.  boot = ("nccl", id) or ("host", port)"""
+    import torch
+    import cup3d_b200
+    from cup3d_b200 import capi
+    dev = rank % torch.cuda.device_count()
+    torch.cuda.set_device(dev)
+    ctx = cup3d_b200.Context(dev, 8)
+    if boot[0] == "nccl":
+        ctx.comm_init(rank, world, boot[1])
+    else:
+        import torch.distributed as dist
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % boot[1], rank=rank, world_size=world)
+        ctx.comm_init_host(rank, world, capi.gloo_allgather())
+    return ctx
+
+
+def disconnect(ctx, boot):
+    ctx.close()
+    if boot[0] == "host":
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def boots():
+    """the bootstraps this box can run: host always (ranks may share a device), nccl with >= 2 GPUs"""
+    import torch
+    return ["host"] + (["nccl"] if torch.cuda.device_count() >= 2 else [])
+
+
+def make_boot(kind):
+    if kind == "nccl":
+        from cup3d_b200 import capi
+        return ("nccl", capi.nccl_unique_id())
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return ("host", port)
+
+
+def run_ranks(target, world, args, timeout=600):
+    import torch.multiprocessing as mp
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    ps = [ctxm.Process(target=target, args=(r, world) + tuple(args) + (q,)) for r in range(world)]
+    for p in ps:
+        p.start()
+    try:
+        got = [q.get(timeout=timeout) for _ in ps]
+    finally:
+        for p in ps:
+            p.join(timeout=60)
+            if p.is_alive():
+                p.kill()
+    for p in ps:
+        assert p.exitcode == 0
+    return got
+
+
+def worker(rank, world, boot, name, coarse, q):
     os.environ["CUP_COARSE_BLOCKS"] = str(coarse)
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import torch
-    torch.cuda.set_device(rank)
-    import cup3d_b200
     from cup3d_b200 import capi
     from util import case
     c = case(name)
     owner = capi.split_owner(c.n, world)
     mine = np.nonzero(owner == rank)[0]
-    ctx = cup3d_b200.Context(rank, 8)
-    ctx.comm_init(rank, world, nid)
+    ctx = connect(rank, world, boot)
     ctx.mesh_upload(c.ib[mine], c.rb[mine], c.bpd, c.level_max)
     ctx.set_params(dt=c.dt, nu=c.nu, uinf=c.uinf, step=5, mean_constraint=2, ptol=1e-10, ptol_rel=1e-12)
     out = {}
@@ -44,27 +107,19 @@ def worker(rank, world, nid, name, coarse, q):
     out["it"] = info.iterations
     out["res"] = info.residual
     q.put((rank, mine, out))
-    ctx.close()
+    disconnect(ctx, boot)
 
 
-@pytest.mark.parametrize("name,coarse", [("u32", 0), ("u64", 0), ("u64", 4096)])
-def test_two_rank_matches_single_rank_reference(built, name, coarse):
+@pytest.mark.parametrize("kind", ["host", "nccl"])
+@pytest.mark.parametrize("name,coarse,world", [("u32", 0, 2), ("u64", 0, 2), ("u64", 4096, 2), ("u64", 64, 3)])
+def test_ranks_match_single_rank_reference(built, name, coarse, world, kind):
+    if kind not in boots():
+        pytest.skip("the NCCL bootstrap needs one GPU per rank")
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    import torch.multiprocessing as mp
-    from cup3d_b200 import capi
+    if kind == "nccl" and torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     c = case(name)
-    nid = capi.nccl_unique_id()
-    ctxm = mp.get_context("spawn")
-    q = ctxm.Queue()
-    ps = [ctxm.Process(target=worker, args=(r, 2, nid, name, coarse, q)) for r in range(2)]
-    for p in ps:
-        p.start()
-    got = [q.get(timeout=300) for _ in ps]
-    for p in ps:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    got = run_ranks(worker, world, (make_boot(kind), name, coarse))
     vc = np.zeros((c.n, 512))
     op = np.zeros((c.n, 512))
     x = np.zeros((c.n, 512))
@@ -76,20 +131,16 @@ def test_two_rank_matches_single_rank_reference(built, name, coarse):
     assert relerr(x, c.g["solve_x_mc2"]) < 1e-8
 
 
-def worker_step(rank, world, nid, name, q):
+def worker_step(rank, world, boot, name, q):
     os.environ["CUP_COARSE_BLOCKS"] = "0"
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import torch
-    torch.cuda.set_device(rank)
-    import cup3d_b200
     from cup3d_b200 import capi
     from util import case
     c = case(name)
     owner = capi.split_owner(c.n, world)
     mine = np.nonzero(owner == rank)[0]
-    ctx = cup3d_b200.Context(rank, 8)
-    ctx.comm_init(rank, world, nid)
+    ctx = connect(rank, world, boot)
     ctx.mesh_upload(c.ib[mine], c.rb[mine], c.bpd, c.level_max)
     ctx.set_params(dt=c.dt, nu=c.nu, uinf=c.uinf, step=5, mean_constraint=2, ptol=1e-10, ptol_rel=1e-12)
     out = {}
@@ -112,28 +163,17 @@ def worker_step(rank, world, nid, name, q):
     ctx.state_d2h(r)
     out["proj"] = r
     q.put((rank, mine, out))
-    ctx.close()
+    disconnect(ctx, boot)
 
 
+@pytest.mark.parametrize("kind", ["host", "nccl"])
 @pytest.mark.parametrize("name", ["u16", "b211"])
-def test_two_rank_time_step_pieces(built, name):
-    """advdiff(), projection() and every stencil sweep, domain-decomposed over 2 GPUs"""
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    import torch.multiprocessing as mp
-    from cup3d_b200 import capi
+def test_two_rank_time_step_pieces(built, name, kind):
+    """advdiff(), projection() and every stencil sweep, domain-decomposed over 2 ranks"""
+    if kind not in boots():
+        pytest.skip("the NCCL bootstrap needs one GPU per rank")
     c = case(name)
-    nid = capi.nccl_unique_id()
-    ctxm = mp.get_context("spawn")
-    q = ctxm.Queue()
-    ps = [ctxm.Process(target=worker_step, args=(r, 2, nid, name, q)) for r in range(2)]
-    for p in ps:
-        p.start()
-    got = [q.get(timeout=300) for _ in ps]
-    for p in ps:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    got = run_ranks(worker_step, 2, (make_boot(kind), name))
     full = {}
     for rank, mine, out in got:
         for k, v in out.items():

@@ -121,3 +121,40 @@ def test_io_pack(built, name):
     eq = c.g["st_q"][:, 0].astype(np.float32)
     assert np.max(np.abs(q - eq)) <= 2e-7 * np.max(np.abs(eq)) and np.mean(q != eq) < 1e-3
     ctx.close()
+
+
+@pytest.mark.parametrize("name", ["b211", "amr2"])
+@pytest.mark.parametrize("st", list(ST))
+def test_stencil_run_block_list(built, name, st):
+    """stencil_run(st, list, n) (main.c:3631-3647): the listed blocks get exactly what the full sweep gives
+    them, every other block keeps its output; list == NULL with n < nblk means the first n blocks"""
+    c = case(name)
+    sid, f0, nc = ST[st]
+    ctx = make_ctx(c)
+    s0 = c.state0()
+    ref = c.g["st_" + st]
+    rng = np.random.default_rng(7)
+    lst = rng.permutation(c.n)[: max(1, c.n // 3)]
+    for blocks, n in ((lst, None), (None, c.n // 2)):
+        ctx.state_h2d(s0)
+        ctx.stencil_run(sid, blocks, n)
+        out = np.zeros_like(s0)
+        ctx.state_d2h(out)
+        sel = np.zeros(c.n, bool)
+        sel[blocks if blocks is not None else np.arange(n)] = True
+        scale = np.max(np.abs(ref))
+        assert np.max(np.abs(out[sel, f0:f0 + nc] - ref[sel])) <= 1e-12 * scale, st
+        assert np.array_equal(out[~sel], s0[~sel]), st
+    ctx.close()
+
+
+def test_stencil_run_rejects_bad_lists(built):
+    import cup3d_b200
+    c = case("u16")
+    ctx = make_ctx(c)
+    for bad in ([0, 0], [c.n], [-1]):
+        with pytest.raises(cup3d_b200.CupError):
+            ctx.stencil_run(capi.ST_DIVP, np.array(bad))
+    with pytest.raises(cup3d_b200.CupError):
+        ctx.stencil_run(capi.ST_DIVP, None, c.n + 1)
+    ctx.close()
