@@ -347,6 +347,12 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))  # device time, max over ranks
     launches = ctx.kernel_launches() - l0
+    if os.environ.get("CUP_STAMP"):
+        # per-phase device timestamps of the last (graph-replayed) cycle, every rank (diagnostics)
+        rep = ctx.trace_report()
+        tot = sum(v for _, v in rep)
+        sys.stderr.write("[stamp rank %d] total %.1f us (incl. ~%d stamp kernels): %s\n" %
+                         (rank, tot / 1e3, len(rep), " ".join("%s=%.1f" % (k, v / 1e3) for k, v in rep)))
     # dominant kernel: finest-level smoother, timed live with CUDA events on the same stream
     # (single-rank kernel time; ghost faces of other ranks are whatever the last exchange left)
     sm_ms = ctx.time_smooth(L, 40)

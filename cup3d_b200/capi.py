@@ -38,7 +38,10 @@ class CupPlan(C.Structure):
     _fields_ = [("nblk", C.c_longlong), ("nslot", C.c_longlong), ("nact", C.c_int), ("nsend", C.c_int),
                 ("nrecv", C.c_int), ("act", _ip), ("ijk", _ip), ("nbr", _ip), ("send_slot", _ip), ("send_plane", _ip),
                 ("send_cnt", _ip), ("recv_cnt", _ip), ("pslot", _ip), ("oct", _ip), ("res_send_cnt", _ip),
-                ("res_recv_cnt", _ip), ("nres_recv", C.c_int), ("res_recv_slot", _ip), ("res_recv_oct", _ip)]
+                ("res_recv_cnt", _ip), ("nres_recv", C.c_int), ("res_recv_slot", _ip), ("res_recv_oct", _ip),
+                ("ghosted", C.c_int), ("nghost", C.c_int), ("ext", _ip), ("nbsend", C.c_int), ("nbrecv", C.c_int),
+                ("bsend_slot", _ip), ("bsend_kind", _ip), ("bsend_peer", _ip), ("bsend_idx", _ip),
+                ("brecv_slot", _ip), ("brecv_kind", _ip)]
 
 
 # every symbol include/cup3d_b200.h declares: name -> (restype, argtypes)
@@ -88,6 +91,7 @@ SYMBOLS = {
                        C.POINTER(CupPlan)]),
     "cup_plan_free": (None, [C.POINTER(CupPlan)]),
     "cup_kernel_launches": (_ll, [_vp]),
+    "cup_trace_report": (_i, [_vp, C.c_char_p, C.c_size_t]),
     "cup_time_smooth": (_i, [_vp, _i, _i, C.POINTER(C.c_float)]),
     "cup_mg_smooth_dev": (_i, [_vp, _i, _i, _vp, _vp]),
     "cup_mg_array": (_vp, [_vp, _i]),
@@ -153,7 +157,11 @@ def plan_build(ib, rb, owner, nranks, rank, bpd, level_max, level):
                send_cnt=arr_of(p.send_cnt, nranks), recv_cnt=arr_of(p.recv_cnt, nranks),
                pslot=arr_of(p.pslot, p.nact if level > 0 else 0), oct=arr_of(p.oct, p.nact if level > 0 else 0),
                res_send_cnt=arr_of(p.res_send_cnt, nranks), res_recv_cnt=arr_of(p.res_recv_cnt, nranks),
-               res_recv_slot=arr_of(p.res_recv_slot, p.nres_recv), res_recv_oct=arr_of(p.res_recv_oct, p.nres_recv))
+               res_recv_slot=arr_of(p.res_recv_slot, p.nres_recv), res_recv_oct=arr_of(p.res_recv_oct, p.nres_recv),
+               ghosted=bool(p.ghosted), nghost=p.nghost, nbsend=p.nbsend, nbrecv=p.nbrecv, ext=arr_of(p.ext, 24 * p.nact).reshape(-1, 6, 4),
+               bsend_slot=arr_of(p.bsend_slot, p.nbsend), bsend_kind=arr_of(p.bsend_kind, p.nbsend),
+               bsend_peer=arr_of(p.bsend_peer, p.nbsend), bsend_idx=arr_of(p.bsend_idx, p.nbsend),
+               brecv_slot=arr_of(p.brecv_slot, p.nbrecv), brecv_kind=arr_of(p.brecv_kind, p.nbrecv))
     lib().cup_plan_free(C.byref(p))
     return out
 
@@ -386,6 +394,12 @@ class Context:
 
     def kernel_launches(self):
         return int(self.L.cup_kernel_launches(self.h))
+
+    def trace_report(self):
+        """[(phase, ns)] of the last V-cycle (needs CUP_STAMP=1 in the environment)"""
+        buf = C.create_string_buffer(1 << 16)
+        n = self.L.cup_trace_report(self.h, buf, len(buf))
+        return [(a, int(b)) for a, b in (ln.split() for ln in buf.raw[:n].decode().splitlines())]
 
     def time_smooth(self, level, reps):
         ms = C.c_float()

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_advdiff_tma(LevelView lv, AdvArgs
   const int t = threadIdx.x, x = t & 7, y = t >> 3;
   const Real *rsl = lv.rslab ? rslab_of<Real>(lv) : nullptr;
   auto rem = [&](int nbc, int c, int l, int e) -> Real {
-    return rsl[(size_t)(kRemote0 - nbc) * (64 * kSlabPlanes) + (c * 3 + l) * 64 + e];
+    return __ldcg(rsl + (size_t)(kRemote0 - nbc) * (64 * kSlabPlanes) + (c * 3 + l) * 64 + e);
   };
   // blocks of this CTA: wi = blockIdx.x + j * gridDim.x
   const int nmine = A.nsub > (int)blockIdx.x ? (A.nsub - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;

@@ -121,7 +121,8 @@ __global__ void __launch_bounds__(TPB) k_smooth_amr(LevelView lv, const int *__r
 template <typename Real>
 __global__ void __launch_bounds__(TPB) k_down_amr(LevelView lv, const int *__restrict__ sub, int nsub,
                                                   const int *__restrict__ pslot, const int *__restrict__ oct,
-                                                  SlotVec<Real> u, SlotVec<Real> f, Real h) {
+                                                  SlotVec<Real> u, SlotVec<Real> f, Real h,
+                                                  Real *const *__restrict__ rptr) {
   __shared__ Real tu[512];
   __shared__ Real tr[512];
   __shared__ Real halo[6][64];
@@ -157,9 +158,15 @@ __global__ void __launch_bounds__(TPB) k_down_amr(LevelView lv, const int *__res
       const Real su = ((((((tu[base] + tu[base + 1]) + tu[base + 8]) + tu[base + 9]) + tu[base + 64]) +
                          tu[base + 65]) + tu[base + 72]) + tu[base + 73];
       const int o = oct[b], ps = pslot[b];
-      const int pidx = ((4 * (o >> 2) + cz) << 6) + ((4 * ((o >> 1) & 1) + cy) << 3) + 4 * (o & 1) + cx;
-      f.at(ps)[pidx] = sr;
-      u.at(ps)[pidx] = (Real)0.125 * su;
+      if (ps >= 0) {
+        const int pidx = ((4 * (o >> 2) + cz) << 6) + ((4 * ((o >> 1) & 1) + cy) << 3) + 4 * (o & 1) + cx;
+        f.at(ps)[pidx] = sr;
+        u.at(ps)[pidx] = (Real)0.125 * su;
+      } else {  // parent on another rank: 64 r + 64 u into its owner's window (MG_M layout, main.c:4750)
+        Real *q = rptr[kRemote0 - ps];
+        q[t] = sr;
+        q[64 + t] = (Real)0.125 * su;
+      }
     }
     __syncthreads();
   }
@@ -607,10 +614,10 @@ int smooth_amr_launch(CupCtx *c, LevelView lv, SlotVec<Real> src, SlotVec<Real> 
 
 template <typename Real>
 int down_amr_launch(CupCtx *c, LevelView lv, const int *pslot, const int *oct, SlotVec<Real> u, SlotVec<Real> f,
-                    Real h, const int *sub, int nsub) {
+                    Real h, const int *sub, int nsub, void *const *rptr) {
   if (nsub < 0)
     nsub = lv.nact;
-  k_down_amr<Real><<<agrid(c, nsub), TPB, 0, c->stream>>>(lv, sub, nsub, pslot, oct, u, f, h);
+  k_down_amr<Real><<<agrid(c, nsub), TPB, 0, c->stream>>>(lv, sub, nsub, pslot, oct, u, f, h, (Real *const *)rptr);
   return CUP_OK;
 }
 
@@ -674,9 +681,9 @@ template int smooth_amr_launch<double>(CupCtx *, LevelView, SlotVec<double>, Slo
 template int smooth_amr_launch<float>(CupCtx *, LevelView, SlotVec<float>, SlotVec<float>, SlotVec<float>,
                                       SlotVec<float>, float, const double *, bool, const int *, int);
 template int down_amr_launch<double>(CupCtx *, LevelView, const int *, const int *, SlotVec<double>, SlotVec<double>,
-                                     double, const int *, int);
+                                     double, const int *, int, void *const *);
 template int down_amr_launch<float>(CupCtx *, LevelView, const int *, const int *, SlotVec<float>, SlotVec<float>,
-                                    float, const int *, int);
+                                    float, const int *, int, void *const *);
 template int apply_amr_launch<double>(CupCtx *, LevelView, const int *, int, SlotVec<double>, SlotVec<double>,
                                       SlotVec<double>, double, const void *, const double *, int);
 template int apply_amr_launch<float>(CupCtx *, LevelView, const int *, int, SlotVec<float>, SlotVec<float>,

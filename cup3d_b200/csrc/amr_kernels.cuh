@@ -11,7 +11,7 @@ int smooth_amr_launch(CupCtx *c, LevelView lv, SlotVec<Real> src, SlotVec<Real> 
                       int nsub = -1);
 template <typename Real>
 int down_amr_launch(CupCtx *c, LevelView lv, const int *pslot, const int *oct, SlotVec<Real> u, SlotVec<Real> f,
-                    Real h, const int *sub = nullptr, int nsub = -1);
+                    Real h, const int *sub = nullptr, int nsub = -1, void *const *rptr = nullptr);
 // mode 0: out = A u (+shift h^3); 1: tau (out += A u, us = u); 2: out = A u with flux correction
 template <typename Real>
 int apply_amr_launch(CupCtx *c, LevelView lv, const int *sub, int nsub, SlotVec<Real> u, SlotVec<Real> out,

@@ -1,4 +1,6 @@
 // capi.cu -- the extern "C" boundary declared in include/cup3d_b200.h.
+#include <algorithm>
+
 #include "blas_kernels.cuh"
 #include "cup_internal.h"
 #include "smooth_tma.cuh"
@@ -29,7 +31,15 @@ __global__ void k_cvt_out(double *__restrict__ dst, const Real *__restrict__ src
 }
 
 static int alloc_state(CupCtx *c) {
-  const size_t bytes = (size_t)c->nblk * 512 * (size_t)c->real_bytes;
+  // nstate = own leaves + the leaf context's ghost blocks (multi-level meshes across ranks)
+  const size_t bytes = (size_t)c->nstate * 512 * (size_t)c->real_bytes;
+  cudaFree(c->leaf_ghost);
+  c->leaf_ghost = nullptr;
+  if (c->leafv.nghost > 0) {
+    const size_t rows = (size_t)std::max<long long>(c->leafv.nghost, c->nslot - c->nblk + 1);
+    CUP_CUDA(cudaMalloc(&c->leaf_ghost, rows * 512 * (size_t)c->real_bytes));
+    CUP_CUDA(cudaMemset(c->leaf_ghost, 0, rows * 512 * (size_t)c->real_bytes));
+  }
   for (int f = 0; f < CUP_F_N; f++) {
     cudaFree(c->state[f]);
     c->state[f] = nullptr;
@@ -176,6 +186,7 @@ int cup_destroy(CupCtx *c) {
   cudaFree(c->p_old);
   cudaFree(c->tmp_stage);
   cudaFree(c->io_buf);
+  cudaFree(c->leaf_ghost);
   cudaFree(c->d_W);
   cudaFree(c->d_hw);
   cudaFree(c->d_scal);
@@ -437,11 +448,11 @@ int cup_plan_build(const CupBlk *gblk, long long G, const int *owner, int nranks
                    int level_max, int level, CupPlan *out) {
   HostMesh m;
   CUP_TRY(build_tables(&m, gblk, G, owner, nranks, rank, bpd, level_max));
-  if (level < 0 || level > m.top || !out) {
+  if (level < -1 || level > m.top || !out) {
     set_error("cup_plan_build: level %d of %d", level, m.top + 1);
     return CUP_ERR_ARG;
   }
-  const Level &v = m.lv[level];
+  const Level &v = level < 0 ? m.leafv : m.lv[level];
   memset(out, 0, sizeof *out);
   out->nblk = m.nblk;
   out->nslot = m.nslot;
@@ -449,7 +460,17 @@ int cup_plan_build(const CupBlk *gblk, long long G, const int *owner, int nranks
   out->nsend = (int)v.face_sslot.size();
   out->nrecv = v.nface_recv;
   out->act = dup_ints(v.act);
-  out->ijk = dup_ints(v.ijk);
+  std::vector<int> ijk = v.ijk;
+  if (level < 0) {  // leaf context: block indices of the local leaves, each at its own level
+    ijk.clear();
+    for (int sl : v.act) {
+      ijk.push_back(m.blk[(size_t)sl].ix);
+      ijk.push_back(m.blk[(size_t)sl].iy);
+      ijk.push_back(m.blk[(size_t)sl].iz);
+    }
+  }
+  ijk.resize(v.act.size() * 3, 0);
+  out->ijk = dup_ints(ijk);
   out->nbr = dup_ints(v.nbr);
   out->send_slot = dup_ints(v.face_sslot);
   out->send_plane = dup_ints(v.face_splane);
@@ -462,6 +483,19 @@ int cup_plan_build(const CupBlk *gblk, long long G, const int *owner, int nranks
   out->nres_recv = (int)v.res_rslot.size();
   out->res_recv_slot = dup_ints(v.res_rslot);
   out->res_recv_oct = dup_ints(v.res_roct);
+  out->ghosted = v.ghosted ? 1 : 0;
+  out->nghost = v.nghost;
+  std::vector<int> ext = v.ext;
+  ext.resize(v.act.size() * 24, -1);
+  out->ext = dup_ints(ext);
+  out->nbsend = (int)v.blk_sslot.size();
+  out->nbrecv = (int)v.blk_rslot.size();
+  out->bsend_slot = dup_ints(v.blk_sslot);
+  out->bsend_kind = dup_ints(v.blk_skind);
+  out->bsend_peer = dup_ints(v.blk_speer);
+  out->bsend_idx = dup_ints(v.blk_sidx);
+  out->brecv_slot = dup_ints(v.blk_rslot);
+  out->brecv_kind = dup_ints(v.blk_rkind);
   return CUP_OK;
 }
 
@@ -481,10 +515,21 @@ void cup_plan_free(CupPlan *p) {
   free(p->res_recv_cnt);
   free(p->res_recv_slot);
   free(p->res_recv_oct);
+  free(p->ext);
+  free(p->bsend_slot);
+  free(p->bsend_kind);
+  free(p->bsend_peer);
+  free(p->bsend_idx);
+  free(p->brecv_slot);
+  free(p->brecv_kind);
   memset(p, 0, sizeof *p);
 }
 
 long long cup_kernel_launches(const CupCtx *c) { return c->launches; }
+int cup_trace_report(CupCtx *c, char *out, size_t cap) {
+  CUP_ENTER(c);
+  return trace_report(c, out, cap);
+}
 int cup_time_smooth(CupCtx *c, int level, int reps, float *ms) {
   CUP_ENTER(c);
   return time_smooth(c, level, reps, ms);

@@ -71,6 +71,7 @@ static int load_nccl() {
   return CUP_OK;
 }
 
+enum { K_FACE = 0, K_RES = 1, K_PRO = 2, K_BLK = 3, NKIND = 4 };  // exchange kinds of one context
 enum { RED_MAX = 32 };  // values per window all-reduce (GMRES: j + 2 <= 32; fish moments: 29)
 
 struct Comm {
@@ -83,7 +84,7 @@ struct Comm {
   size_t flag_bytes = 0;               // bytes in front of the per-level areas
   std::vector<char *> peer_win;        // mapped base of every rank's window (own = win)
   char **d_peer_win = nullptr;
-  unsigned long long *d_seq = nullptr; // [levels][3] exchange counters of THIS rank (face, restrict, prolong) + [1] all-reduce
+  unsigned long long *d_seq = nullptr; // [contexts][NKIND] exchange counters of THIS rank (face, restrict, prolong, blocks) + [1] all-reduce
   size_t red_flag_index = 0;           // index (in 8-byte words) of the [nranks] all-reduce flag words
   size_t red_data_off = 0;             // byte offset of the all-reduce data [2][nranks][RED_MAX] doubles
 };
@@ -298,7 +299,7 @@ static int allreduce_impl(CupCtx *c, int first, int n, bool is_max) {
     for (int o = 0; o < n; o += RED_MAX) {
       const int m = n - o < RED_MAX ? n - o : RED_MAX;
       k_allreduce_win<<<1, 256, 0, c->stream>>>(c->d_scal + first + o, m, is_max ? 1 : 0,
-                                                cm->d_seq + (size_t)(c->top + 1) * 3, cm->d_peer_win, c->rank,
+                                                cm->d_seq + (size_t)(c->top + 2) * NKIND, cm->d_peer_win, c->rank,
                                                 c->nranks, cm->red_flag_index, cm->red_data_off, c->h_err);
       c->launches++;
     }
@@ -330,7 +331,6 @@ int comm_allreduce(CupCtx *c, int first, int n) { return allreduce_impl(c, first
 //  * NCCL (CUP_P2P=0 or IPC unavailable): pack to a staging buffer, grouped
 //    ncclSend/ncclRecv per peer.
 // ===========================================================================
-enum { K_FACE = 0, K_RES = 1, K_PRO = 2 };
 
 int comm_allreduce_max(CupCtx *c, int first, int n) { return allreduce_impl(c, first, n, true); }
 
@@ -434,6 +434,82 @@ __global__ void __launch_bounds__(64) k_get(const int *__restrict__ rslot, const
   comm_post_at_exit(post);
 }
 
+// ---------------------------------------------------------------------------
+// ghost BLOCKS (levels with coarse-fine interfaces and the leaf context of multi-level meshes):
+// whole 8^3 blocks, as the reference's halo_sync ships them (main.c:3101-3112)
+// ---------------------------------------------------------------------------
+// multigrid context: entry e = block sslot[e] of the swept vector (kind 0) or of the canonical U0
+// (kind 1: a coarser leaf behind an interface)
+template <typename Real>
+__global__ void __launch_bounds__(128) k_pack_blocks_mg(const int *__restrict__ sslot, const int *__restrict__ skind,
+                                                        int n, SlotVec<Real> same, SlotVec<Real> can,
+                                                        Real *const *__restrict__ dst0, Real *const *__restrict__ dst1,
+                                                        const unsigned long long *__restrict__ seq, PostDesc post) {
+  const bool odd = ((*(const volatile unsigned long long *)seq + 1) & 1) != 0;
+  for (int e = blockIdx.x; e < n; e += gridDim.x) {
+    const Real *src = (skind[e] ? can : same).at(sslot[e]);
+    Real *d = (odd ? dst1 : dst0)[e];
+    for (int j = threadIdx.x; j < 512; j += blockDim.x)
+      d[j] = src[j];
+  }
+  comm_post_at_exit(post);
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(128) k_unpack_blocks_mg(const int *__restrict__ rslot, const int *__restrict__ rkind,
+                                                          int n, const Real *__restrict__ area, long long stride,
+                                                          const unsigned long long *__restrict__ seq,
+                                                          SlotVec<Real> same, SlotVec<Real> can, WaitDesc wait) {
+  comm_wait_cta(wait);
+  const Real *in = area + ((*(const volatile unsigned long long *)seq & 1) ? stride : 0);
+  for (int e = blockIdx.x; e < n; e += gridDim.x) {
+    Real *d = (rkind[e] ? can : same).at(rslot[e]);
+    const Real *q = in + (size_t)e * 512;
+    for (int j = threadIdx.x; j < 512; j += blockDim.x)
+      d[j] = ld_recv(q + j);
+  }
+}
+
+// leaf context: ncomp flat component arrays, entry layout [comp][512]
+template <typename Real>
+struct BlkComps {
+  const Real *src[BLK_COMPS];
+  Real *dst[BLK_COMPS];
+};
+
+template <typename Real>
+__global__ void __launch_bounds__(128) k_pack_blocks_leaf(const int *__restrict__ sslot, int n, int ncomp, int stride_c,
+                                                          BlkComps<Real> cp, Real *const *__restrict__ dst0,
+                                                          Real *const *__restrict__ dst1,
+                                                          const unsigned long long *__restrict__ seq, PostDesc post) {
+  const bool odd = ((*(const volatile unsigned long long *)seq + 1) & 1) != 0;
+  for (int e = blockIdx.x; e < n; e += gridDim.x) {
+    Real *d = (odd ? dst1 : dst0)[e];
+    const size_t off = (size_t)sslot[e] * 512;
+    for (int q = 0; q < ncomp; q++)
+      for (int j = threadIdx.x; j < 512; j += blockDim.x)
+        d[(size_t)q * stride_c + j] = cp.src[q][off + j];
+  }
+  comm_post_at_exit(post);
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(128) k_unpack_blocks_leaf(const int *__restrict__ rslot, int n, int ncomp,
+                                                            int stride_c, int entry_reals,
+                                                            const Real *__restrict__ area, long long stride,
+                                                            const unsigned long long *__restrict__ seq,
+                                                            BlkComps<Real> cp, long long dst_off, WaitDesc wait) {
+  comm_wait_cta(wait);
+  const Real *in = area + ((*(const volatile unsigned long long *)seq & 1) ? stride : 0);
+  for (int e = blockIdx.x; e < n; e += gridDim.x) {
+    const size_t off = (size_t)((long long)rslot[e] - dst_off) * 512;
+    const Real *q0 = in + (size_t)e * entry_reals;
+    for (int q = 0; q < ncomp; q++)
+      for (int j = threadIdx.x; j < 512; j += blockDim.x)
+        cp.dst[q][off + j] = ld_recv(q0 + (size_t)q * stride_c + j);
+  }
+}
+
 // bump this rank's sequence number for (level, kind) and publish it to the peers' flag words
 __global__ void __launch_bounds__(64) k_signal(unsigned long long *seq, char *const *peer_win, const int *peers, int np,
                                                size_t flag_index) {
@@ -530,6 +606,13 @@ void comm_free_level_buffers(CupCtx *c) {
     cudaFree(v.d_fptr1);
     cudaFree(v.d_rptr);
     cudaFree(v.d_pptr);
+    cudaFree(v.d_bptr0);
+    cudaFree(v.d_bptr1);
+    cudaFree(v.d_blk_speers);
+    cudaFree(v.d_blk_rpeers);
+    v.d_bptr0 = v.d_bptr1 = nullptr;
+    v.d_blk_speers = v.d_blk_rpeers = nullptr;
+    v.d_brecv = nullptr;
     for (int k = 0; k < 3; k++) {
       cudaFree(v.d_speers[k]);
       cudaFree(v.d_rpeers[k]);
@@ -537,6 +620,19 @@ void comm_free_level_buffers(CupCtx *c) {
     }
     v.d_fsend = v.d_frecv = v.d_rsend = v.d_rrecv = v.d_precv = nullptr;
     v.d_fptr0 = v.d_fptr1 = v.d_rptr = v.d_pptr = nullptr;
+  }
+  {
+    Level &v = c->leafv;  // the leaf context only has ghost blocks
+    cudaFree(v.d_bptr0);
+    cudaFree(v.d_bptr1);
+    cudaFree(v.d_counters);
+    cudaFree(v.d_blk_speers);
+    cudaFree(v.d_blk_rpeers);
+    v.d_bptr0 = v.d_bptr1 = nullptr;
+    v.d_counters = nullptr;
+    v.d_blk_speers = v.d_blk_rpeers = nullptr;
+    v.d_brecv = nullptr;
+    v.p2p = false;
   }
 }
 
@@ -551,8 +647,9 @@ static int open_windows(CupCtx *c, bool *ok) {
   const int R = c->nranks;
   const size_t rb = (size_t)c->real_bytes;
   *ok = false;
-  // [level][kind][rank] exchange flags | [rank] all-reduce flags | all-reduce data [2][R][RED_MAX]
-  const size_t nflag = (size_t)(c->top + 1) * 3 * R;
+  // [context][kind][rank] exchange flags | [rank] all-reduce flags | all-reduce data [2][R][RED_MAX];
+  // contexts: the multigrid levels 0..top and the leaf context (top + 1)
+  const size_t nflag = (size_t)(c->top + 2) * NKIND * R;
   cm->red_flag_index = nflag;
   cm->red_data_off = ((nflag + (size_t)R) * sizeof(unsigned long long) + 255) / 256 * 256;
   cm->flag_bytes = (cm->red_data_off + (size_t)2 * R * RED_MAX * sizeof(double) + 255) / 256 * 256;
@@ -605,10 +702,47 @@ static int open_windows(CupCtx *c, bool *ok) {
     return CUP_OK;
   }
   CUP_TRY(up(&cm->d_peer_win, cm->peer_win));
-  const size_t nseq = (size_t)(c->top + 1) * 3 + 1;
+  const size_t nseq = (size_t)(c->top + 2) * NKIND + 1;
   CUP_CUDA(cudaMalloc((void **)&cm->d_seq, nseq * sizeof(unsigned long long)));
   CUP_CUDA(cudaMemset(cm->d_seq, 0, nseq * sizeof(unsigned long long)));
   *ok = true;
+  return CUP_OK;
+}
+
+// ghost blocks of one context: own area inside the window, destination of every send entry, peers
+static int setup_ghost_blocks(CupCtx *c, Level &v, bool p2p, bool is_leaf) {
+  Comm *cm = (Comm *)c->comm;
+  if (!v.ghosted)
+    return CUP_OK;
+  if (!p2p) {
+    set_error("multi-level meshes across ranks need the peer-window transport (CUDA IPC); CUP_P2P=0 / NCCL staging "
+              "is implemented for uniform meshes only");
+    return CUP_ERR_UNSUPPORTED;
+  }
+  const size_t rb = (size_t)c->real_bytes;
+  const int me = c->rank;
+  const size_t ent = (size_t)512 * v.blk_ncomp;
+  const size_t ns = v.blk_sslot.size();
+  std::vector<char *> b0(ns), b1(ns);
+  v.d_brecv = cm->win + cm->flag_bytes + (size_t)v.win_blk[me] * rb;
+  v.blk_stride = (long long)v.win_nblk[me] * (long long)ent;
+  for (size_t e = 0; e < ns; e++) {
+    const int p = v.blk_speer[e];
+    b0[e] = cm->peer_win[p] + cm->flag_bytes + ((size_t)v.win_blk[p] + (size_t)v.blk_sidx[e] * ent) * rb;
+    b1[e] = b0[e] + (size_t)v.win_nblk[p] * ent * rb;
+  }
+  CUP_TRY(up((char ***)&v.d_bptr0, b0));
+  CUP_TRY(up((char ***)&v.d_bptr1, b1));
+  v.blk_speers = peers_of(v.blk_scnt);
+  v.blk_rpeers = peers_of(v.blk_rcnt);
+  CUP_TRY(up(&v.d_blk_speers, v.blk_speers));
+  CUP_TRY(up(&v.d_blk_rpeers, v.blk_rpeers));
+  if (is_leaf) {
+    CUP_CUDA(cudaMalloc((void **)&v.d_counters, 8 * sizeof(unsigned int)));
+    CUP_CUDA(cudaMemset(v.d_counters, 0, 8 * sizeof(unsigned int)));
+    v.p2p = true;
+    v.d_seq = cm->d_seq + (size_t)v.xid * NKIND;
+  }
   return CUP_OK;
 }
 
@@ -637,7 +771,10 @@ int comm_alloc_level_buffers(CupCtx *c) {
   }
   cm->p2p = p2p;
   const int me = c->rank;
+  c->leafv.xid = c->top + 1;
+  CUP_TRY(setup_ghost_blocks(c, c->leafv, p2p, true));
   for (auto &v : c->lv) {
+    v.xid = v.L;
     const size_t ns = v.face_sslot.size(), nr = (size_t)v.nface_recv;
     const size_t cs = (size_t)sum(v.res_scnt), cr = (size_t)sum(v.res_rcnt);
     std::vector<char *> f0(ns), f1(ns), rp(cs), pp(cr);
@@ -735,7 +872,8 @@ int comm_alloc_level_buffers(CupCtx *c) {
     }
     v.p2p = p2p;
     v.rface_stride = p2p ? (long long)nr * 64 : 0;
-    v.d_seq = p2p ? cm->d_seq + (size_t)v.L * 3 : nullptr;
+    v.d_seq = p2p ? cm->d_seq + (size_t)v.xid * NKIND : nullptr;
+    CUP_TRY(setup_ghost_blocks(c, v, p2p, false));
   }
   return CUP_OK;
 }
@@ -748,12 +886,12 @@ static WaitDesc make_wait(CupCtx *c, const Level &v, int kind) {
   Comm *cm = (Comm *)c->comm;
   if (!cm || !v.p2p || v.rpeers[kind].empty())
     return w;
-  w.seq = cm->d_seq + (size_t)v.L * 3 + kind;
-  w.flags = (const unsigned long long *)cm->win + ((size_t)v.L * 3 + kind) * c->nranks;
+  w.seq = cm->d_seq + (size_t)v.xid * NKIND + kind;
+  w.flags = (const unsigned long long *)cm->win + ((size_t)v.xid * NKIND + kind) * c->nranks;
   w.peers = v.d_rpeers[kind];
   w.np = (int)v.rpeers[kind].size();
   w.err = c->h_err;
-  w.code = 1 + v.L * 4 + kind;
+  w.code = 1 + v.xid * 4 + kind;
   return w;
 }
 
@@ -762,11 +900,11 @@ static PostDesc make_post(CupCtx *c, const Level &v, int kind, int counter) {
   Comm *cm = (Comm *)c->comm;
   if (!cm || !v.p2p)
     return p;
-  p.seq = cm->d_seq + (size_t)v.L * 3 + kind;
+  p.seq = cm->d_seq + (size_t)v.xid * NKIND + kind;
   p.peer_win = cm->d_peer_win;
   p.peers = v.d_speers[kind];
   p.np = (int)v.speers[kind].size();
-  p.flag_index = ((size_t)v.L * 3 + kind) * c->nranks + c->rank;
+  p.flag_index = ((size_t)v.xid * NKIND + kind) * c->nranks + c->rank;
   p.counter = v.d_counters + counter;
   return p;
 }
@@ -774,8 +912,8 @@ static PostDesc make_post(CupCtx *c, const Level &v, int kind, int counter) {
 // bump the sequence number of an exchange this rank takes part in without sending anything
 static int post_empty(CupCtx *c, Level &v, int kind) {
   Comm *cm = (Comm *)c->comm;
-  const size_t fidx = ((size_t)v.L * 3 + kind) * c->nranks + c->rank;
-  k_signal<<<1, 64, 0, c->stream>>>(cm->d_seq + (size_t)v.L * 3 + kind, cm->d_peer_win, v.d_speers[kind],
+  const size_t fidx = ((size_t)v.xid * NKIND + kind) * c->nranks + c->rank;
+  k_signal<<<1, 64, 0, c->stream>>>(cm->d_seq + (size_t)v.xid * NKIND + kind, cm->d_peer_win, v.d_speers[kind],
                                     (int)v.speers[kind].size(), fidx);
   c->launches++;
   return CUP_OK;
@@ -801,18 +939,18 @@ bool comm_fused_desc(CupCtx *c, Level &v, FusedComm *out) {
   out->bsend = v.d_bsend;
   out->fptr0 = v.d_fptr0;
   out->fptr1 = v.d_fptr1;
-  out->seq = cm->d_seq + (size_t)v.L * 3 + K_FACE;
-  out->my_flags = (const unsigned long long *)cm->win + ((size_t)v.L * 3 + K_FACE) * c->nranks;
+  out->seq = cm->d_seq + (size_t)v.xid * NKIND + K_FACE;
+  out->my_flags = (const unsigned long long *)cm->win + ((size_t)v.xid * NKIND + K_FACE) * c->nranks;
   out->rpeers = v.d_rpeers[K_FACE];
   out->nrp = (int)v.rpeers[K_FACE].size();
   out->peer_win = cm->d_peer_win;
   out->speers = v.d_speers[K_FACE];
   out->nsp = (int)v.speers[K_FACE].size();
-  out->flag_index = ((size_t)v.L * 3 + K_FACE) * c->nranks + c->rank;
+  out->flag_index = ((size_t)v.xid * NKIND + K_FACE) * c->nranks + c->rank;
   out->counters = v.d_counters;
   out->nbnd = (int)v.bnd.size();
   out->err = c->h_err;
-  out->code = 1 + v.L * 4 + K_FACE;
+  out->code = 1 + v.xid * 4 + K_FACE;
   return true;
 }
 
@@ -931,6 +1069,100 @@ int prolong_exchange(CupCtx *c, Level &v, SlotVec<Real> u, SlotVec<Real> us) {
   return CUP_OK;
 }
 
+// ---- ghost blocks --------------------------------------------------------------------------
+static void blk_descs(CupCtx *c, Level &v, PostDesc *post, WaitDesc *wait) {
+  Comm *cm = (Comm *)c->comm;
+  post->peers = v.d_blk_speers;
+  post->np = (int)v.blk_speers.size();
+  wait->peers = v.d_blk_rpeers;
+  wait->np = (int)v.blk_rpeers.size();
+  post->seq = cm->d_seq + (size_t)v.xid * NKIND + K_BLK;
+  post->peer_win = cm->d_peer_win;
+  post->flag_index = ((size_t)v.xid * NKIND + K_BLK) * c->nranks + c->rank;
+  post->counter = v.d_counters + 7;
+  wait->seq = post->seq;
+  wait->flags = (const unsigned long long *)cm->win + ((size_t)v.xid * NKIND + K_BLK) * c->nranks;
+  wait->err = c->h_err;
+  wait->code = 1 + v.xid * 4 + K_BLK;
+}
+
+// multigrid level with coarse-fine interfaces: refresh the ghost copies of `same` (blocks of this level
+// owned by other ranks) and of `can` (coarser leaves behind interfaces, canonical U0) before a sweep
+template <typename Real>
+int block_exchange_mg(CupCtx *c, Level &v, SlotVec<Real> same, SlotVec<Real> can) {
+  if (c->nranks == 1 || !v.ghosted)
+    return CUP_OK;
+  Comm *cm = (Comm *)c->comm;
+  PostDesc post;
+  WaitDesc wait;
+  blk_descs(c, v, &post, &wait);
+  const unsigned long long *seq = cm->d_seq + (size_t)v.xid * NKIND + K_BLK;
+  const int ns = (int)v.blk_sslot.size(), nr = (int)v.blk_rslot.size();
+  if (ns) {
+    k_pack_blocks_mg<Real><<<cgrid(c, ns), 128, 0, c->stream>>>(v.d_blk_sslot, v.d_blk_skind, ns, same, can,
+                                                               (Real *const *)v.d_bptr0, (Real *const *)v.d_bptr1, seq,
+                                                               post);
+    c->launches++;
+  } else {
+    k_signal<<<1, 64, 0, c->stream>>>(post.seq, cm->d_peer_win, nullptr, 0, post.flag_index);
+    c->launches++;
+  }
+  if (nr) {
+    k_unpack_blocks_mg<Real><<<cgrid(c, nr), 128, 0, c->stream>>>(v.d_blk_rslot, v.d_blk_rkind, nr,
+                                                                 (const Real *)v.d_brecv, v.blk_stride, seq, same, can,
+                                                                 wait);
+    c->launches++;
+  }
+  CUP_CUDA(cudaGetLastError());
+  return CUP_OK;
+}
+
+// leaf context of a multi-level mesh: ghost blocks of ncomp component arrays.  src[q]: [nblk][512] (own
+// leaves); dst[q]: where slot s >= nblk of component q lives is dst[q] + (s - dst_off) * 512 (dst_off = 0 for
+// the state arrays, which hold nstate blocks; = nblk for the ghost scratch of a flat vector)
+template <typename Real>
+int block_exchange_leaf(CupCtx *c, const Real *const *src, Real *const *dst, int ncomp, long long dst_off) {
+  Level &v = c->leafv;
+  if (c->nranks == 1 || !v.ghosted)
+    return CUP_OK;
+  if (ncomp > BLK_COMPS) {
+    set_error("block_exchange_leaf: %d components > %d", ncomp, (int)BLK_COMPS);
+    return CUP_ERR_ARG;
+  }
+  Comm *cm = (Comm *)c->comm;
+  PostDesc post;
+  WaitDesc wait;
+  blk_descs(c, v, &post, &wait);
+  const unsigned long long *seq = cm->d_seq + (size_t)v.xid * NKIND + K_BLK;
+  BlkComps<Real> cp;
+  for (int q = 0; q < BLK_COMPS; q++) {
+    cp.src[q] = q < ncomp ? src[q] : nullptr;
+    cp.dst[q] = q < ncomp ? dst[q] : nullptr;
+  }
+  const int ns = (int)v.blk_sslot.size(), nr = (int)v.blk_rslot.size();
+  if (ns) {
+    k_pack_blocks_leaf<Real><<<cgrid(c, ns), 128, 0, c->stream>>>(v.d_blk_sslot, ns, ncomp, 512, cp,
+                                                                 (Real *const *)v.d_bptr0, (Real *const *)v.d_bptr1, seq,
+                                                                 post);
+    c->launches++;
+  } else {
+    k_signal<<<1, 64, 0, c->stream>>>(post.seq, cm->d_peer_win, nullptr, 0, post.flag_index);
+    c->launches++;
+  }
+  if (nr) {
+    k_unpack_blocks_leaf<Real><<<cgrid(c, nr), 128, 0, c->stream>>>(v.d_blk_rslot, nr, ncomp, 512, 512 * v.blk_ncomp,
+                                                                   (const Real *)v.d_brecv, v.blk_stride, seq, cp,
+                                                                   dst_off, wait);
+    c->launches++;
+  }
+  CUP_CUDA(cudaGetLastError());
+  return CUP_OK;
+}
+
+template int block_exchange_mg<double>(CupCtx *, Level &, SlotVec<double>, SlotVec<double>);
+template int block_exchange_mg<float>(CupCtx *, Level &, SlotVec<float>, SlotVec<float>);
+template int block_exchange_leaf<double>(CupCtx *, const double *const *, double *const *, int, long long);
+template int block_exchange_leaf<float>(CupCtx *, const float *const *, float *const *, int, long long);
 template int slab_exchange<double>(CupCtx *, Level &, const SlabSrc<double> &, int, int);
 template int slab_exchange<float>(CupCtx *, Level &, const SlabSrc<float> &, int, int);
 template int halo_post<double>(CupCtx *, Level &, SlotVec<double>);

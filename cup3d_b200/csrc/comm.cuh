@@ -37,6 +37,11 @@ int restrict_exchange(CupCtx *c, Level &v, SlotVec<Real> f, SlotVec<Real> u, boo
 // one-sided transport: descriptors for kernels that wait for / publish an exchange themselves
 // (empty descriptors -- null seq -- on one rank, in NCCL mode, or when there is nothing to do)
 enum { COMM_FACE = 0, COMM_RES = 1, COMM_PRO = 2 };
+// ghost blocks (levels with coarse-fine interfaces / the leaf context of a multi-level mesh across ranks)
+template <typename Real>
+int block_exchange_mg(CupCtx *c, Level &v, SlotVec<Real> same, SlotVec<Real> can);
+template <typename Real>
+int block_exchange_leaf(CupCtx *c, const Real *const *src, Real *const *dst, int ncomp, long long dst_off);
 WaitDesc comm_wait_desc(CupCtx *c, Level &v, int kind);
 PostDesc comm_post_desc(CupCtx *c, Level &v, int kind);
 template <typename Real>

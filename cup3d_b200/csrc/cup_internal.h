@@ -103,6 +103,29 @@ struct Level {
   // fused prolongation (UpFuse, smooth_tma.cuh): [nact][7] parent index/octant of own + face neighbours
   std::vector<int> upinfo;
   int *d_upinfo = nullptr;
+  // ---- ghost BLOCKS (multi-level meshes across ranks; the reference ships whole blocks for every
+  // remote neighbour, halo_sync main.c:3101-3112).  On a level that has coarse-fine interfaces anywhere
+  // (and in the leaf context of a multi-level mesh) every block of another rank that a local block
+  // reads -- same-level neighbours, the coarser leaf behind an interface, the finer leaves, and for the
+  // wide advdiff stencil the edge / corner neighbours of interface blocks -- has a local GHOST SLOT
+  // appended after the rank's own slots; the tables refer to it like to any local block, so the
+  // interface kernels need no remote cases.  Before a sweep the owners push those blocks (comm.cu).
+  int xid = 0;                             // exchange id: index of this context's sequence numbers / flag words
+  bool ghosted = false;
+  int nghost = 0;                          // ghost slots of this context (leaf context: after nblk; MG: after own slots)
+  std::vector<int> blk_sslot, blk_skind;   // send: local slot, kind (0: the swept vector, 1: the canonical U0)
+  std::vector<int> blk_speer, blk_sidx;    // send: destination rank, entry in its block area
+  std::vector<int> blk_rslot, blk_rkind;   // recv (entry order): local ghost slot, kind
+  std::vector<int> blk_scnt, blk_rcnt;     // [nranks]
+  std::vector<long long> win_blk;          // [nranks] offset (Reals) of rank p's block area for this context
+  std::vector<int> win_nblk;               // [nranks] entries rank p receives
+  int *d_blk_sslot = nullptr, *d_blk_skind = nullptr, *d_blk_rslot = nullptr, *d_blk_rkind = nullptr;
+  std::vector<int> blk_speers, blk_rpeers; // ranks notified / awaited by the block exchange
+  int *d_blk_speers = nullptr, *d_blk_rpeers = nullptr;
+  void **d_bptr0 = nullptr, **d_bptr1 = nullptr;  // per send entry: destination (parity 0 / 1)
+  void *d_brecv = nullptr;                 // own block area
+  long long blk_stride = 0;                // Reals between the two parities
+  int blk_ncomp = 1;                       // components per entry the area is sized for (leaf context: 7)
   // levels with coarse-fine interfaces: blocks whose six neighbours are all same-level / wall run
   // the fast (TMA) kernels, the others the generic ghost fill
   std::vector<int> reg, irr, par_reg, par_irr;
@@ -114,6 +137,7 @@ struct HostMesh {
   int nranks = 1, rank = 0, top = -1, level_max = 1;
   int bpd[3] = {1, 1, 1};
   long long nblk = 0, nslot = 0, gblocks = 0, gnslot = 0, pin_local = -1;
+  long long nown = 0;  // own slots (leaves + own parents); slots >= nown are ghost blocks of other ranks
   std::vector<long long> win_reals;  // [nranks] size of every rank's receive window, in Reals
   double gvol = 0;
   bool leaf_uniform = true;
@@ -133,7 +157,9 @@ struct CupCtx {
   cudaStream_t stream = nullptr;    // where all work is enqueued (own_stream unless the caller set one)
   cudaStream_t own_stream = nullptr;  // blocking stream: ordered against the legacy default stream
   CupParams prm{};
-  long long nblk = 0, nslot = 0;   // LOCAL leaves / local slots
+  long long nblk = 0, nslot = 0;   // LOCAL leaves / local slots (own + ghost blocks of other ranks)
+  long long nstate = 0;            // blocks per state component: nblk + leaf-context ghost blocks
+  void *leaf_ghost = nullptr;      // ghost blocks of a flat vector in the leaf context (pois_op): [leafv.nghost][512]
   long long gblocks = 0;           // leaves over all ranks
   double gvol = 0;                 // volume over all ranks (pois_solve's vol)
   long long pin_local = -1;        // local index of block (0,0,0) or -1 (pois_pin)
@@ -190,6 +216,7 @@ int mg_vcycle_dev(CupCtx *c, const void *d_in, void *d_out);
 int pois_op_dev(CupCtx *c, const void *d_in, void *d_out);
 int mg_smooth_slots(CupCtx *c, int level, int n, void *d_u, const void *d_f);
 int time_smooth(CupCtx *c, int level, int reps, float *ms);
+int trace_report(CupCtx *c, char *out, size_t cap);
 
 // blas_kernels.cu
 int wdot(CupCtx *c, const void *a, const void *b, int scal_idx);  // -> d_scal[idx] (accumulates from 0)
@@ -223,6 +250,6 @@ int comm_init_host(CupCtx *c, int rank, int nranks, CupAllgatherFn fn, void *use
 int comm_check_error(CupCtx *c);  // after a stream synchronisation: CUP_ERR_COMM if a wait timed out
 int comm_unique_id(void *out, size_t bytes);
 
-enum { SCAL_N = 256, SLAB_PLANES = 9 };  // 3 components x 3 layers (k_advdiff) is the largest slab
+enum { SCAL_N = 256, SLAB_PLANES = 9, BLK_COMPS = 7 };  // leaf ghost blocks carry up to 7 fields (k_prhs: vel, udef, chi)  // 3 components x 3 layers (k_advdiff) is the largest slab
 
 }  // namespace cup

@@ -131,7 +131,8 @@ int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner_
 
   // ---- leaf context: every local leaf with its six face neighbours (same level, wall,
   // one coarser leaf, or four finer leaves).  Context of pois_op and the stencil sweeps on
-  // multi-level meshes (the reference's top-level mesh: lab_load :3579-3602).
+  // multi-level meshes (the reference's top-level mesh: lab_load :3579-3602).  Leaves of other
+  // ranks that a local leaf reads become ghost blocks (slots nblk, nblk+1, ...).
   {
     Level &lf = m->leafv;
     lf = Level();
@@ -143,88 +144,205 @@ int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner_
       map.reserve((size_t)G * 2);
       for (long long i = 0; i < G; i++)
         map.emplace(key_of(gblk[i].level, gblk[i].ix, gblk[i].iy, gblk[i].iz), (int)i);
-      for (long long i = 0; i < G; i++) {
-        if (owner[i] != rank)
-          continue;
+      auto find = [&](int L, int x, int y, int z) -> int {
+        auto it = map.find(key_of(L, x, y, z));
+        return it == map.end() ? -1 : it->second;
+      };
+      // face f of leaf i: code (global id / NBR_WALL / NBR_COARSE / NBR_FINE) and e4 (global ids / quadrant)
+      auto face_of = [&](long long i, int f, int &code, int (&e4)[4]) -> bool {
         const CupBlk &b = gblk[i];
         const int L = b.level;
         const int dim[3] = {bpd[0] << L, bpd[1] << L, bpd[2] << L};
         const int idx[3] = {b.ix, b.iy, b.iz};
-        lf.act.push_back(g2l[i]);
-        lf.hblk.push_back(b.h);
+        const int d = f / 2, sgn = (f & 1) ? 1 : -1, t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
+        int q[3] = {idx[0], idx[1], idx[2]};
+        q[d] += sgn;
+        code = NBR_WALL;
+        e4[0] = e4[1] = e4[2] = e4[3] = -1;
+        if (q[d] < 0 || q[d] >= dim[d])
+          return true;
+        int id = find(L, q[0], q[1], q[2]);
+        if (id >= 0) {
+          code = id;
+          return true;
+        }
+        if (L > 0 && (id = find(L - 1, q[0] / 2, q[1] / 2, q[2] / 2)) >= 0) {
+          code = NBR_COARSE;
+          e4[0] = id;
+          e4[1] = (idx[t1] & 1) + 2 * (idx[t2] & 1);
+          return true;
+        }
+        code = NBR_FINE;
+        for (int qd = 0; qd < 4; qd++) {
+          int cc[3];
+          cc[d] = 2 * q[d] + (sgn > 0 ? 0 : 1);
+          cc[t1] = 2 * q[t1] + (qd & 1);
+          cc[t2] = 2 * q[t2] + (qd >> 1);
+          e4[qd] = find(L + 1, cc[0], cc[1], cc[2]);
+          if (e4[qd] < 0) {
+            set_error("leaf level %d (%d,%d,%d): face %d has no neighbour at levels %d..%d (2:1 balance broken)", L,
+                      b.ix, b.iy, b.iz, f, L - 1, L + 1);
+            return false;
+          }
+        }
+        return true;
+      };
+      // every other leaf that leaf i reads: face neighbours; for blocks at a coarse-fine interface also
+      // the leaves behind the edges and corners (the wide advdiff stencil samples the coarse-level view
+      // around the block, cs_sample in amr_advdiff.cu)
+      std::vector<int> tmp;
+      auto reads = [&](long long i, std::vector<int> &out) -> bool {
+        out.clear();
+        bool iface = false;
         for (int f = 0; f < 6; f++) {
-          const int d = f / 2, s = (f & 1) ? 1 : -1, t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
-          int q[3] = {idx[0], idx[1], idx[2]};
-          q[d] += s;
-          int code = NBR_WALL, e4[4] = {-1, -1, -1, -1};
-          if (q[d] >= 0 && q[d] < dim[d]) {
-            auto it = map.find(key_of(L, q[0], q[1], q[2]));
-            if (it != map.end()) {
-              code = it->second;
-            } else if (L > 0 && (it = map.find(key_of(L - 1, q[0] / 2, q[1] / 2, q[2] / 2))) != map.end()) {
-              code = NBR_COARSE;
-              e4[0] = it->second;
-              e4[1] = (idx[t1] & 1) + 2 * (idx[t2] & 1);
-            } else {
-              code = NBR_FINE;
-              for (int qd = 0; qd < 4; qd++) {
+          int code, e4[4];
+          if (!face_of(i, f, code, e4))
+            return false;
+          if (code >= 0)
+            out.push_back(code);
+          else if (code == NBR_COARSE) {
+            out.push_back(e4[0]);
+            iface = true;
+          } else if (code == NBR_FINE) {
+            for (int z = 0; z < 4; z++)
+              out.push_back(e4[z]);
+            iface = true;
+          }
+        }
+        if (!iface)
+          return true;
+        const CupBlk &b = gblk[i];
+        const int L = b.level;
+        const int dim[3] = {bpd[0] << L, bpd[1] << L, bpd[2] << L};
+        for (int dz = -1; dz <= 1; dz++)
+          for (int dy = -1; dy <= 1; dy++)
+            for (int dx = -1; dx <= 1; dx++) {
+              if ((dx != 0) + (dy != 0) + (dz != 0) < 2)
+                continue;  // faces are done, the block itself is not a neighbour
+              const int o[3] = {dx, dy, dz}, q[3] = {b.ix + dx, b.iy + dy, b.iz + dz};
+              if (q[0] < 0 || q[1] < 0 || q[2] < 0 || q[0] >= dim[0] || q[1] >= dim[1] || q[2] >= dim[2])
+                continue;
+              int id = find(L, q[0], q[1], q[2]);
+              if (id < 0 && L > 0)
+                id = find(L - 1, q[0] / 2, q[1] / 2, q[2] / 2);
+              if (id >= 0) {
+                out.push_back(id);
+                continue;
+              }
+              // finer leaves that touch this block: the children of q on the side facing it
+              for (int c = 0; c < 8; c++) {
                 int cc[3];
-                cc[d] = 2 * q[d] + (s > 0 ? 0 : 1);
-                cc[t1] = 2 * q[t1] + (qd & 1);
-                cc[t2] = 2 * q[t2] + (qd >> 1);
-                auto jf = map.find(key_of(L + 1, cc[0], cc[1], cc[2]));
-                if (jf == map.end()) {
-                  set_error("leaf level %d (%d,%d,%d): face %d has no neighbour at levels %d..%d (2:1 balance broken)",
-                            L, b.ix, b.iy, b.iz, f, L - 1, L + 1);
-                  return CUP_ERR_MESH;
+                bool touch = true;
+                for (int d = 0; d < 3; d++) {
+                  const int bit = (c >> d) & 1;
+                  if ((o[d] < 0 && bit == 0) || (o[d] > 0 && bit == 1))
+                    touch = false;
+                  cc[d] = 2 * q[d] + bit;
                 }
-                e4[qd] = jf->second;
+                if (touch && (id = find(L + 1, cc[0], cc[1], cc[2])) >= 0)
+                  out.push_back(id);
               }
             }
-          }
-          if (code >= 0 || code == NBR_COARSE || code == NBR_FINE) {
-            // global -> local slots (multi-level meshes are single-rank for now)
-            int *pp[5] = {&code, &e4[0], &e4[1], &e4[2], &e4[3]};
-            for (int z = 0; z < 5; z++) {
-              if (z == 0 && code < 0)
-                continue;
-              if (z == 2 && code == NBR_COARSE)
-                continue;  // quadrant, not a slot
-              if (*pp[z] < 0)
-                continue;
-              if (owner[*pp[z]] != rank) {
-                set_error("multi-level meshes are single-rank in this build");
-                return CUP_ERR_UNSUPPORTED;
-              }
-              *pp[z] = g2l[*pp[z]];
+        return true;
+      };
+      // ghost blocks: need[r] = leaves of other ranks that rank r reads, ordered by (owner, global index).
+      // Every rank derives every rank's list, so both sides of the exchange and the window layouts agree
+      // without negotiation.
+      std::vector<std::vector<int>> need((size_t)nranks);
+      if (nranks > 1) {
+        for (long long i = 0; i < G; i++) {
+          if (!reads(i, tmp))
+            return CUP_ERR_MESH;
+          for (int g : tmp)
+            if (owner[g] != owner[i])
+              need[(size_t)owner[i]].push_back(g);
+        }
+        for (auto &v : need) {
+          std::sort(v.begin(), v.end(), [&](int a, int b2) {
+            return owner[a] != owner[b2] ? owner[a] < owner[b2] : a < b2;
+          });
+          v.erase(std::unique(v.begin(), v.end()), v.end());
+        }
+      }
+      std::unordered_map<int, int> ghost;  // global leaf -> local ghost slot
+      {
+        const std::vector<int> &mine = need[(size_t)rank];
+        ghost.reserve(mine.size() * 2);
+        lf.blk_rcnt.assign(nranks, 0);
+        lf.blk_scnt.assign(nranks, 0);
+        for (size_t e = 0; e < mine.size(); e++) {
+          ghost[mine[e]] = (int)(m->nblk + (long long)e);
+          lf.blk_rslot.push_back((int)(m->nblk + (long long)e));
+          lf.blk_rkind.push_back(0);
+          lf.blk_rcnt[owner[mine[e]]]++;
+        }
+        lf.nghost = (int)mine.size();
+        for (int r = 0; r < nranks; r++) {
+          if (r == rank)
+            continue;
+          for (size_t e = 0; e < need[(size_t)r].size(); e++)
+            if (owner[need[(size_t)r][e]] == rank) {
+              lf.blk_sslot.push_back(g2l[need[(size_t)r][e]]);
+              lf.blk_skind.push_back(0);
+              lf.blk_speer.push_back(r);
+              lf.blk_sidx.push_back((int)e);
+              lf.blk_scnt[r]++;
             }
-          }
+        }
+        lf.win_nblk.assign(nranks, 0);
+        for (int r = 0; r < nranks; r++)
+          lf.win_nblk[r] = (int)need[(size_t)r].size();
+        lf.ghosted = nranks > 1;
+        lf.blk_ncomp = BLK_COMPS;
+      }
+      auto local_of = [&](int g) -> int { return owner[g] == rank ? g2l[g] : ghost.at(g); };
+      for (long long i = 0; i < G; i++) {
+        if (owner[i] != rank)
+          continue;
+        lf.act.push_back(g2l[i]);
+        lf.hblk.push_back(gblk[i].h);
+        for (int f = 0; f < 6; f++) {
+          int code, e4[4];
+          if (!face_of(i, f, code, e4))
+            return CUP_ERR_MESH;
+          if (code >= 0)
+            code = local_of(code);
+          else if (code == NBR_COARSE)
+            e4[0] = local_of(e4[0]);
+          else if (code == NBR_FINE)
+            for (int z = 0; z < 4; z++)
+              e4[z] = local_of(e4[z]);
           lf.nbr.push_back(code);
           for (int z = 0; z < 4; z++)
             lf.ext.push_back(e4[z]);
         }
       }
       lf.uniform = false;
-      // device hash of all leaves: key = key_of(...) + 1 (0 marks an empty bucket)
+      // device hash of the leaves this rank can read (own + ghosts): key = key_of(...) + 1 (0 = empty bucket)
       size_t cap = 64;
-      while (cap < (size_t)G * 2)
+      while (cap < (size_t)(m->nblk + lf.nghost) * 2)
         cap *= 2;
       lf.hkeys.assign(cap, 0ULL);
       lf.hvals.assign(cap, -1);
-      for (long long i = 0; i < G; i++) {
-        if (owner[i] != rank)
-          continue;
-        const unsigned long long k = key_of(gblk[i].level, gblk[i].ix, gblk[i].iy, gblk[i].iz) + 1;
+      auto hput = [&](int g, int slot) {
+        const unsigned long long k = key_of(gblk[g].level, gblk[g].ix, gblk[g].iy, gblk[g].iz) + 1;
         size_t h = (size_t)((k * 0x9E3779B97F4A7C15ULL) >> 20) & (cap - 1);
         while (lf.hkeys[h] != 0)
           h = (h + 1) & (cap - 1);
         lf.hkeys[h] = k;
-        lf.hvals[h] = g2l[i];
+        lf.hvals[h] = slot;
+      };
+      for (long long i = 0; i < G; i++) {
+        if (owner[i] != rank)
+          continue;
+        hput((int)i, g2l[i]);
         lf.bijk.push_back(gblk[i].level);
         lf.bijk.push_back(gblk[i].ix);
         lf.bijk.push_back(gblk[i].iy);
         lf.bijk.push_back(gblk[i].iz);
       }
+      for (int g : need[(size_t)rank])
+        hput(g, ghost.at(g));
     }
   }
 
@@ -284,6 +402,7 @@ int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner_
       break;
     // parents: one new global slot per distinct parent, first-appearance order;
     // owner = smallest rank among the children (mg_build, main.c:4561-4569)
+    // (their level is L - 1: glevel below)
     std::unordered_map<uint64_t, int> pmap;
     std::vector<Ent> next;
     next.reserve(cur.size() - na + na / 8 + 1);
@@ -335,8 +454,32 @@ int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner_
   for (long long s = G; s < gnslot; s++)
     if (owner[s] == rank)
       g2l[s] = (int)lnslot++;
-  m->nslot = lnslot;
+  m->nown = lnslot;
   m->gnslot = gnslot;
+  // level of every global slot, and which levels have coarse-fine interfaces ANYWHERE: on those, blocks of
+  // other ranks are read as ghost blocks (slots >= nown, one per remote block whatever the level that
+  // reads it); on uniform levels 8x8 faces travel (plans below)
+  std::vector<int> glevel((size_t)gnslot, 0);
+  std::vector<char> ghosted_level((size_t)m->top + 1, 0);
+  for (int L = 0; L <= m->top; L++) {
+    for (const Ent &e : gl[L].act)
+      glevel[(size_t)e.gslot] = L;
+    if (nranks > 1)
+      for (int code : gl[L].nbr)
+        if (code == NBR_COARSE) {
+          ghosted_level[(size_t)L] = 1;
+          break;
+        }
+  }
+  std::unordered_map<int, int> mg_ghost;  // global slot -> local ghost slot of this rank
+  auto ghost_slot = [&](int gs) -> int {
+    auto it = mg_ghost.find(gs);
+    if (it != mg_ghost.end())
+      return it->second;
+    const int ls = (int)lnslot++;
+    mg_ghost.emplace(gs, ls);
+    return ls;
+  };
 
   // ---- localise ----------------------------------------------------------
   for (int L = 0; L <= m->top; L++) {
@@ -349,17 +492,61 @@ int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner_
     std::vector<Xent> rx, sx;  // face recv / send
     // traffic matrices of this level over ALL ranks: fmat[s][d] faces, rmat[s][d] restricted children
     std::vector<long long> fmat((size_t)nranks * nranks, 0), rmat((size_t)nranks * nranks, 0);
+    const bool ghosted = nranks > 1 && ghosted_level[(size_t)L];
+    std::vector<std::vector<int>> need((size_t)nranks);  // ghosted level: global slots rank r reads from others
     if (nranks > 1)
       for (size_t k = 0; k < g.act.size(); k++) {
         const int os = owner[g.act[k].gslot];
         for (int f = 0; f < 6; f++) {
           const int gn = g.nbr[k * 6 + f];
-          if (gn >= 0 && owner[gn] != os)
+          if (ghosted) {
+            const int src = gn >= 0 ? gn : (gn == NBR_COARSE ? g.ext[(k * 6 + f) * 4] : -1);
+            if (src >= 0 && owner[src] != os)
+              need[(size_t)os].push_back(src);
+          } else if (gn >= 0 && owner[gn] != os)
             fmat[(size_t)os * nranks + owner[gn]]++;  // os sends its plane f to the neighbour's owner
         }
         if (L >= 1 && owner[g.pg[k]] != os)
           rmat[(size_t)os * nranks + owner[g.pg[k]]]++;
       }
+    if (ghosted) {
+      for (auto &nv : need) {
+        std::sort(nv.begin(), nv.end(), [&](int a, int b2) {
+          return owner[a] != owner[b2] ? owner[a] < owner[b2] : a < b2;
+        });
+        nv.erase(std::unique(nv.begin(), nv.end()), nv.end());
+      }
+      v.ghosted = true;
+      v.uniform = false;  // the sweeps of this level go through the interface path, which refreshes the ghost blocks
+      v.blk_ncomp = 1;
+      v.blk_rcnt.assign(nranks, 0);
+      v.blk_scnt.assign(nranks, 0);
+      // kind 0: a block of this level (read from the vector being swept); kind 1: a coarser leaf
+      // behind an interface (read from the canonical U0)
+      for (int gs : need[(size_t)rank]) {
+        v.blk_rslot.push_back(ghost_slot(gs));
+        v.blk_rkind.push_back(glevel[(size_t)gs] == L ? 0 : 1);
+        v.blk_rcnt[owner[gs]]++;
+      }
+      v.nghost = (int)need[(size_t)rank].size();
+      for (int r = 0; r < nranks; r++) {
+        if (r == rank)
+          continue;
+        for (size_t e = 0; e < need[(size_t)r].size(); e++) {
+          const int gs = need[(size_t)r][e];
+          if (owner[gs] != rank)
+            continue;
+          v.blk_sslot.push_back(g2l[gs]);
+          v.blk_skind.push_back(glevel[(size_t)gs] == L ? 0 : 1);
+          v.blk_speer.push_back(r);
+          v.blk_sidx.push_back((int)e);
+          v.blk_scnt[r]++;
+        }
+      }
+      v.win_nblk.assign(nranks, 0);
+      for (int r = 0; r < nranks; r++)
+        v.win_nblk[r] = (int)need[(size_t)r].size();
+    }
     for (size_t k = 0; k < g.act.size(); k++) {
       const int gs = g.act[k].gslot;
       if (owner[gs] != rank)
@@ -377,17 +564,15 @@ int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner_
           if (gn == NBR_COARSE) {
             v.uniform = false;
             const int gc = g.ext[(k * 6 + f) * 4];
-            if (owner[gc] != rank) {
-              set_error("coarse-fine interface across ranks (level %d): multi-level meshes are single-rank in this build", L);
-              return CUP_ERR_UNSUPPORTED;
-            }
             if (v.ext.size() < v.nbr.size() * 4 + 4)
               v.ext.resize((size_t)(v.nbr.size() + 1) * 4, -1);
-            v.ext[v.nbr.size() * 4 + 0] = g2l[gc];
+            v.ext[v.nbr.size() * 4 + 0] = owner[gc] == rank ? g2l[gc] : mg_ghost.at(gc);
             v.ext[v.nbr.size() * 4 + 1] = g.ext[(k * 6 + f) * 4 + 1];
           }
         } else if (owner[gn] == rank) {
           code = g2l[gn];
+        } else if (ghosted) {
+          code = mg_ghost.at(gn);  // a ghost block: addressed like a local one
         } else {
           code = 0;  // patched after sorting
           rx.push_back({owner[gn], -1, f ^ 1, lk * 6 + f});
@@ -516,13 +701,21 @@ int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner_
       (rem ? v.bnd : v.inner).push_back((int)k);
     }
   }
-  // lay out every rank's receive window: per level [faces parity 0][faces parity 1][restrict][prolong]
+  m->nslot = lnslot;  // own slots + ghost blocks
+  // lay out every rank's receive window: per level [faces parity 0][faces parity 1][restrict][prolong][ghost blocks x2]
   m->win_reals.assign(nranks, 0);
   int finest = m->top;
   while (finest > 0 && m->lv[finest].gnact == 0)
     finest--;
-  for (int L = 0; L <= m->top; L++)
+  for (int L = 0; L <= m->top; L++) {
     m->lv[L].win_slab.assign(nranks, -1);
+    m->lv[L].win_blk.assign(nranks, -1);
+    if (m->lv[L].win_nblk.empty())
+      m->lv[L].win_nblk.assign(nranks, 0);
+  }
+  m->leafv.win_blk.assign(nranks, -1);
+  if (m->leafv.win_nblk.empty())
+    m->leafv.win_nblk.assign(nranks, 0);
   for (int p = 0; p < nranks; p++) {
     long long off = 0;
     for (int L = 0; L <= m->top; L++) {
@@ -538,6 +731,14 @@ int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner_
         v.win_slab[p] = off;
         off += 2LL * v.win_nrecv[p] * 64 * SLAB_PLANES;
       }
+      if (v.ghosted) {
+        v.win_blk[p] = off;
+        off += 2LL * v.win_nblk[p] * 512 * v.blk_ncomp;
+      }
+    }
+    if (m->leafv.ghosted) {
+      m->leafv.win_blk[p] = off;
+      off += 2LL * m->leafv.win_nblk[p] * 512 * m->leafv.blk_ncomp;
     }
     m->win_reals[p] = off;
   }
@@ -576,6 +777,10 @@ void free_mesh(CupCtx *c) {
     cudaFree(v.d_face_splane);
     cudaFree(v.d_res_rslot);
     cudaFree(v.d_res_roct);
+    cudaFree(v.d_blk_sslot);
+    cudaFree(v.d_blk_skind);
+    cudaFree(v.d_blk_rslot);
+    cudaFree(v.d_blk_rkind);
   }
   c->lv.clear();
   {
@@ -589,6 +794,10 @@ void free_mesh(CupCtx *c) {
     cudaFree(v.d_bijk);
     cudaFree(v.d_hkeys);
     cudaFree(v.d_hvals);
+    cudaFree(v.d_blk_sslot);
+    cudaFree(v.d_blk_skind);
+    cudaFree(v.d_blk_rslot);
+    cudaFree(v.d_blk_rkind);
     v = Level();
   }
   cudaFree(c->d_list);
@@ -614,6 +823,7 @@ int build_mesh(CupCtx *c, const CupBlk *gblk, long long G, const int *owner, con
   c->win_reals.swap(m.win_reals);
   c->nblk = m.nblk;
   c->nslot = m.nslot;
+  c->nstate = m.nblk + m.leafv.nghost;
   c->gblocks = m.gblocks;
   c->gvol = m.gvol;
   c->pin_local = m.pin_local;
@@ -676,6 +886,10 @@ int build_mesh(CupCtx *c, const CupBlk *gblk, long long G, const int *owner, con
     CUP_TRY(upload(&v.d_face_splane, v.face_splane));
     CUP_TRY(upload(&v.d_res_rslot, v.res_rslot));
     CUP_TRY(upload(&v.d_res_roct, v.res_roct));
+    CUP_TRY(upload(&v.d_blk_sslot, v.blk_sslot));
+    CUP_TRY(upload(&v.d_blk_skind, v.blk_skind));
+    CUP_TRY(upload(&v.d_blk_rslot, v.blk_rslot));
+    CUP_TRY(upload(&v.d_blk_rkind, v.blk_rkind));
   }
   {
     Level &v = c->leafv;
@@ -692,6 +906,10 @@ int build_mesh(CupCtx *c, const CupBlk *gblk, long long G, const int *owner, con
     }
     CUP_TRY(upload(&v.d_reg, v.reg));
     CUP_TRY(upload(&v.d_irr, v.irr));
+    CUP_TRY(upload(&v.d_blk_sslot, v.blk_sslot));
+    CUP_TRY(upload(&v.d_blk_skind, v.blk_skind));
+    CUP_TRY(upload(&v.d_blk_rslot, v.blk_rslot));
+    CUP_TRY(upload(&v.d_blk_rkind, v.blk_rkind));
     CUP_TRY(upload(&v.d_bijk, v.bijk));
     CUP_TRY(upload(&v.d_hkeys, v.hkeys));
     CUP_TRY(upload(&v.d_hvals, v.hvals));

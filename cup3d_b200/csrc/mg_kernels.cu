@@ -462,6 +462,10 @@ int smooth_level(CupCtx *c, Level &v, int n, Arr<Real> &a, bool first_is_zero, c
       SlotVec<Real> &src = (it & 1) ? a.u1 : a.u0;
       SlotVec<Real> &dst = (it & 1) ? a.u0 : a.u1;
       const bool zero = it == 0 && first_is_zero;
+      if (!zero)  // blocks of other ranks this sweep reads (ghost blocks; no-op on one rank)
+        CUP_TRY(block_exchange_mg<Real>(c, v, src, a.u0));
+      if (v.act.empty())
+        continue;  // this rank holds nothing of the level (it still took part in the exchange above)
       if (!zero && smooth_use_tma() && amr_split() && !v.reg.empty()) {
         // regular blocks (all neighbours same level / wall): TMA sweep; interface blocks: generic
         const Real hh = (Real)v.h;
@@ -538,12 +542,45 @@ int smooth_level(CupCtx *c, Level &v, int n, Arr<Real> &a, bool first_is_zero, c
   return CUP_OK;
 }
 
-// CUP_TRACE=1: time the phases of one eager V-cycle with CUDA events (debug aid)
+// Phase timing of a V-cycle (diagnostics).
+//   CUP_TRACE=1: eager launches bracketed by CUDA events, summary on stderr after every cycle.
+//   CUP_STAMP=1: a one-thread kernel stores %globaltimer after every phase; it is captured into the
+//                CUDA graph like any other node, so the REPLAYED cycle is what gets measured (the
+//                eager trace is dominated by host launch latency at 8 GPUs).  cup_trace_report()
+//                returns "phase ns" lines of the last cycle.
+__global__ void k_stamp(unsigned long long *slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *slot = t;
+}
+
 struct Trace {
   std::vector<cudaEvent_t> ev;
   std::vector<std::string> name;
-  bool on = false;
+  bool on = false, stamp = false;
+  unsigned long long *d_stamps = nullptr;
+  int nstamp = 0;
+  enum { MAX_STAMPS = 256 };
+  void begin(CupCtx *c) {
+    const char *e = getenv("CUP_TRACE"), *s = getenv("CUP_STAMP");
+    on = e && atoi(e) != 0;
+    stamp = s && atoi(s) != 0;
+    if (stamp) {
+      if (!d_stamps)
+        cudaMalloc((void **)&d_stamps, MAX_STAMPS * sizeof(unsigned long long));
+      nstamp = 0;
+      name.clear();
+    }
+    mark(c, "start");
+  }
   void mark(CupCtx *c, const std::string &n) {
+    if (stamp) {
+      if (d_stamps && nstamp < MAX_STAMPS) {
+        k_stamp<<<1, 1, 0, c->stream>>>(d_stamps + nstamp++);
+        name.push_back(n);
+      }
+      return;
+    }
     if (!on)
       return;
     cudaEvent_t e;
@@ -553,7 +590,7 @@ struct Trace {
     name.push_back(n);
   }
   void report(CupCtx *c) {
-    if (!on || ev.empty())
+    if (stamp || !on || ev.empty())
       return;
     cudaStreamSynchronize(c->stream);
     std::map<std::string, float> acc;
@@ -578,11 +615,7 @@ static Trace g_tr;
 template <typename Real>
 int vcycle_t(CupCtx *c, const Real *d_in, Real *d_out) {
   const int nleaf = (int)c->nblk;
-  {
-    const char *e = getenv("CUP_TRACE");
-    g_tr.on = e && atoi(e) != 0;
-  }
-  g_tr.mark(c, "start");
+  g_tr.begin(c);
   Arr<Real> a;
   a.u0 = SlotVec<Real>{d_out, (Real *)c->u0_x, nleaf};
   a.u1 = SlotVec<Real>{(Real *)c->u1_leaf, (Real *)c->u1_x, nleaf};
@@ -609,6 +642,8 @@ int vcycle_t(CupCtx *c, const Real *d_in, Real *d_out) {
     const PostDesc dpost = v.uniform ? comm_post_desc(c, v, COMM_RES) : PostDesc{};
     if (!dwait.seq)
       CUP_TRY(halo_wait(c, v));
+    if (!v.uniform || v.ghosted)
+      CUP_TRY(block_exchange_mg<Real>(c, v, a.u0, a.u0));
     if (!v.act.empty()) {
       const int grid = grid_for(c, (long long)v.act.size(), 12);
       if (!v.uniform && smooth_use_tma() && amr_split() && !v.reg.empty()) {
@@ -616,11 +651,11 @@ int vcycle_t(CupCtx *c, const Real *d_in, Real *d_out) {
                                       (int)v.reg.size()));
         if (!v.irr.empty()) {
           CUP_TRY(down_amr_launch<Real>(c, view(v), v.d_pslot, v.d_oct, a.u0, a.f, (Real)v.h, v.d_irr,
-                                        (int)v.irr.size()));
+                                        (int)v.irr.size(), v.d_rptr));
           c->launches++;
         }
       } else if (!v.uniform)
-        CUP_TRY(down_amr_launch<Real>(c, view(v), v.d_pslot, v.d_oct, a.u0, a.f, (Real)v.h));
+        CUP_TRY(down_amr_launch<Real>(c, view(v), v.d_pslot, v.d_oct, a.u0, a.f, (Real)v.h, nullptr, -1, v.d_rptr));
       else if (smooth_use_tma())
         CUP_TRY(down_tma_launch<Real>(c, view(v), v.d_pslot, v.d_oct, a.u0, a.f, (Real)v.h, v.d_rptr, nullptr, -1,
                                       &dwait, &dpost));
@@ -636,6 +671,8 @@ int vcycle_t(CupCtx *c, const Real *d_in, Real *d_out) {
     const WaitDesc twait = (w.uniform && !w.par.empty()) ? comm_wait_desc(c, w, COMM_FACE) : WaitDesc{};
     if (!twait.seq)
       CUP_TRY(halo_wait(c, w));
+    if (!w.uniform || w.ghosted)
+      CUP_TRY(block_exchange_mg<Real>(c, w, a.u0, a.u0));  // the restricted u of other ranks' blocks (ghost blocks)
     if (!w.par.empty()) {
       const int gridw = grid_for(c, (long long)w.par.size(), 12);
       if (!w.uniform && smooth_use_tma() && amr_split()) {
@@ -784,7 +821,15 @@ int pois_op_t(CupCtx *c, const Real *d_in, Real *d_out) {
   }
   const int nleaf = (int)c->nblk;
   SlotVec<Real> u{const_cast<Real *>(d_in), nullptr, nleaf}, o{d_out, nullptr, nleaf}, us{nullptr, nullptr, nleaf};
-  CUP_TRY(halo_exchange<Real>(c, v, u));
+  if (!c->leaf_uniform && c->nranks > 1) {
+    // multi-level mesh across ranks: leaves of other ranks are ghost blocks behind the own ones (slots >= nblk)
+    u.extra = (Real *)c->leaf_ghost;
+    const Real *src[1] = {d_in};
+    Real *dst[1] = {(Real *)c->leaf_ghost};
+    CUP_TRY(block_exchange_leaf<Real>(c, src, dst, 1, c->nblk));
+  } else {
+    CUP_TRY(halo_exchange<Real>(c, v, u));
+  }
   const Real h = (Real)v.h;
   // stencil_run(&st_lhs / &st_mg, list, n): only the listed blocks (cup_stencil_run)
   const int *sub = c->run_nsub >= 0 ? c->run_sub : nullptr;
@@ -963,6 +1008,31 @@ int mg_vcycle_dev(CupCtx *c, const void *d_in, void *d_out) {
   CUP_CUDA(cudaGraphLaunch(it->second.exec, c->stream));
   c->launches += it->second.launches;
   return CUP_OK;
+}
+
+// "phase ns" lines of the last V-cycle that ran with CUP_STAMP=1 (device timestamps, so also valid
+// for a graph replay); returns the number of bytes written
+int trace_report(CupCtx *c, char *out, size_t cap) {
+  if (!out || cap == 0)
+    return 0;
+  out[0] = 0;
+  if (!g_tr.stamp || g_tr.nstamp < 2)
+    return 0;
+  cudaStreamSynchronize(c->stream);
+  std::vector<unsigned long long> h((size_t)g_tr.nstamp);
+  if (cudaMemcpy(h.data(), g_tr.d_stamps, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) !=
+      cudaSuccess)
+    return 0;
+  size_t off = 0;
+  for (int i = 1; i < g_tr.nstamp && off + 64 < cap; i++) {
+    std::string nm = g_tr.name[(size_t)i];
+    for (char &ch : nm)
+      if (ch == ' ')
+        ch = '_';
+    off += (size_t)snprintf(out + off, cap - off, "%s %lld\n", nm.c_str(),
+                            (long long)(h[(size_t)i] - h[(size_t)i - 1]));
+  }
+  return (int)off;
 }
 
 int pois_op_dev(CupCtx *c, const void *d_in, void *d_out) {

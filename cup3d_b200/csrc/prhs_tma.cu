@@ -84,7 +84,9 @@ __global__ void __launch_bounds__(TPB, 6) k_prhs_tma(LevelView lv, PrhsArgs<Real
   __shared__ PrhsStage<Real> s;
   const int t = threadIdx.x, x = t & 7, y = t >> 3, a = t & 7, c2 = t >> 3;
   const Real *rsl = lv.rslab ? rslab_of<Real>(lv) : nullptr;
-  auto rem = [&](int nbc, int q) -> Real { return rsl[(size_t)(kRemote0 - nbc) * (64 * kSlabPlanes) + q * 64 + t]; };
+  auto rem = [&](int nbc, int q) -> Real {  // stored by another GPU: read through L2
+    return __ldcg(rsl + (size_t)(kRemote0 - nbc) * (64 * kSlabPlanes) + q * 64 + t);
+  };
   const int nmine = lv.nact > (int)blockIdx.x ? (lv.nact - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   if (nmine == 0)
     return;

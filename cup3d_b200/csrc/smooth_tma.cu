@@ -392,8 +392,9 @@ int get_map(CupCtx *c, const void *base, long long nblocks, int kind, CUtensorMa
 }  // namespace
 
 int tma_slab_maps(CupCtx *c, const void *leaf, CUtensorMap out[2]) {
-  CUP_TRY(get_map(c, leaf, c->nblk, 6, &out[0]));
-  CUP_TRY(get_map(c, leaf, c->nblk, 7, &out[1]));
+  // state components hold nstate = nblk + leaf-context ghost blocks
+  CUP_TRY(get_map(c, leaf, c->nstate, 6, &out[0]));
+  CUP_TRY(get_map(c, leaf, c->nstate, 7, &out[1]));
   return CUP_OK;
 }
 

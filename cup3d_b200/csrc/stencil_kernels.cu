@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_advdiff(LevelView lv, const int *
   // ghost value of component c, layer l (counted from the face) of the slab received for code nbc
   // (element e of the 8x8 face: the thread's own for z and y faces, any for x faces)
   auto rem = [&](int nbc, int c, int l, int e) -> Real {
-    return rsl[(size_t)(kRemote0 - nbc) * (64 * kSlabPlanes) + (c * 3 + l) * 64 + e];
+    return __ldcg(rsl + (size_t)(kRemote0 - nbc) * (64 * kSlabPlanes) + (c * 3 + l) * 64 + e);
   };
   for (int wi = blockIdx.x; wi < nsub; wi += gridDim.x) {
     const int b = sub ? sub[wi] : wi;
@@ -195,7 +195,9 @@ __global__ void __launch_bounds__(TPB, 8) k_prhs(LevelView lv, const Real *__res
   const int a = t & 7, c2 = t >> 3;
   const Real *rsl = lv.rslab ? rslab_of<Real>(lv) : nullptr;
   // component q (0..5 = u v w udef_x udef_y udef_z), single layer, of the slab received for code nbc
-  auto rem = [&](int nbc, int q) -> Real { return rsl[(size_t)(kRemote0 - nbc) * (64 * kSlabPlanes) + q * 64 + t]; };
+  auto rem = [&](int nbc, int q) -> Real {
+    return __ldcg(rsl + (size_t)(kRemote0 - nbc) * (64 * kSlabPlanes) + q * 64 + t);
+  };
   // the block index and neighbour list of the NEXT iteration are fetched one iteration ahead, so the
   // field loads of a block do not wait behind a dependent index load (ncu r01: 17.6 warps per issue
   // stalled on the long scoreboard, three dependent DRAM round trips per block)
@@ -349,7 +351,7 @@ __global__ void __launch_bounds__(TPB) k_velgrad(LevelView lv, const Real *__res
         // face owned by another rank: component q, single layer, of the received slab
         hl[q][f][t] = nb >= 0 ? vel[q][(size_t)nb * 512 + idx]
                               : (nb == kWall ? ((f >> 1) == q ? -vel[q][own + idx] : vel[q][own + idx])
-                                             : rsl[(size_t)(kRemote0 - nb) * (64 * kSlabPlanes) + q * 64 + t]);
+                                             : __ldcg(rsl + (size_t)(kRemote0 - nb) * (64 * kSlabPlanes) + q * 64 + t));
       }
     }
     __syncthreads();
@@ -526,6 +528,38 @@ int stencil_amr_t(CupCtx *c, CupStencilId id) {
   lv.nsub = c->run_nsub;
   Real **S = (Real **)c->state;
   const double dt = c->prm.dt;
+  if (c->nranks > 1) {
+    // halo_sync (main.c:3632): the input fields of the leaves other ranks own, as ghost blocks behind the
+    // own ones (each state component holds nstate = nblk + ghost blocks)
+    int fl[BLK_COMPS], nf = 0;
+    switch (id) {
+    case CUP_ST_ADVDIFF:
+    case CUP_ST_VORT:
+    case CUP_ST_Q:
+      for (int q = 0; q < 3; q++)
+        fl[nf++] = CUP_F_VEL + q;
+      break;
+    case CUP_ST_PRHS:
+      for (int q = 0; q < 3; q++)
+        fl[nf++] = CUP_F_VEL + q;
+      for (int q = 0; q < 3; q++)
+        fl[nf++] = CUP_F_TMP + q;
+      fl[nf++] = CUP_F_CHI;
+      break;
+    case CUP_ST_DIVP:
+    case CUP_ST_GRADP:
+      fl[nf++] = CUP_F_PRES;
+      break;
+    default:
+      break;
+    }
+    const Real *src[BLK_COMPS];
+    Real *dst[BLK_COMPS];
+    for (int q = 0; q < nf; q++)
+      src[q] = dst[q] = S[fl[q]];
+    if (nf > 0)
+      CUP_TRY(block_exchange_leaf<Real>(c, src, dst, nf, 0));
+  }
   switch (id) {
   case CUP_ST_ADVDIFF: {
     // blocks whose neighbours are all same-level / wall: the uniform kernel with per-block factors;
@@ -661,8 +695,7 @@ int stencil_t(CupCtx *c, CupStencilId id, const int *d_sub, long long nsub) {
   }
   case CUP_ST_PRHS: {
     const double fac = 0.5 * hd * hd / dt;
-    // (its received-face path has not run on two GPUs yet: multi-rank contexts keep the plain loads)
-    if (prhs_tma() && c->nranks == 1 && !listed)
+    if (prhs_tma() && !listed)
       return prhs_tma_launch<Real>(c, lv, fac);
     static bool carve = false;  // 8 CTAs x 21.5 KB need the large shared-memory configuration
     if (!carve) {

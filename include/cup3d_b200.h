@@ -236,13 +236,26 @@ typedef struct CupPlan {
   int *res_send_cnt, *res_recv_cnt; /* [nranks] children sent to / received from each peer */
   int nres_recv;
   int *res_recv_slot, *res_recv_oct; /* [nres_recv] local parent slot + octant of received children */
+  /* ghost BLOCKS (levels with coarse-fine interfaces, and the leaf context = level -1, on several ranks):
+   * blocks of other ranks get local slots >= the rank's own slots; nbr / ext refer to them like to local
+   * blocks.  kind 0: a block of the swept vector, 1: a coarser leaf read from the canonical vector. */
+  int ghosted, nghost;
+  int *ext;                          /* [nact][6][4] coarse-fine faces: {coarse slot, quadrant} / four finer slots */
+  int nbsend, nbrecv;
+  int *bsend_slot, *bsend_kind, *bsend_peer, *bsend_idx; /* [nbsend] own slot, kind, destination rank, its entry */
+  int *brecv_slot, *brecv_kind;      /* [nbrecv] (entry order) local ghost slot, kind */
 } CupPlan;
+/* level = -1: the LEAF context (all local leaves of a multi-level mesh; act = local leaf slots) */
 int cup_plan_build(const CupBlk *gblk, long long nglobal, const int *owner, int nranks, int rank, const int bpd[3],
                    int level_max, int level, CupPlan *out);
 void cup_plan_free(CupPlan *p);
 
 /* instrumentation: number of kernels launched by this context so far */
 long long cup_kernel_launches(const CupCtx *ctx);
+/* with CUP_STAMP=1 in the environment every phase of a V-cycle is followed by a one-thread kernel
+ * that stores the device's %globaltimer (captured into the replayed CUDA graph like any node):
+ * writes "phase nanoseconds" lines of the last cycle into out, returns the bytes written */
+int cup_trace_report(CupCtx *ctx, char *out, size_t cap);
 /* timing of an internal kernel class with CUDA events on the ctx stream:
  * runs `reps` launches of the level-`level` smoother; returns ms per launch */
 int cup_time_smooth(CupCtx *ctx, int level, int reps, float *ms_per_launch);

@@ -187,3 +187,76 @@ def test_two_rank_time_step_pieces(built, name, kind):
     assert relerr(full["advdiff"][:, 2:5], c.g["advdiff"][:, 0:3]) < 1e-12
     assert relerr(full["proj"][:, 1], c.g["proj_step5"][:, 0]) < 1e-7
     assert relerr(full["proj"][:, 2:5], c.g["proj_step5"][:, 1:4]) < 1e-9
+
+
+def worker_amr(rank, world, boot, name, q):
+    """everything test_gpu_amr.py checks on one rank, on a multi-level mesh split over `world` ranks"""
+    os.environ["CUP_COARSE_BLOCKS"] = "0"
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from cup3d_b200 import capi
+    from util import case
+    c = case(name)
+    owner = capi.split_owner(c.n, world)
+    mine = np.nonzero(owner == rank)[0]
+    ctx = connect(rank, world, boot)
+    ctx.mesh_upload(c.ib[mine], c.rb[mine], c.bpd, c.level_max)
+    ctx.set_params(dt=c.dt, nu=c.nu, uinf=c.uinf, step=5, mean_constraint=2, ptol=1e-10, ptol_rel=1e-12)
+    out = {}
+    out["vc"] = ctx.mg_vcycle(np.ascontiguousarray(c.F["cosrhs"][mine]))
+    out["vc2"] = ctx.mg_vcycle(np.ascontiguousarray(c.F["cosrhs"][mine]))  # CUDA-graph replay
+    out["op"] = ctx.pois_op(np.ascontiguousarray(c.F["pres"][mine]))
+    s0 = np.ascontiguousarray(c.state0()[mine])
+    if name == "amr2":
+        for st, sid in (("lhs", capi.ST_LHS), ("advdiff", capi.ST_ADVDIFF), ("prhs", capi.ST_PRHS),
+                        ("divp", capi.ST_DIVP), ("gradp", capi.ST_GRADP), ("vort", capi.ST_VORT), ("q", capi.ST_Q)):
+            ctx.state_h2d(s0)
+            ctx.stencil_apply(sid)
+            r = np.zeros_like(s0)
+            ctx.state_d2h(r)
+            out["st_" + st] = r
+        ctx.state_h2d(s0)
+        ctx.advdiff()
+        r = np.zeros_like(s0)
+        ctx.state_d2h(r)
+        out["advdiff"] = r
+        ctx.state_h2d(s0)
+        info = ctx.projection()
+        r = np.zeros_like(s0)
+        ctx.state_d2h(r)
+        out["proj"] = r
+        out["proj_res"] = (info.residual, info.rhs_norm)
+    q.put((rank, mine, out))
+    disconnect(ctx, boot)
+
+
+@pytest.mark.parametrize("kind", ["host", "nccl"])
+@pytest.mark.parametrize("name,world", [("amr2", 2), ("amr2", 3), ("amr3", 2), ("amr3", 4)])
+def test_multi_level_mesh_across_ranks(built, name, world, kind):
+    """coarse-fine interfaces ACROSS ranks (halo_sync of whole blocks main.c:3101-3112, fc_fill :3228-3293,
+    remote parents on AMR levels :4734-4807): same goldens and tolerances as the single-rank AMR tests"""
+    if kind not in boots():
+        pytest.skip("the NCCL bootstrap needs one GPU per rank")
+    import torch
+    if kind == "nccl" and torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    c = case(name)
+    got = run_ranks(worker_amr, world, (make_boot(kind), name))
+    full = {}
+    for rank, mine, out in got:
+        for k, v in out.items():
+            if k == "proj_res":
+                assert v[0] < max(1e-10, 1e-12 * v[1])
+                continue
+            full.setdefault(k, np.zeros((c.n,) + v.shape[1:]))[mine] = v
+    assert relerr(full["vc"], c.g["vc_out_cosrhs"]) < 1e-11
+    assert relerr(full["vc2"], c.g["vc_out_cosrhs"]) < 1e-11
+    assert relerr(full["op"], c.g["op_out_mc2"]) < 1e-12
+    if name != "amr2":
+        return
+    for st, f0, nc in (("lhs", 8, 1), ("advdiff", 5, 3), ("prhs", 8, 1), ("divp", 5, 1), ("gradp", 5, 3),
+                       ("vort", 5, 3), ("q", 8, 1)):
+        assert relerr(full["st_" + st][:, f0:f0 + nc], c.g["st_" + st]) < 1e-12, st
+    assert relerr(full["advdiff"][:, 2:5], c.g["advdiff"][:, 0:3]) < 1e-12
+    assert relerr(full["proj"][:, 1], c.g["proj_step5"][:, 0]) < 1e-7
+    assert relerr(full["proj"][:, 2:5], c.g["proj_step5"][:, 1:4]) < 1e-9

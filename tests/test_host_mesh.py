@@ -111,11 +111,19 @@ def test_malformed_meshes_are_rejected(built):
     _expect_error(lambda: capi.plan_build(c.ib, c.rb, own, 1, 0, c.bpd, c.level_max, 99), "level")
 
 
-def test_multi_level_meshes_are_single_rank_for_now(built):
-    """the documented restriction is reported, not silently mis-handled"""
+def test_multi_level_meshes_split_over_ranks(built):
+    """multi-level meshes across ranks: levels with interfaces use ghost blocks, uniform levels 8x8 faces
+    (the plans themselves are checked in tests/test_ghost_plans.py)"""
     c = case("amr2")
     own = capi.split_owner(c.n, 2)
-    _expect_error(lambda: capi.plan_build(c.ib, c.rb, own, 2, 0, c.bpd, c.level_max, 0), "single-rank")
+    finest = int(c.ib[:, 0].max())
+    for r in range(2):
+        leafp = capi.plan_build(c.ib, c.rb, own, 2, r, c.bpd, c.level_max, -1)
+        assert leafp["ghosted"] and leafp["nghost"] > 0 and leafp["nact"] == int((own == r).sum())
+        top = capi.plan_build(c.ib, c.rb, own, 2, r, c.bpd, c.level_max, finest)
+        assert top["ghosted"] and top["nsend"] == 0 and top["nrecv"] == 0
+        base = capi.plan_build(c.ib, c.rb, own, 2, r, c.bpd, c.level_max, 0)
+        assert not base["ghosted"] and base["nghost"] == 0
 
 
 def test_broken_two_to_one_balance(built):
