@@ -64,6 +64,10 @@ struct AdvArgs {
   int nsub;
   const Real *hblk;
   Real dtnu_dt, dtnu_nu, fac_a0, fac_d0, uinf[3];
+  // fused Runge-Kutta stage (advdiff(), main.c:5039-5054): with T = TMP + rhs the kernel stores
+  // vout = u + T * rk_ih3 and TMP = T * rk_beta instead of TMP = T (vout != vel: neighbours still read u)
+  Real *vout[3];
+  Real rk_ih3, rk_beta;
 };
 
 // producer: ghost layers of component c of the block with neighbours nb[] -> ghost slot h
@@ -91,7 +95,11 @@ __device__ __forceinline__ void issue_halo(Real *h, uint64_t *bar, const Real *v
 
 // NS = 2: ghost arrays double buffered (32 KB per CTA in fp64, 6 CTAs per SM); NS = 1: single
 // buffered (22 KB, 8 CTAs per SM), the next item's ghosts are requested when the current item is done
-template <typename Real, int NS, int MINB>
+// The component loop is ROLLED (one copy of the 8-cell body instead of three: 64 KB of SASS thrashed
+// the instruction cache with only three warps per scheduler -- ncu r01: 1.4 warps per issue stalled on
+// instruction fetch).  What depends on the component is selected at run time: the line of u_c comes
+// from the shared core, the summation order of main.c:5016-5017 from three selects.
+template <typename Real, int NS, int MINB, bool RK>
 __global__ void __launch_bounds__(TPB, MINB) k_advdiff_tma(LevelView lv, AdvArgs<Real> A,
                                                            const __grid_constant__ AdvMaps M) {
   __shared__ __align__(128) Real core[3][CORE];
@@ -155,16 +163,20 @@ __global__ void __launch_bounds__(TPB, MINB) k_advdiff_tma(LevelView lv, AdvArgs
 #pragma unroll
     for (int f = 0; f < 6; f++)
       odd |= nbc[f] < 0;
-    // U of all three components, once per block
-    Real vv[3][8];
+    // U of all three components: once per block into registers when the double-buffered variant is
+    // shared-memory limited anyway (NS == 2); read cell by cell from the resident cores in the
+    // single-buffered variant, whose eight CTAs per SM leave 128 registers per thread
+    Real vv[3][NS == 2 ? 8 : 1];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
       mbar_wait(&bar_core[c], j & 1);
+      if (NS == 2) {
 #pragma unroll
-      for (int k = 0; k < 8; k++)
-        vv[c][k] = core[c][k * 64 + t];
+        for (int k = 0; k < 8; k++)
+          vv[c][NS == 2 ? k : 0] = core[c][k * 64 + t];
+      }
     }
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < 3; c++, item++) {
       const int s = NS == 2 ? (item & 1) : 0;
       Real *H = halo[s];
@@ -239,9 +251,9 @@ __global__ void __launch_bounds__(TPB, MINB) k_advdiff_tma(LevelView lv, AdvArgs
       }
 #pragma unroll
       for (int k = 0; k < 8; k++)
-        line[3 + k] = vv[c][k];
-      const int a1 = (c + 1) % 3, a2 = (c + 2) % 3;
+        line[3 + k] = C[k * 64 + t];  // == vv[c][k]; from shared so that c can stay a run-time value
       Real *oc = A.tmp[c];
+      Real *vo = RK ? A.vout[c] : nullptr;
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         const Real u = line[3 + k];
@@ -252,20 +264,37 @@ __global__ void __launch_bounds__(TPB, MINB) k_advdiff_tma(LevelView lv, AdvArgs
           yv[m] = C[oy[m] + k * syk[m]];
         }
         Real dd[3], pr[3];
-        const Real U0 = vv[0][k] + A.uinf[0], U1 = vv[1][k] + A.uinf[1], U2 = vv[2][k] + A.uinf[2];
+        const Real U0 = (NS == 2 ? vv[0][NS == 2 ? k : 0] : core[0][k * 64 + t]) + A.uinf[0],
+                   U1 = (NS == 2 ? vv[1][NS == 2 ? k : 0] : core[1][k * 64 + t]) + A.uinf[1],
+                   U2 = (NS == 2 ? vv[2][NS == 2 ? k : 0] : core[2][k * 64 + t]) + A.uinf[2];
         dd[0] = upwind<Real>(U0, xv[0], xv[1], xv[2], u, xv[3], xv[4], xv[5]);
         pr[0] = xv[3] + xv[2];
         dd[1] = upwind<Real>(U1, yv[0], yv[1], yv[2], u, yv[3], yv[4], yv[5]);
         pr[1] = yv[3] + yv[2];
         dd[2] = upwind<Real>(U2, line[k], line[k + 1], line[k + 2], u, line[k + 4], line[k + 5], line[k + 6]);
         pr[2] = line[k + 4] + line[k + 2];
-        const Real Uabs[3] = {U0, U1, U2};
-        const Real adv = Uabs[c] * dd[c] + (Uabs[a1] * dd[a1] + Uabs[a2] * dd[a2]);
-        const Real lap = (pr[c] + (pr[a1] + pr[a2])) - (Real)6 * u;
+        // adv = U_c d_c + (U_a1 d_a1 + U_a2 d_a2), a1 = (c+1)%3, a2 = (c+2)%3 (main.c:5016): same order, by selects
+        const Real p0 = U0 * dd[0], p1 = U1 * dd[1], p2 = U2 * dd[2];
+        const Real pc = c == 0 ? p0 : (c == 1 ? p1 : p2);
+        const Real pa = c == 0 ? p1 : (c == 1 ? p2 : p0);
+        const Real pb = c == 0 ? p2 : (c == 1 ? p0 : p1);
+        const Real adv = pc + (pa + pb);
+        const Real qc = c == 0 ? pr[0] : (c == 1 ? pr[1] : pr[2]);
+        const Real qa = c == 0 ? pr[1] : (c == 1 ? pr[2] : pr[0]);
+        const Real qb = c == 0 ? pr[2] : (c == 1 ? pr[0] : pr[1]);
+        const Real lap = (qc + (qa + qb)) - (Real)6 * u;
+        Real T;
         if (NS == 2)
-          oc[own + k * 64 + t] = acc[k] + (fac_a * adv + fac_d * lap);
+          T = acc[k] + (fac_a * adv + fac_d * lap);
         else
-          oc[own + k * 64 + t] += fac_a * adv + fac_d * lap;
+          T = oc[own + k * 64 + t] + (fac_a * adv + fac_d * lap);
+        if (RK) {
+          // the Runge-Kutta stage update of this cell (main.c:5047-5052): V += T ih3 ; TMP = T beta
+          vo[own + k * 64 + t] = u + T * A.rk_ih3;
+          oc[own + k * 64 + t] = T * A.rk_beta;
+        } else {
+          oc[own + k * 64 + t] = T;
+        }
       }
       __syncthreads();  // core c and ghost slot s are free
       if (t == 0) {
@@ -306,7 +335,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_advdiff_tma(LevelView lv, AdvArgs
 
 template <typename Real>
 int advdiff_tma_launch(CupCtx *c, LevelView lv, const int *d_sub, int nsub, const void *d_hblk, double dtnu_dt,
-                       double dtnu_nu, double fac_a, double fac_d) {
+                       double dtnu_nu, double fac_a, double fac_d, const AdvRk *rk) {
   if (nsub <= 0)
     return CUP_OK;
   AdvMaps M;
@@ -327,25 +356,34 @@ int advdiff_tma_launch(CupCtx *c, LevelView lv, const int *d_sub, int nsub, cons
   A.dtnu_nu = (Real)dtnu_nu;
   A.fac_a0 = (Real)fac_a;
   A.fac_d0 = (Real)fac_d;
+  for (int q = 0; q < 3; q++)
+    A.vout[q] = rk ? (Real *)rk->vout[q] : nullptr;
+  A.rk_ih3 = rk ? (Real)rk->ih3 : (Real)0;
+  A.rk_beta = rk ? (Real)rk->beta : (Real)0;
   static int ns = getenv("CUP_ADV_SLOTS") ? atoi(getenv("CUP_ADV_SLOTS")) : 2;
   static int per_sm = getenv("CUP_ADV_PER_SM") ? atoi(getenv("CUP_ADV_PER_SM")) : (ns == 2 ? 6 : 8);
   long long g = (long long)c->num_sms * per_sm;
   if (g > nsub)
     g = nsub;
-  if (ns == 2)
-    k_advdiff_tma<Real, 2, 6><<<(int)g, TPB, 0, c->stream>>>(lv, A, M);
+  if (rk) {
+    if (ns == 2)
+      k_advdiff_tma<Real, 2, 6, true><<<(int)g, TPB, 0, c->stream>>>(lv, A, M);
+    else
+      k_advdiff_tma<Real, 1, 8, true><<<(int)g, TPB, 0, c->stream>>>(lv, A, M);
+  } else if (ns == 2)
+    k_advdiff_tma<Real, 2, 6, false><<<(int)g, TPB, 0, c->stream>>>(lv, A, M);
   else if (per_sm <= 7)
-    k_advdiff_tma<Real, 1, 7><<<(int)g, TPB, 0, c->stream>>>(lv, A, M);
+    k_advdiff_tma<Real, 1, 7, false><<<(int)g, TPB, 0, c->stream>>>(lv, A, M);
   else
-    k_advdiff_tma<Real, 1, 8><<<(int)g, TPB, 0, c->stream>>>(lv, A, M);
+    k_advdiff_tma<Real, 1, 8, false><<<(int)g, TPB, 0, c->stream>>>(lv, A, M);
   c->launches++;
   CUP_CUDA(cudaGetLastError());
   return CUP_OK;
 }
 
 template int advdiff_tma_launch<double>(CupCtx *, LevelView, const int *, int, const void *, double, double, double,
-                                        double);
+                                        double, const AdvRk *);
 template int advdiff_tma_launch<float>(CupCtx *, LevelView, const int *, int, const void *, double, double, double,
-                                       double);
+                                       double, const AdvRk *);
 
 }  // namespace cup

@@ -65,6 +65,85 @@ __global__ void __launch_bounds__(256) k_bminus(Real *__restrict__ r, const Real
     r[i] = b[i] - r[i];
 }
 
+// ---- fused Krylov kernels (pois_solve, main.c:4875-4979).  The modified Gram-Schmidt loop
+//   for k <= j:  h_k = <w, V_k> ;  w -= h_k V_k            (:4930-4937)
+// is sequential in k, but the axpy of step k and the dot of step k+1 touch the same w: one kernel does
+// w -= h_k V_k and accumulates <w_new, V_{k+1}> (the last one <w_new, w_new>, :4938), i.e. four vector
+// passes per k instead of five and one launch instead of two.  Arithmetic per element and per block is
+// that of k_axpy / k_wdot.
+template <typename Real>
+__global__ void __launch_bounds__(256) k_axpy_dot(Real *__restrict__ w, const Real *__restrict__ vk,
+                                                  const Real *vnext, const Real *__restrict__ h3, long long nblk,
+                                                  const double *__restrict__ alpha, double *out) {
+  __shared__ double red[8];
+  const Real al = (Real)(-1.0 * (*alpha));
+  double s = 0;
+  for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const long long i0 = blk * 512 + threadIdx.x, i1 = i0 + 256;
+    Real w0 = w[i0], w1 = w[i1];
+    w0 += al * vk[i0];
+    w1 += al * vk[i1];
+    w[i0] = w0;
+    w[i1] = w1;
+    const Real n0 = vnext ? vnext[i0] : w0, n1 = vnext ? vnext[i1] : w1;
+    const double sb = (double)w0 * (double)n0 + (double)w1 * (double)n1;
+    s += sb / (double)h3[blk];
+  }
+  for (int o = 16; o > 0; o >>= 1)
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0)
+    red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0;
+    for (int i = 0; i < 8; i++)
+      tot += red[i];
+    atomicAdd(out, tot);
+  }
+}
+
+// r = b - r and <r, r> in one pass (pois_solve's residual, :4915-4917 / :4974-4976)
+template <typename Real>
+__global__ void __launch_bounds__(256) k_bminus_dot(Real *__restrict__ r, const Real *__restrict__ b,
+                                                    const Real *__restrict__ h3, long long nblk, double *out) {
+  __shared__ double red[8];
+  double s = 0;
+  for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const long long i0 = blk * 512 + threadIdx.x, i1 = i0 + 256;
+    const Real r0 = b[i0] - r[i0], r1 = b[i1] - r[i1];
+    r[i0] = r0;
+    r[i1] = r1;
+    const double sb = (double)r0 * (double)r0 + (double)r1 * (double)r1;
+    s += sb / (double)h3[blk];
+  }
+  for (int o = 16; o > 0; o >>= 1)
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0)
+    red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0;
+    for (int i = 0; i < 8; i++)
+      tot += red[i];
+    atomicAdd(out, tot);
+  }
+}
+
+// w = sum_k y_k V_k (k < m), accumulated in the order of the reference's axpy loop (:4968-4970)
+struct MultiY {
+  double y[32];
+};
+template <typename Real>
+__global__ void __launch_bounds__(256) k_multi_axpy(Real *__restrict__ w, const Real *__restrict__ V, long long n,
+                                                    int m, MultiY Y) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    Real acc = 0;
+    for (int k = 0; k < m; k++)
+      acc += (Real)Y.y[k] * V[(size_t)k * n + i];
+    w[i] = acc;
+  }
+}
+
 static inline int sgrid(const CupCtx *c, long long n) {
   long long g = (n + 255) / 256;
   long long cap = (long long)c->num_sms * 8;
@@ -84,6 +163,51 @@ int wdot(CupCtx *c, const void *a, const void *b, int idx) {
   c->launches++;
   CUP_CUDA(cudaGetLastError());
   return comm_allreduce(c, idx, 1);  // MPI_Allreduce of pois_dot, main.c:4860
+}
+
+static inline int bgrid8(const CupCtx *c) {
+  const long long g = c->nblk < (long long)c->num_sms * 8 ? c->nblk : (long long)c->num_sms * 8;
+  return (int)(g < 1 ? 1 : g);
+}
+
+int axpy_dot(CupCtx *c, void *w, const void *vk, const void *vnext, int alpha_idx, int out_idx) {
+  if (c->real_bytes == 8)
+    k_axpy_dot<double><<<bgrid8(c), 256, 0, c->stream>>>((double *)w, (const double *)vk, (const double *)vnext,
+                                                         (const double *)c->d_hw, c->nblk, c->d_scal + alpha_idx,
+                                                         c->d_scal + out_idx);
+  else
+    k_axpy_dot<float><<<bgrid8(c), 256, 0, c->stream>>>((float *)w, (const float *)vk, (const float *)vnext,
+                                                        (const float *)c->d_hw, c->nblk, c->d_scal + alpha_idx,
+                                                        c->d_scal + out_idx);
+  c->launches++;
+  CUP_CUDA(cudaGetLastError());
+  return comm_allreduce(c, out_idx, 1);
+}
+
+int bminus_dot(CupCtx *c, void *r, const void *b, int out_idx) {
+  CUP_CUDA(cudaMemsetAsync(c->d_scal + out_idx, 0, sizeof(double), c->stream));
+  if (c->real_bytes == 8)
+    k_bminus_dot<double><<<bgrid8(c), 256, 0, c->stream>>>((double *)r, (const double *)b, (const double *)c->d_hw,
+                                                           c->nblk, c->d_scal + out_idx);
+  else
+    k_bminus_dot<float><<<bgrid8(c), 256, 0, c->stream>>>((float *)r, (const float *)b, (const float *)c->d_hw,
+                                                          c->nblk, c->d_scal + out_idx);
+  c->launches++;
+  CUP_CUDA(cudaGetLastError());
+  return comm_allreduce(c, out_idx, 1);
+}
+
+int multi_axpy(CupCtx *c, void *w, const void *V, long long n, int m, const double *y) {
+  MultiY Y;
+  for (int k = 0; k < 32; k++)
+    Y.y[k] = k < m ? y[k] : 0.0;
+  if (c->real_bytes == 8)
+    k_multi_axpy<double><<<sgrid(c, n), 256, 0, c->stream>>>((double *)w, (const double *)V, n, m, Y);
+  else
+    k_multi_axpy<float><<<sgrid(c, n), 256, 0, c->stream>>>((float *)w, (const float *)V, n, m, Y);
+  c->launches++;
+  CUP_CUDA(cudaGetLastError());
+  return CUP_OK;
 }
 
 // sta_umax (main.c:5918-5939): max over cells of max(|u+uinf_x|, |v+uinf_y|, |w+uinf_z|).  The

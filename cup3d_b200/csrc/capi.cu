@@ -35,6 +35,10 @@ static int alloc_state(CupCtx *c) {
   const size_t bytes = (size_t)c->nstate * 512 * (size_t)c->real_bytes;
   cudaFree(c->leaf_ghost);
   c->leaf_ghost = nullptr;
+  for (int q = 0; q < 3; q++) {
+    cudaFree(c->vel_spare[q]);
+    c->vel_spare[q] = nullptr;
+  }
   if (c->leafv.nghost > 0) {
     const size_t rows = (size_t)std::max<long long>(c->leafv.nghost, c->nslot - c->nblk + 1);
     CUP_CUDA(cudaMalloc(&c->leaf_ghost, rows * 512 * (size_t)c->real_bytes));
@@ -187,6 +191,8 @@ int cup_destroy(CupCtx *c) {
   cudaFree(c->tmp_stage);
   cudaFree(c->io_buf);
   cudaFree(c->leaf_ghost);
+  for (int q = 0; q < 3; q++)
+    cudaFree(c->vel_spare[q]);
   cudaFree(c->d_W);
   cudaFree(c->d_hw);
   cudaFree(c->d_scal);

@@ -187,6 +187,8 @@ struct CupCtx {
   cup::Krylov *kr = nullptr;
   long long launches = 0;
   void *p_old = nullptr;        // projection(): previous pressure
+  void *vel_spare[3] = {nullptr, nullptr, nullptr};  // advdiff(): second velocity buffer of the fused RK stages
+  const void *adv_rk = nullptr;  // cup::AdvRk of the stage being swept (advdiff_t -> stencil_t), else null
   void *graph_cache = nullptr;  // captured V-cycles keyed by (in, out) (mg_kernels.cu)
   void *tma_cache = nullptr;    // tensor-map cache (smooth_tma.cu)
   bool no_flux_correction = false;  // st_mg on the leaves (stencil_apply(CUP_ST_MG)): k_mg has no flux faces

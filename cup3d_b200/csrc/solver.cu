@@ -18,14 +18,13 @@ enum { KR_M = 30, KR_MAXIT = 1000 };  // main.c:4400
 
 struct Krylov {
   long long cap = 0;
-  void *x = nullptr, *b = nullptr, *r = nullptr, *w = nullptr, *z = nullptr, *V = nullptr;
+  // x and b are the state's F_PRES / F_LHS themselves (the reference solves in place, :4900-4905)
+  void *r = nullptr, *w = nullptr, *z = nullptr, *V = nullptr;
 };
 
 void free_krylov(CupCtx *c) {
   if (!c->kr)
     return;
-  cudaFree(c->kr->x);
-  cudaFree(c->kr->b);
   cudaFree(c->kr->r);
   cudaFree(c->kr->w);
   cudaFree(c->kr->z);
@@ -40,8 +39,6 @@ static int kr_alloc(CupCtx *c, long long N) {
   free_krylov(c);
   c->kr = new Krylov;
   const size_t rb = (size_t)c->real_bytes;
-  CUP_CUDA(cudaMalloc(&c->kr->x, N * rb));
-  CUP_CUDA(cudaMalloc(&c->kr->b, N * rb));
   CUP_CUDA(cudaMalloc(&c->kr->r, N * rb));
   CUP_CUDA(cudaMalloc(&c->kr->w, N * rb));
   CUP_CUDA(cudaMalloc(&c->kr->z, N * rb));
@@ -70,23 +67,18 @@ int pois_solve(CupCtx *c, CupSolveInfo *info) {
   const double vol = c->gvol;          // sum over ALL ranks (MPI_Allreduce, main.c:4891)
   const long long pin = c->pin_local;  // block (0,0,0) on its owner, else -1
   auto Vj = [&](int j) { return (void *)((char *)K.V + (size_t)j * N * rb); };
-  // b = F_LHS (with the pinned cell zeroed for constraint 1 / >2), x = F_PRES
-  CUP_CUDA(cudaMemcpyAsync(K.b, c->state[CUP_F_LHS], N * rb, cudaMemcpyDeviceToDevice, c->stream));
-  CUP_CUDA(cudaMemcpyAsync(K.x, c->state[CUP_F_PRES], N * rb, cudaMemcpyDeviceToDevice, c->stream));
+  // b = F_LHS (with the pinned cell zeroed for constraint 1 / >2), x = F_PRES: used in place
+  void *const Kb = c->state[CUP_F_LHS], *const Kx = c->state[CUP_F_PRES];
   if ((mc == 1 || mc > 2) && pin >= 0) {
-    if (c->real_bytes == 8) {
-      k_setcell<double><<<1, 1, 0, c->stream>>>((double *)c->state[CUP_F_LHS], pin * 512, 0.0);
-      k_setcell<double><<<1, 1, 0, c->stream>>>((double *)K.b, pin * 512, 0.0);
-    } else {
-      k_setcell<float><<<1, 1, 0, c->stream>>>((float *)c->state[CUP_F_LHS], pin * 512, 0.f);
-      k_setcell<float><<<1, 1, 0, c->stream>>>((float *)K.b, pin * 512, 0.f);
-    }
-    c->launches += 2;
+    if (c->real_bytes == 8)
+      k_setcell<double><<<1, 1, 0, c->stream>>>((double *)Kb, pin * 512, 0.0);
+    else
+      k_setcell<float><<<1, 1, 0, c->stream>>>((float *)Kb, pin * 512, 0.f);
+    c->launches++;
   }
-  CUP_TRY(wdot(c, K.b, K.b, 2));
-  CUP_TRY(pois_op_dev(c, K.x, K.r));
-  CUP_TRY(bminus(c, K.r, K.b, N));
-  CUP_TRY(wdot(c, K.r, K.r, 3));
+  CUP_TRY(wdot(c, Kb, Kb, 2));
+  CUP_TRY(pois_op_dev(c, Kx, K.r));
+  CUP_TRY(bminus_dot(c, K.r, Kb, 3));  // r = b - A x and <r, r> in one pass
   CUP_TRY(fetch_scalars(c, 2, 2));
   const double bnorm = std::sqrt(c->h_scal[2] / vol);
   double beta = std::sqrt(c->h_scal[3]);
@@ -108,12 +100,12 @@ int pois_solve(CupCtx *c, CupSolveInfo *info) {
       CUP_TRY(mg_vcycle_dev(c, Vj(j), K.z));
       vcycles++;
       CUP_TRY(pois_op_dev(c, K.z, K.w));
-      // modified Gram-Schmidt: H[k][j] stays on the device (scalar 8+k)
-      for (int k = 0; k <= j; k++) {
-        CUP_TRY(wdot(c, K.w, Vj(k), 8 + k));
-        CUP_TRY(axpy(c, K.w, Vj(k), N, 0.0, 8 + k, -1.0));
-      }
-      CUP_TRY(wdot(c, K.w, K.w, 8 + j + 1));
+      // modified Gram-Schmidt: H[k][j] stays on the device (scalar 8+k).  The axpy of step k and the dot
+      // of step k+1 run in one kernel (the last one accumulates <w, w>): same sequential semantics
+      CUP_CUDA(cudaMemsetAsync(c->d_scal + 8, 0, (size_t)(j + 2) * sizeof(double), c->stream));
+      CUP_TRY(wdot(c, K.w, Vj(0), 8));
+      for (int k = 0; k <= j; k++)
+        CUP_TRY(axpy_dot(c, K.w, Vj(k), k < j ? Vj(k + 1) : nullptr, 8 + k, 8 + k + 1));
       CUP_TRY(fetch_scalars(c, 8, j + 2));
       for (int k = 0; k <= j; k++)
         H[k][j] = c->h_scal[8 + k];
@@ -151,21 +143,17 @@ int pois_solve(CupCtx *c, CupSolveInfo *info) {
       y[k] = H[k][k] != 0 ? y[k] / H[k][k] : 0;
     }
     // x += M(sum_k y_k V_k): one more V-cycle on the combination (main.c:4968-4972)
-    CUP_CUDA(cudaMemsetAsync(K.w, 0, N * rb, c->stream));
-    for (int k = 0; k < j; k++)
-      CUP_TRY(axpy(c, K.w, Vj(k), N, y[k], -1, 1.0));
+    CUP_TRY(multi_axpy(c, K.w, K.V, N, j, y));  // w = sum_k y_k V_k in one pass over the basis
     CUP_TRY(mg_vcycle_dev(c, K.w, K.z));
     vcycles++;
-    CUP_TRY(axpy(c, K.x, K.z, N, 1.0, -1, 1.0));
-    CUP_TRY(pois_op_dev(c, K.x, K.r));
-    CUP_TRY(bminus(c, K.r, K.b, N));
-    CUP_TRY(wdot(c, K.r, K.r, 3));
+    CUP_TRY(axpy(c, Kx, K.z, N, 1.0, -1, 1.0));
+    CUP_TRY(pois_op_dev(c, Kx, K.r));
+    CUP_TRY(bminus_dot(c, K.r, Kb, 3));
     CUP_TRY(fetch_scalars(c, 3, 1));
     beta = std::sqrt(c->h_scal[3]);
     norm = beta / std::sqrt(vol);
     restarts++;
   }
-  CUP_CUDA(cudaMemcpyAsync(c->state[CUP_F_PRES], K.x, N * rb, cudaMemcpyDeviceToDevice, c->stream));
   CUP_CUDA(cudaStreamSynchronize(c->stream));
   if (info) {
     info->iterations = it;

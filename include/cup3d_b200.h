@@ -120,7 +120,8 @@ long long cup_mg_nact(const CupCtx *ctx, int level);
  * f0/nc select a field range (e.g. CUP_F_VEL,3). */
 int cup_state_h2d(CupCtx *ctx, const double *h_fld, int f0, int nc);
 int cup_state_d2h(CupCtx *ctx, double *h_fld, int f0, int nc);
-/* device pointer of one state component: flat [nblk][512] Reals */
+/* device pointer of one state component: flat [nblk][512] Reals.  Ask again after cup_advdiff: on uniform
+ * meshes its fused Runge-Kutta stages ping-pong F_VEL between two buffers and the pointers swap. */
 void *cup_state_dev(CupCtx *ctx, int f);
 
 /* the per-block compute loop.  cup_stencil_run is stencil_run(st, list, n) (main.c:3631-3647):

@@ -28,7 +28,8 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--level", type=int, required=True)
+    ap.add_argument("--level", type=int, default=-1, help="uniform grid (8 << level)^3, bpd 1")
+    ap.add_argument("--case", default="", help="a mesh of tests/golden/make_golden.py (CASES; adapted ones included)")
     ap.add_argument("--dir", required=True)
     ap.add_argument("--ops", default="vcycle")
     ap.add_argument("--real", type=int, default=8)
@@ -37,18 +38,26 @@ def main():
     ap.add_argument("--nu", type=float, default=1e-3)
     ap.add_argument("--uinf", default="0.1,-0.05,0.02")
     ap.add_argument("--ptol", type=float, default=1e-9)
+    ap.add_argument("--ptol-rel", type=float, default=1e-14)
     a = ap.parse_args()
     if a.threads > 0:
         os.environ["OMP_NUM_THREADS"] = str(a.threads)
     from oracle import refbind as R
     t0 = time.time()
-    R.init(real_bytes=a.real, levelStart=a.level, levelMax=a.level + 1)
+    if a.case:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        import make_golden as MG
+        R.init(real_bytes=a.real, **MG.CASES[a.case])
+        MG.adapt_like_golden(R, a.case)  # the reference's own mesh_adapt passes of the adapted cases
+    else:
+        R.init(real_bytes=a.real, levelStart=a.level, levelMax=a.level + 1)
     meta = {"mesh_init_s": time.time() - t0, "nblk": R.nblk(), "threads": R.threads(), "real_bytes": a.real}
     ib, rb = R.blocks()
     np.save(os.path.join(a.dir, "ib.npy"), ib)
+    np.save(os.path.join(a.dir, "rb.npy"), rb)
     ops = [o for o in a.ops.split(",") if o]
     uinf = tuple(float(v) for v in a.uinf.split(","))
-    R.set_scalars(dt=a.dt, nu=a.nu, uinf=uinf, step=5, mean_constraint=2, ptol=a.ptol, ptol_rel=1e-14)
+    R.set_scalars(dt=a.dt, nu=a.nu, uinf=uinf, step=5, mean_constraint=2, ptol=a.ptol, ptol_rel=a.ptol_rel)
     if "vcycle" in ops or "op" in ops:
         x = np.load(os.path.join(a.dir, "in_vec.npy"))
         if "vcycle" in ops:

@@ -80,10 +80,8 @@ def solve_rhs(F, rb):
     return rhs - rhs.sum() / rhs.size
 
 
-def worker(case):
-    from oracle import refbind as R
-    R.init(**CASES[case])
-    tier = TIER[case]
+def adapt_like_golden(R, case):
+    """the reference's own mesh_adapt passes that produce the multi-level meshes of the adapted cases"""
     for _ in range(ADAPT.get(case, 0)):
         # refine where 0 < chi < 0.9 (blob surface); velocity zero so vorticity does not tag
         ib, rb = R.blocks()
@@ -94,6 +92,13 @@ def worker(case):
         st[:, 0] = (1.0 / (1.0 + np.exp((r - 0.07) / 0.006))).reshape(-1, 512)
         R.state_set(st)
         R.mesh_adapt(5.0, -1.0)
+
+
+def worker(case):
+    from oracle import refbind as R
+    R.init(**CASES[case])
+    tier = TIER[case]
+    adapt_like_golden(R, case)
     ib, rb = R.blocks()
     n = R.nblk()
     F = fields(ib, rb, seed=1234)

@@ -41,8 +41,7 @@ def free_ram_gb():
 def run_ref(level, d, ops, real=8, timeout=1500):
     cmd = [sys.executable, os.path.join(ROOT, "oracle", "live_ref.py"), "--level", str(level), "--dir", d, "--ops", ops,
            "--real", str(real)]
-    env = dict(os.environ)
-    env.pop("OMP_NUM_THREADS", None)
+    env = dict(os.environ)  # OMP_NUM_THREADS: conftest.py's bounded default (the reference does not scale past ~24)
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout, env=env)
     assert r.returncode == 0, r.stdout[-3000:]
 
