@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libcup3d_b200.so")
 
 BS3 = 512
 F_CHI, F_PRES, F_VEL, F_TMP, F_LHS, F_N = 0, 1, 2, 5, 8, 9
-ST_LHS, ST_MG, ST_ADVDIFF, ST_PRHS, ST_DIVP, ST_GRADP, ST_VORT, ST_Q = range(8)
+ST_LHS, ST_MG, ST_ADVDIFF, ST_PRHS, ST_DIVP, ST_GRADP, ST_VORT, ST_Q, ST_GRADCHI = range(9)
 M_N = 29  # CUP_M_N: entries of ObstacleBlock.mom (enum M_*, main.c:64-95)
 
 
@@ -56,6 +56,7 @@ SYMBOLS = {
     "cup_set_params": (_i, [_vp, C.POINTER(CupParams)]),
     "cup_synchronize": (_i, [_vp]),
     "cup_mesh_upload": (_i, [_vp, C.POINTER(CupBlk), _ll, C.POINTER(_i), _i]),
+    "cup_mesh_adapt": (_i, [_vp, C.POINTER(CupBlk), _ll, C.POINTER(_i), C.POINTER(_ll), C.POINTER(_i), _i]),
     "cup_nblk": (_ll, [_vp]),
     "cup_nslot": (_ll, [_vp]),
     "cup_mg_levels": (_i, [_vp]),
@@ -264,6 +265,16 @@ class Context:
         arr = blocks_to_struct(np.asarray(ib), np.asarray(rb))
         b = (C.c_int * 3)(*bpd)
         check(self.L.cup_mesh_upload(self.h, arr, len(ib), b, level_max))
+
+    def mesh_adapt(self, ib, rb, kind, src, bpd, level_max):
+        """cup_mesh_adapt: install the new block list, carrying the fields over on the device (kind 0 keep,
+        1 child of the refined old block src, 2 parent of compressed old blocks)"""
+        arr = blocks_to_struct(np.asarray(ib), np.asarray(rb))
+        k = np.ascontiguousarray(kind, np.int32)
+        s = np.ascontiguousarray(src, np.int64)
+        b = (C.c_int * 3)(*bpd)
+        check(self.L.cup_mesh_adapt(self.h, arr, len(ib), k.ctypes.data_as(C.POINTER(_i)),
+                                    s.ctypes.data_as(C.POINTER(_ll)), b, level_max))
 
     @property
     def nblk(self):

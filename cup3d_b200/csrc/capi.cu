@@ -262,6 +262,42 @@ int cup_mesh_upload(CupCtx *c, const CupBlk *blk, long long n, const int bpd[3],
   return rc;
 }
 
+int cup_mesh_adapt(CupCtx *c, const CupBlk *nb, long long n, const int *kind, const long long *src, const int bpd[3],
+                   int level_max) {
+  CUP_ENTER(c);
+  if (!nb || !kind || !src || !bpd || n <= 0) {
+    set_error("cup_mesh_adapt: null argument or n = %lld", n);
+    return CUP_ERR_ARG;
+  }
+  if (c->nblk == 0) {
+    set_error("cup_mesh_adapt: no mesh uploaded");
+    return CUP_ERR_STATE;
+  }
+  void *out[CUP_F_N] = {nullptr};
+  int rc = adapt_fields(c, nb, n, kind, src, out);
+  if (rc == CUP_OK) {
+    rc = mesh_upload_impl(c, nb, n, bpd, level_max);
+    if (rc != CUP_OK) {
+      const std::string keep = cup_last_error();
+      comm_free_level_buffers(c);
+      free_mesh(c);
+      set_error("%s", keep.c_str());
+    }
+  }
+  if (rc == CUP_OK) {
+    const size_t bytes = (size_t)n * 512 * (size_t)c->real_bytes;
+    for (int f = 0; f < CUP_F_N && rc == CUP_OK; f++)
+      if (cudaMemcpyAsync(c->state[f], out[f], bytes, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) {
+        set_error("cup_mesh_adapt: copy of field %d failed", f);
+        rc = CUP_ERR_CUDA;
+      }
+    cudaStreamSynchronize(c->stream);
+  }
+  for (int f = 0; f < CUP_F_N; f++)
+    cudaFree(out[f]);
+  return rc;
+}
+
 long long cup_nblk(const CupCtx *c) { return c->nblk; }
 long long cup_nslot(const CupCtx *c) { return c->nslot; }
 int cup_mg_levels(const CupCtx *c) { return c->top + 1; }

@@ -236,6 +236,11 @@ int vorticity(CupCtx *c);  // vorticity(), main.c:5786: k_vort then 1/h^3
 int stencil_run(CupCtx *c, CupStencilId id, const long long *list, long long n);
 void free_krylov(CupCtx *c);
 
+// adapt_kernels.cu
+int gradchi(CupCtx *c);  // k_gradchi (main.c:3649): F_CHI -> marks in F_TMP
+int adapt_fields(CupCtx *c, const CupBlk *nb, long long n_new, const int *kind, const long long *src,
+                 void *out[CUP_F_N]);
+
 // obstacle.cu
 int obstacle_upload(CupCtx *c, int body, int nob, const int *blk, const double *chi, const double *udef);
 int obstacle_motion(CupCtx *c, int body, const double com[3], const double vel[3], const double omega[3]);

@@ -343,6 +343,28 @@ int build_tables(HostMesh *m, const CupBlk *gblk, long long G, const int *owner_
       }
       for (int g : need[(size_t)rank])
         hput(g, ghost.at(g));
+    } else {
+      // single-level mesh: only the hash and the block coordinates (the tensorial labs of the adaptation
+      // kernels look their 26 neighbours up; sweeps use the level's own tables)
+      size_t cap = 64;
+      while (cap < (size_t)m->nblk * 2)
+        cap *= 2;
+      lf.hkeys.assign(cap, 0ULL);
+      lf.hvals.assign(cap, -1);
+      for (long long i = 0; i < G; i++) {
+        if (owner[i] != rank)
+          continue;
+        const unsigned long long k = key_of(gblk[i].level, gblk[i].ix, gblk[i].iy, gblk[i].iz) + 1;
+        size_t h = (size_t)((k * 0x9E3779B97F4A7C15ULL) >> 20) & (cap - 1);
+        while (lf.hkeys[h] != 0)
+          h = (h + 1) & (cap - 1);
+        lf.hkeys[h] = k;
+        lf.hvals[h] = g2l[i];
+        lf.bijk.push_back(gblk[i].level);
+        lf.bijk.push_back(gblk[i].ix);
+        lf.bijk.push_back(gblk[i].iy);
+        lf.bijk.push_back(gblk[i].iz);
+      }
     }
   }
 

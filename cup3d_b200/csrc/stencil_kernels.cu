@@ -870,7 +870,7 @@ int stencil_run(CupCtx *c, CupStencilId id, const long long *list, long long n) 
     set_error("stencil_run: n = %lld outside [0, %lld]", n, c->nblk);
     return CUP_ERR_ARG;
   }
-  if ((int)id < 0 || (int)id > (int)CUP_ST_Q) {
+  if ((int)id < 0 || (int)id > (int)CUP_ST_GRADCHI) {
     set_error("stencil_run: unknown stencil id %d", (int)id);
     return CUP_ERR_ARG;
   }
@@ -898,7 +898,9 @@ int stencil_run(CupCtx *c, CupStencilId id, const long long *list, long long n) 
     c->run_sub = c->d_list;
     c->run_nsub = (int)n;
   }
-  const int rc = c->real_bytes == 8 ? stencil_t<double>(c, id, nullptr, n) : stencil_t<float>(c, id, nullptr, n);
+  const int rc = id == CUP_ST_GRADCHI
+                     ? gradchi(c)
+                     : (c->real_bytes == 8 ? stencil_t<double>(c, id, nullptr, n) : stencil_t<float>(c, id, nullptr, n));
   c->run_sub = nullptr;
   c->run_nsub = -1;
   return rc;

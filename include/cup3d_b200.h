@@ -66,7 +66,9 @@ typedef enum {
   CUP_ST_DIVP = 4,    /* st_divp    F_PRES -> F_TMP[0] */
   CUP_ST_GRADP = 5,   /* st_gradp   F_PRES -> F_TMP[0..2] */
   CUP_ST_VORT = 6,    /* st_vort    F_VEL  -> F_TMP[0..2] (h^3-weighted vorticity, with its flux correction) */
-  CUP_ST_Q = 7        /* st_q       F_VEL  -> F_LHS (Q criterion) */
+  CUP_ST_Q = 7,       /* st_q       F_VEL  -> F_LHS (Q criterion) */
+  CUP_ST_GRADCHI = 8  /* st_gradchi F_CHI (ss = 2, tensorial) -> F_TMP: cells inside bodies zeroed, blocks whose
+                         extended neighbourhood holds 1e-5 < chi < 0.9 marked with 1e10 (main.c:3649-3681) */
 } CupStencilId;
 
 /* run-time scalars the kernels read from the reference's sim/sta globals */
@@ -194,6 +196,20 @@ int cup_vorticity(CupCtx *ctx);
  * 1e10 marker of blocks whose extended chi neighbourhood contains 1e-5 < chi < 0.9, depends on F_CHI
  * alone and stays on the host (F_CHI is produced there by fish_build).  NULL = not wanted. */
 int cup_block_linf(CupCtx *ctx, int f0, double *linf_all, double *linf_fluid);
+
+/* The data-parallel half of mesh_adapt (main.c:4012-4190).  The host keeps the tree surgery: from
+ * cup_vorticity + cup_stencil_apply(CUP_ST_GRADCHI) + cup_block_linf it tags (mesh_tag), balances (mesh_fix)
+ * and builds the NEW block list; this call then produces the new state on the device from the old one and
+ * installs the new mesh (what cup_mesh_upload does, but the fields are carried over instead of zeroed):
+ *   kind[i] = 0  new block i is old block src[i], unchanged                       (all nine fields copied)
+ *   kind[i] = 1  new block i is a child of the REFINED old block src[i]; all eight children must be listed;
+ *                F_PRES and F_VEL are interpolated (mesh_refine :3790), the other fields are zero (:4068)
+ *   kind[i] = 2  new block i is the parent of eight COMPRESSED old blocks, src[i] = any one of them;
+ *                all nine fields are 2x2x2 averages (:4129-4146)
+ * One rank only (the reference also rebalances blocks between ranks here, mesh_bal; not built).
+ * Obstacle blocks are dropped, as by cup_mesh_upload. */
+int cup_mesh_adapt(CupCtx *ctx, const CupBlk *new_blk, long long n_new, const int *kind, const long long *src,
+                   const int bpd[3], int level_max);
 
 /* io_dump's field part (main.c:1441-1442, :1525-1535): vorticity(); qcrit();
  * then float32 packing on the device -- attr[nblk*512] = chi, vort[nblk*512][3] (interleaved),

@@ -13,6 +13,9 @@ inputs  D/in_vec.npy   [n,512]    right-hand side / operand of vcycle and op
         D/in_state.npy [n,9,512]  sta.fld for advdiff / proj
 outputs D/out_vcycle.npy, D/out_op.npy, D/out_advdiff.npy [n,3,512] (F_VEL),
         D/out_proj.npy [n,4,512] (F_PRES, F_VEL), D/ib.npy, D/meta.json
+        gradchi: D/out_gradchi.npy [n,3,512] = F_TMP after stencil_apply(&st_gradchi) (main.c:3649)
+        adapt:   vorticity(); gradchi -> D/adapt_mid.npy (the state mesh_adapt's refinement / compression
+                 read), then mesh_adapt(--rtol, --ctol) -> D/adapt_ib.npy, D/adapt_rb.npy, D/adapt_state.npy
 """
 import argparse
 import json
@@ -39,6 +42,8 @@ def main():
     ap.add_argument("--uinf", default="0.1,-0.05,0.02")
     ap.add_argument("--ptol", type=float, default=1e-9)
     ap.add_argument("--ptol-rel", type=float, default=1e-14)
+    ap.add_argument("--rtol", type=float, default=1e9)
+    ap.add_argument("--ctol", type=float, default=-1.0)
     a = ap.parse_args()
     if a.threads > 0:
         os.environ["OMP_NUM_THREADS"] = str(a.threads)
@@ -67,7 +72,7 @@ def main():
         if "op" in ops:
             np.save(os.path.join(a.dir, "out_op.npy"), R.pois_op(x))
         del x
-    if "advdiff" in ops or "proj" in ops:
+    if any(o in ops for o in ("advdiff", "proj", "gradchi", "adapt")):
         st = np.load(os.path.join(a.dir, "in_state.npy"))
         if "advdiff" in ops:
             R.state_set(st)
@@ -81,6 +86,20 @@ def main():
             R.projection()
             meta["proj_s"] = time.time() - t0
             np.save(os.path.join(a.dir, "out_proj.npy"), R.state_get()[:, 1:5])
+        if "gradchi" in ops:
+            R.state_set(st)
+            R.stencil("gradchi")
+            np.save(os.path.join(a.dir, "out_gradchi.npy"), R.state_get()[:, 5:8])
+        if "adapt" in ops:  # last: it changes the mesh
+            R.state_set(st)
+            R.vorticity()
+            R.stencil("gradchi")
+            np.save(os.path.join(a.dir, "adapt_mid.npy"), R.state_get())
+            R.mesh_adapt(a.rtol, a.ctol)
+            ib2, rb2 = R.blocks()
+            np.save(os.path.join(a.dir, "adapt_ib.npy"), ib2)
+            np.save(os.path.join(a.dir, "adapt_rb.npy"), rb2)
+            np.save(os.path.join(a.dir, "adapt_state.npy"), R.state_get())
     with open(os.path.join(a.dir, "meta.json"), "w") as f:
         json.dump(meta, f)
 
