@@ -474,11 +474,22 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
         "sweeps": sweeps,
     }
-    print(json.dumps(line), flush=True)
     try:
         ctx.close()
     except Exception:
         pass
+    # secondary, N = 1: BASELINE.json configs[2] (AMR full time step, fp32) measured by this same script in a
+    # fresh process (bench.py --config amr), after everything above; a failure there cannot touch the line
+    if world == 1 and not args.no_amr:
+        try:
+            torch.cuda.empty_cache()
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--config", "amr", "--steps", "3",
+                                "--warmup", "1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=420)
+            got = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            line["amr_step"] = json.loads(got[-1]) if got else {"error": r.stderr[-300:]}
+        except Exception as ex:
+            line["amr_step"] = {"error": str(ex)[:200]}
+    print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
     if parity.get("rel_err") is not None and parity["rel_err"] > 1e-10:
@@ -649,6 +660,7 @@ def main():
                          "ours; for --impl reference 6 when the host has >= 48 GB free, else 5)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-parity", action="store_true", help="skip the live parity check against the reference")
+    ap.add_argument("--no-amr", action="store_true", help="skip the secondary AMR time-step measurement (N = 1)")
     ap.add_argument("--config", default="vcycle", choices=["vcycle", "amr"],
                     help="vcycle: BASELINE.json's headline (512^3 V-cycle); amr: configs[2], the full AMR time step")
     ap.add_argument("--amr-base", type=int, default=32, help="base blocks per dimension (32 = 256^3 cells)")

@@ -66,6 +66,10 @@ __global__ void __launch_bounds__(TPB) k_advdiff_amr(LevelView lv, const int *__
                                                      Real ux, Real uy, Real uz) {
   __shared__ Real tile[8 * AD_SLAB];
   __shared__ Real patch[6][16];
+  // level L-1 view behind a face towards a coarser leaf: 3 coarse layers x 6 x 6 (the 3x3x3 neighbourhoods of
+  // the coarse cells under the third ghost layer), sampled ONCE per (block, component, face) -- the Taylor
+  // expansion of every ghost cell then reads shared memory instead of probing the leaf hash 19 times
+  __shared__ Real cscr[6][108];
   const int t = threadIdx.x, x = t & 7, y = t >> 3, a = t & 7, c2 = t >> 3;
   const Real *vel[3] = {v0, v1, v2};
   Real *tmp[3] = {t0, t1, t2};
@@ -99,6 +103,21 @@ __global__ void __launch_bounds__(TPB) k_advdiff_amr(LevelView lv, const int *__
       for (int f = 0; f < 6; f++)
         if (nb[f] == kCoarse)
           coarse_patch_load<Real>(vc + (size_t)ext24[f * 4] * 512, f, ext24[f * 4 + 1], t, patch[f]);
+#pragma unroll 1
+      for (int f = 0; f < 6; f++) {
+        if (nb[f] != kCoarse)
+          continue;
+        const int d = f >> 1, t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
+        const int corg[3] = {bx * 4, by * 4, bz * 4};  // the block's origin in level L-1 cells
+        for (int e = t; e < 108; e += TPB) {
+          const int n = e / 36, j = (e / 6) % 6, i = e % 6;
+          int cc[3];
+          cc[d] = (f & 1) ? corg[d] + 4 + n : corg[d] - 3 + n;
+          cc[t1] = corg[t1] - 1 + i;
+          cc[t2] = corg[t2] - 1 + j;
+          cscr[f][e] = cs_sample<Real>(geo, vc, c, L - 1, cc[0], cc[1], cc[2]);
+        }
+      }
       __syncthreads();
       // ghost of face f at distance g for plane element (pa, pc)
       auto ghost = [&](int f, int g, int pa, int pc) -> Real {
@@ -120,22 +139,36 @@ __global__ void __launch_bounds__(TPB) k_advdiff_amr(LevelView lv, const int *__
           return g == 1 ? (Real)(1.0 / 15.0) * ((Real)8.0 * vt + ((Real)10.0 * bb - (Real)3.0 * cq))
                         : (Real)(1.0 / 15.0) * ((Real)24.0 * vt + ((Real)-15.0 * bb + (Real)6 * cq));
         }
-        // third layer: fine cell n = -3 (or 10) along d; tangential (pa, pc)
-        int fi[3];
+        // third layer: fine cell n = -3 (or 10) along d, tangential (pa, pc): OP_INTERP (main.c:3439) around the
+        // coarse cell under it -- the middle one of the three sampled layers
         const int t1 = d == 0 ? 1 : 0, t2 = d == 2 ? 1 : 2;
-        fi[d] = (f & 1) ? 10 : -3;
-        fi[t1] = pa;
-        fi[t2] = pc;
-        const int org[3] = {bx * 8, by * 8, bz * 8};
-        int cc[3];
+        const int i1 = (pa >> 1) + 1, i2 = (pc >> 1) + 1;
+        const Real *S0 = cscr[f];
+        auto C3 = [&](int I, int J, int K) -> Real {
+          const int o[3] = {I - 1, J - 1, K - 1};
+          return S0[((1 + o[d]) * 6 + (i2 + o[t2])) * 6 + (i1 + o[t1])];
+        };
         Real sg[3];
-#pragma unroll
-        for (int q = 0; q < 3; q++) {
-          const int gf = org[q] + fi[q];  // global fine cell (may be outside the block)
-          cc[q] = gf >> 1;                // arithmetic shift == floor for negatives
-          sg[q] = (gf & 1) ? (Real)1 : (Real)-1;
+        {
+          // child offsets: parity of the global fine cell (the block origin is even in every direction)
+          const int fn = (f & 1) ? 10 : -3;
+          sg[d] = (fn & 1) ? (Real)1 : (Real)-1;
+          sg[t1] = (pa & 1) ? (Real)1 : (Real)-1;
+          sg[t2] = (pc & 1) ? (Real)1 : (Real)-1;
         }
-        return interp_ghost<Real>(geo, vc, c, L - 1, cc[0], cc[1], cc[2], sg[0], sg[1], sg[2]);
+        const Real c111 = C3(1, 1, 1);
+        const Real c011 = C3(0, 1, 1), c211 = C3(2, 1, 1), c101 = C3(1, 0, 1), c121 = C3(1, 2, 1), c110 = C3(1, 1, 0),
+                   c112 = C3(1, 1, 2);
+        const Real dudx = (Real)0.125 * (c211 - c011);
+        const Real dudy = (Real)0.125 * (c121 - c101);
+        const Real dudz = (Real)0.125 * (c112 - c110);
+        const Real dudxdy = (Real)0.015625 * (((C3(0, 0, 1) + C3(2, 2, 1)) - C3(2, 0, 1)) - C3(0, 2, 1));
+        const Real dudxdz = (Real)0.015625 * (((C3(0, 1, 0) + C3(2, 1, 2)) - C3(2, 1, 0)) - C3(0, 1, 2));
+        const Real dudydz = (Real)0.015625 * (((C3(1, 0, 0) + C3(1, 2, 2)) - C3(1, 2, 0)) - C3(1, 0, 2));
+        const Real lap =
+            c111 + (Real)0.03125 * ((((((c011 + c211) + c101) + c121) + c110) + c112) + (Real)(-6.0) * c111);
+        const Real sx = sg[0], sy = sg[1], sz = sg[2];
+        return (((((lap + sx * dudx) + sy * dudy) + sz * dudz) + sx * sy * dudxdy) + sx * sz * dudxdz) + sy * sz * dudydz;
       };
       // z-extended line
       Real line[14];

@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(TPB, 12)
                const __grid_constant__ CUtensorMap myl, const __grid_constant__ CUtensorMap mxe,
                const __grid_constant__ CUtensorMap mye) {
   __shared__ Stage<Real> st;
+  __shared__ Real s_res[128];
   const int t = threadIdx.x, x = t & 7, y = t >> 3, G = gridDim.x;
   const Real *rf = rface_of<Real>(lv);
   if (t == 0) {
@@ -81,9 +82,9 @@ __global__ void __launch_bounds__(TPB, 12)
       sr[k2] += __shfl_xor_sync(0xffffffffu, sr[k2], 8);
       su[k2] += __shfl_xor_sync(0xffffffffu, su[k2], 8);
     }
-    if (((x | y) & 1) == 0) {
-      const int cx = x >> 1, cy = y >> 1;
-      if (ps >= 0) {
+    if (ps >= 0) {
+      if (((x | y) & 1) == 0) {
+        const int cx = x >> 1, cy = y >> 1;
         Real *pf = f.at(ps), *pu = u.at(ps);
 #pragma unroll
         for (int cz = 0; cz < 4; cz++) {
@@ -91,14 +92,24 @@ __global__ void __launch_bounds__(TPB, 12)
           pf[pidx] = sr[cz];
           pu[pidx] = (Real)0.125 * su[cz];
         }
-      } else {  // parent on another rank: MG_M layout (64 r, 64 u), main.c:4750
-        Real *q = rptr[kRemote0 - ps];
+      }
+    } else {
+      // parent on another rank: MG_M layout (64 r, 64 u), main.c:4750.  The 128 values are gathered in shared
+      // memory first so that they cross NVLink as two contiguous 64-element stores of the whole CTA instead
+      // of sixteen threads' scattered words (ps is the same for the whole block: no divergence)
+      if (((x | y) & 1) == 0) {
+        const int cx = x >> 1, cy = y >> 1;
 #pragma unroll
         for (int cz = 0; cz < 4; cz++) {
-          q[(cz * 4 + cy) * 4 + cx] = sr[cz];
-          q[64 + (cz * 4 + cy) * 4 + cx] = (Real)0.125 * su[cz];
+          s_res[(cz * 4 + cy) * 4 + cx] = sr[cz];
+          s_res[64 + (cz * 4 + cy) * 4 + cx] = (Real)0.125 * su[cz];
         }
       }
+      __syncthreads();
+      Real *q = rptr[kRemote0 - ps];
+      q[t] = s_res[t];
+      q[64 + t] = s_res[64 + t];
+      __syncthreads();
     }
   }
   comm_post_at_exit(post);  // children of remote parents are in their owners' windows
