@@ -540,9 +540,13 @@ def run_amr(args, rank, world, local_rank):
         stn[s0:s0 + m, 4] = (0.1 * np.sin(2 * np.pi * Z)).reshape(m, 512)
     hmin = float(grb[:, 0].min())
     ptol, ptol_rel = (1e-4, 1e-3) if rbytes == 4 else (1e-6, 1e-4)
-    ctx.set_params(dt=0.2 * hmin, nu=1e-3, uinf=(0.0, 0.0, 0.0), step=5, mean_constraint=2, ptol=ptol,
-                   ptol_rel=ptol_rel)
+    nu, cfl = 1e-3, 0.4
+    ctx.set_params(dt=1e-6, nu=nu, uinf=(0.0, 0.0, 0.0), step=5, mean_constraint=2, ptol=ptol, ptol_rel=ptol_rel)
     ctx.state_h2d(stn)
+    # the reference's time-step control (sta_dt, main.c:5941-5961) for this velocity field, then fixed
+    um = ctx.umax()
+    dt = min(cfl * hmin / (um + 1e-8), (1.0 / 6.0) * hmin * hmin / (nu + (1.0 / 6.0) * hmin * um))
+    ctx.set_params(dt=dt)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
 
@@ -627,7 +631,7 @@ def run_amr(args, rank, world, local_rank):
                                "advdiff() + projection() per step, %s" % (8 * base, nlev, args.amr_dtype),
                    "blocks": len(gib), "cells": gcells, "blocks_per_level": np.bincount(gib[:, 0]).tolist(),
                    "mg_active_blocks_per_level": [int(v) for v in nact.tolist()],
-                   "poisson_tolerance": [ptol, ptol_rel],
+                   "poisson_tolerance": [ptol, ptol_rel], "dt": dt, "nu": nu, "cfl": cfl,
                    "l2_policy": "inputs larger than L2 (%.2f GB per field per rank)" % (n * 512 * rbytes / 1e9),
                    "parallelism": "%d rank(s); coarse-fine interfaces across ranks through ghost blocks" % world},
         "krylov_iterations_per_step": its / args.steps, "vcycles_per_step": vcs / args.steps,

@@ -733,8 +733,17 @@ static int setup_ghost_blocks(CupCtx *c, Level &v, bool p2p, bool is_leaf) {
   }
   CUP_TRY(up((char ***)&v.d_bptr0, b0));
   CUP_TRY(up((char ***)&v.d_bptr1, b1));
-  v.blk_speers = peers_of(v.blk_scnt);
-  v.blk_rpeers = peers_of(v.blk_rcnt);
+  // Who reads whose blocks is NOT symmetric (a fine block reads the coarser leaf behind an interface, the
+  // coarse leaf's owner may read nothing back), but the double-buffered areas rely on "nobody is more than
+  // one exchange ahead of a peer": every rank therefore notifies AND awaits every rank it exchanges blocks
+  // with in either direction.
+  {
+    std::vector<int> both((size_t)c->nranks, 0);
+    for (int p = 0; p < c->nranks; p++)
+      both[(size_t)p] = (v.blk_scnt[(size_t)p] > 0 || v.blk_rcnt[(size_t)p] > 0) ? 1 : 0;
+    v.blk_speers = peers_of(both);
+    v.blk_rpeers = v.blk_speers;
+  }
   CUP_TRY(up(&v.d_blk_speers, v.blk_speers));
   CUP_TRY(up(&v.d_blk_rpeers, v.blk_rpeers));
   if (is_leaf) {
@@ -1104,13 +1113,16 @@ int block_exchange_mg(CupCtx *c, Level &v, SlotVec<Real> same, SlotVec<Real> can
                                                                post);
     c->launches++;
   } else {
-    k_signal<<<1, 64, 0, c->stream>>>(post.seq, cm->d_peer_win, nullptr, 0, post.flag_index);
+    k_signal<<<1, 64, 0, c->stream>>>(post.seq, cm->d_peer_win, post.peers, post.np, post.flag_index);
     c->launches++;
   }
   if (nr) {
     k_unpack_blocks_mg<Real><<<cgrid(c, nr), 128, 0, c->stream>>>(v.d_blk_rslot, v.d_blk_rkind, nr,
                                                                  (const Real *)v.d_brecv, v.blk_stride, seq, same, can,
                                                                  wait);
+    c->launches++;
+  } else if (wait.np > 0) {
+    k_wait<<<1, 64, 0, c->stream>>>(wait);  // a pure sender still stays in step with its receivers
     c->launches++;
   }
   CUP_CUDA(cudaGetLastError());
@@ -1146,13 +1158,16 @@ int block_exchange_leaf(CupCtx *c, const Real *const *src, Real *const *dst, int
                                                                  post);
     c->launches++;
   } else {
-    k_signal<<<1, 64, 0, c->stream>>>(post.seq, cm->d_peer_win, nullptr, 0, post.flag_index);
+    k_signal<<<1, 64, 0, c->stream>>>(post.seq, cm->d_peer_win, post.peers, post.np, post.flag_index);
     c->launches++;
   }
   if (nr) {
     k_unpack_blocks_leaf<Real><<<cgrid(c, nr), 128, 0, c->stream>>>(v.d_blk_rslot, nr, ncomp, 512, 512 * v.blk_ncomp,
                                                                    (const Real *)v.d_brecv, v.blk_stride, seq, cp,
                                                                    dst_off, wait);
+    c->launches++;
+  } else if (wait.np > 0) {
+    k_wait<<<1, 64, 0, c->stream>>>(wait);
     c->launches++;
   }
   CUP_CUDA(cudaGetLastError());

@@ -41,7 +41,7 @@ def blob_state(c, centre, radius, seed=5):
     return np.ascontiguousarray(st)
 
 
-@pytest.mark.parametrize("name,centre,radius", [("u16", (0.5, 0.45, 0.55), 0.2), ("amr2", (0.3, 0.35, 0.4), 0.07),
+@pytest.mark.parametrize("name,centre,radius", [("u32", (0.3, 0.35, 0.4), 0.12), ("amr2", (0.3, 0.35, 0.4), 0.07),
                                                 ("amr2", (0.55, 0.5, 0.45), 0.25), ("amr3", (0.3, 0.35, 0.4), 0.1)])
 def test_gradchi(built, name, centre, radius):
     import cup3d_b200
