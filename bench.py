@@ -575,27 +575,24 @@ def run_amr(args, rank, world, local_rank):
     l0 = ctx.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     its, vcs = 0, 0
+    marks = []  # (before advdiff, between, after projection) of every step: the two halves of the step
     e0.record(stream)
     for _ in range(args.steps):
-        info = step()
+        m = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        m[0].record(stream)
+        ctx.advdiff()
+        m[1].record(stream)
+        info = ctx.projection()
+        m[2].record(stream)
+        marks.append(m)
         its += info.iterations
         vcs += info.vcycles
     e1.record(stream)
     barrier()
     ms = maxr(e0.elapsed_time(e1))
     launches = ctx.kernel_launches() - l0
-    # the two halves of a step, timed separately (3 calls each)
-    phase_ms = {}
-    for name in ("advdiff", "projection"):
-        fn = getattr(ctx, name)
-        barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record(stream)
-        for _ in range(3):
-            fn()
-        a1.record(stream)
-        barrier()
-        phase_ms[name] = maxr(a0.elapsed_time(a1)) / 3
+    phase_ms = {"advdiff": maxr(sum(m[0].elapsed_time(m[1]) for m in marks) / len(marks)),
+                "projection": maxr(sum(m[1].elapsed_time(m[2]) for m in marks) / len(marks))}
     clocks = clk.stop()
     umax = ctx.umax()
     # end to end: the velocity goes up from pinned host memory every step, the step's result (the

@@ -1,5 +1,6 @@
 // capi.cu -- the extern "C" boundary declared in include/cup3d_b200.h.
 #include <algorithm>
+#include <thread>
 
 #include "blas_kernels.cuh"
 #include "cup_internal.h"
@@ -103,6 +104,149 @@ struct DevGuard {
   }                                          \
   cup::DevGuard guard_(c)
 
+// ---- sta.fld <-> device.  The host layout is [blk][9][512] doubles, the device keeps one flat vector per
+// field.  A strided (2-D) DMA copy pays ~10 us per 4 KB row -- 7 s for the three velocity fields of a
+// 241k-block mesh -- so the transfer goes through CONTIGUOUS chunks instead: a pinned bounce buffer
+// [blocks of the chunk][nc][512] (filled / emptied by a few host threads when nc < 9; the user's memory
+// itself when all nine fields move), one 1-D copy per chunk, and a device kernel that (un)interleaves
+// and converts to / from Real.
+namespace {
+enum { XFER_CHUNK_BYTES = 64 << 20 };
+
+struct Xfer {
+  double *h_bounce[2] = {nullptr, nullptr};
+  double *d_stage[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};
+};
+Xfer *xfer_of(CupCtx *c) {
+  if (!c->xfer) {
+    Xfer *x = new Xfer;
+    for (int i = 0; i < 2; i++) {
+      if (cudaMallocHost((void **)&x->h_bounce[i], XFER_CHUNK_BYTES) != cudaSuccess ||
+          cudaMalloc((void **)&x->d_stage[i], XFER_CHUNK_BYTES) != cudaSuccess ||
+          cudaEventCreateWithFlags(&x->done[i], cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        for (int j = 0; j < 2; j++) {
+          if (x->h_bounce[j])
+            cudaFreeHost(x->h_bounce[j]);
+          cudaFree(x->d_stage[j]);
+          if (x->done[j])
+            cudaEventDestroy(x->done[j]);
+        }
+        delete x;
+        return nullptr;
+      }
+    }
+    c->xfer = x;
+  }
+  return (Xfer *)c->xfer;
+}
+
+struct FieldPtrs {
+  void *p[CUP_F_N];
+};
+
+// stage [nb][nc][512] doubles <-> fields f0..f0+nc-1, blocks b0..b0+nb-1
+template <typename Real, bool IN>
+__global__ void __launch_bounds__(256) k_xfer(double *__restrict__ stage, FieldPtrs F, int f0, int nc, long long b0,
+                                              int nb) {
+  const long long n = (long long)nb * nc * 512;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int cell = (int)(i & 511);
+    const long long r = i >> 9;
+    const int q = (int)(r % nc);
+    const long long blk = b0 + r / nc;
+    Real *fp = (Real *)F.p[f0 + q] + blk * 512 + cell;
+    if (IN)
+      *fp = (Real)stage[i];
+    else
+      stage[i] = (double)*fp;
+  }
+}
+
+// copy rows of `rowd` doubles between the user's strided layout and a dense buffer with a few threads
+void host_rows(double *dense, double *strided, long long nrows, size_t rowd, size_t pitchd, bool gather) {
+  const int nt = nrows > 4096 ? 8 : 1;
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; t++)
+    th.emplace_back([=]() {
+      for (long long r = nrows * t / nt; r < nrows * (t + 1) / nt; r++) {
+        if (gather)
+          memcpy(dense + (size_t)r * rowd, strided + (size_t)r * pitchd, rowd * sizeof(double));
+        else
+          memcpy(strided + (size_t)r * pitchd, dense + (size_t)r * rowd, rowd * sizeof(double));
+      }
+    });
+  for (auto &x : th)
+    x.join();
+}
+
+int state_xfer(CupCtx *c, double *h_fld, int f0, int nc, bool in) {
+  Xfer *x = xfer_of(c);
+  if (!x) {
+    set_error("cup_state_%s: cannot allocate the transfer buffers", in ? "h2d" : "d2h");
+    return CUP_ERR_CUDA;
+  }
+  FieldPtrs F;
+  for (int f = 0; f < CUP_F_N; f++)
+    F.p[f] = c->state[f];
+  const size_t rowd = (size_t)nc * 512, pitchd = (size_t)CUP_F_N * 512;
+  const long long per = (long long)(XFER_CHUNK_BYTES / (rowd * sizeof(double)));
+  const bool dense = nc == CUP_F_N;  // the user's memory is contiguous for this range
+  int k = 0;
+  // d2h with a bounce buffer: the scatter of chunk i runs while chunk i+1 is in flight
+  long long pend_b0 = -1, pend_nb = 0;
+  int pend_k = 0;
+  auto scatter_pending = [&]() -> int {
+    if (pend_b0 < 0)
+      return CUP_OK;
+    CUP_CUDA(cudaEventSynchronize(x->done[pend_k]));
+    host_rows(x->h_bounce[pend_k], h_fld + (size_t)pend_b0 * pitchd + (size_t)f0 * 512, pend_nb, rowd, pitchd, false);
+    pend_b0 = -1;
+    return CUP_OK;
+  };
+  for (long long b0 = 0; b0 < c->nblk; b0 += per, k ^= 1) {
+    const int nb = (int)std::min<long long>(per, c->nblk - b0);
+    const size_t bytes = (size_t)nb * rowd * sizeof(double);
+    const int grid = (int)std::min<long long>(((long long)nb * rowd + 255) / 256, (long long)c->num_sms * 8);
+    double *hsrc = dense ? h_fld + (size_t)b0 * pitchd : x->h_bounce[k];
+    if (in) {
+      if (!dense) {
+        CUP_CUDA(cudaEventSynchronize(x->done[k]));  // the copy that last used this bounce buffer has left it
+        host_rows(x->h_bounce[k], h_fld + (size_t)b0 * pitchd + (size_t)f0 * 512, nb, rowd, pitchd, true);
+      }
+      CUP_CUDA(cudaMemcpyAsync(x->d_stage[k], hsrc, bytes, cudaMemcpyHostToDevice, c->stream));
+      CUP_CUDA(cudaEventRecord(x->done[k], c->stream));
+      if (c->real_bytes == 8)
+        k_xfer<double, true><<<grid, 256, 0, c->stream>>>(x->d_stage[k], F, f0, nc, b0, nb);
+      else
+        k_xfer<float, true><<<grid, 256, 0, c->stream>>>(x->d_stage[k], F, f0, nc, b0, nb);
+    } else {
+      if (c->real_bytes == 8)
+        k_xfer<double, false><<<grid, 256, 0, c->stream>>>(x->d_stage[k], F, f0, nc, b0, nb);
+      else
+        k_xfer<float, false><<<grid, 256, 0, c->stream>>>(x->d_stage[k], F, f0, nc, b0, nb);
+      if (!dense && pend_b0 >= 0 && pend_k == k)
+        CUP_TRY(scatter_pending());  // this bounce buffer still holds an unscattered chunk
+      CUP_CUDA(cudaMemcpyAsync(hsrc, x->d_stage[k], bytes, cudaMemcpyDeviceToHost, c->stream));
+      CUP_CUDA(cudaEventRecord(x->done[k], c->stream));
+      if (!dense) {
+        CUP_TRY(scatter_pending());
+        pend_b0 = b0;
+        pend_nb = nb;
+        pend_k = k;
+      }
+    }
+    c->launches++;
+  }
+  CUP_CUDA(cudaGetLastError());
+  CUP_TRY(scatter_pending());
+  CUP_CUDA(cudaStreamSynchronize(c->stream));
+  return comm_check_error(c);
+}
+}  // namespace
+
+
 }  // namespace cup
 
 using namespace cup;
@@ -195,6 +339,16 @@ int cup_destroy(CupCtx *c) {
     cudaFree(c->vel_spare[q]);
   cudaFree(c->d_W);
   cudaFree(c->d_hw);
+  if (c->xfer) {
+    Xfer *x = (Xfer *)c->xfer;
+    for (int i = 0; i < 2; i++) {
+      cudaFreeHost(x->h_bounce[i]);
+      cudaFree(x->d_stage[i]);
+      cudaEventDestroy(x->done[i]);
+    }
+    delete x;
+    c->xfer = nullptr;
+  }
   cudaFree(c->d_scal);
   cudaFreeHost(c->h_scal);
   if (c->h_err)
@@ -307,47 +461,20 @@ long long cup_mg_nact(const CupCtx *c, int level) {
 
 int cup_state_h2d(CupCtx *c, const double *h_fld, int f0, int nc) {
   CUP_ENTER(c);
-  if (f0 < 0 || nc < 1 || f0 + nc > CUP_F_N || c->nblk == 0) {
-    set_error("cup_state_h2d: bad field range %d+%d", f0, nc);
+  if (!h_fld || f0 < 0 || nc < 1 || f0 + nc > CUP_F_N || c->nblk == 0) {
+    set_error("cup_state_h2d: bad field range %d+%d (or no mesh / null pointer)", f0, nc);
     return CUP_ERR_ARG;
   }
-  const size_t spitch = (size_t)CUP_F_N * 512 * 8, row = 512 * 8;
-  for (int f = f0; f < f0 + nc; f++) {
-    void *dst = c->real_bytes == 8 ? c->state[f] : c->tmp_stage;
-    CUP_CUDA(cudaMemcpy2DAsync(dst, row, h_fld + (size_t)f * 512, spitch, row, (size_t)c->nblk,
-                               cudaMemcpyHostToDevice, c->stream));
-    if (c->real_bytes == 4) {
-      k_cvt_in<float><<<c->num_sms * 8, 256, 0, c->stream>>>((float *)c->state[f], (const double *)c->tmp_stage,
-                                                             c->nblk * 512);
-      c->launches++;
-    }
-  }
-  CUP_CUDA(cudaStreamSynchronize(c->stream));
-  return CUP_OK;
+  return state_xfer(c, const_cast<double *>(h_fld), f0, nc, true);
 }
 
 int cup_state_d2h(CupCtx *c, double *h_fld, int f0, int nc) {
   CUP_ENTER(c);
-  if (f0 < 0 || nc < 1 || f0 + nc > CUP_F_N || c->nblk == 0) {
-    set_error("cup_state_d2h: bad field range %d+%d", f0, nc);
+  if (!h_fld || f0 < 0 || nc < 1 || f0 + nc > CUP_F_N || c->nblk == 0) {
+    set_error("cup_state_d2h: bad field range %d+%d (or no mesh / null pointer)", f0, nc);
     return CUP_ERR_ARG;
   }
-  const size_t dpitch = (size_t)CUP_F_N * 512 * 8, row = 512 * 8;
-  for (int f = f0; f < f0 + nc; f++) {
-    const void *src = c->state[f];
-    if (c->real_bytes == 4) {
-      k_cvt_out<float><<<c->num_sms * 8, 256, 0, c->stream>>>((double *)c->tmp_stage, (const float *)c->state[f],
-                                                              c->nblk * 512);
-      c->launches++;
-      src = c->tmp_stage;
-    }
-    CUP_CUDA(cudaMemcpy2DAsync(h_fld + (size_t)f * 512, dpitch, src, row, row, (size_t)c->nblk,
-                               cudaMemcpyDeviceToHost, c->stream));
-    if (c->real_bytes == 4)
-      CUP_CUDA(cudaStreamSynchronize(c->stream));
-  }
-  CUP_CUDA(cudaStreamSynchronize(c->stream));
-  return CUP_OK;
+  return state_xfer(c, h_fld, f0, nc, false);
 }
 
 void *cup_state_dev(CupCtx *c, int f) { return (f < 0 || f >= CUP_F_N) ? nullptr : c->state[f]; }

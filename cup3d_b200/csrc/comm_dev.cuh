@@ -128,6 +128,51 @@ __device__ __forceinline__ void push_faces(const int *__restrict__ bs, void *con
   }
 }
 
+// The same through shared memory: x planes would leave the SM as 64 separate 8-byte stores (one per
+// thread, 64-byte apart in the thread's view), which crosses NVLink at a fraction of its rate (r02 trace at
+// 8 GPUs: ~30 us per finest-level sweep above the 1/8 share of the single-GPU time).  The CTA first gathers
+// the planes it has to send in `stage` (>= 384 Reals, free at the call), then every plane leaves as ONE
+// contiguous 64-element store of the whole CTA.  All 64 threads must call it (it synchronises).
+template <typename Real>
+__device__ __forceinline__ void push_faces_staged(const int *__restrict__ bs, void *const *__restrict__ fp,
+                                                  const Real (&v)[8], int t, int x, int y, Real *stage) {
+  const int e0 = bs[0], e1 = bs[1], e2 = bs[2], e3 = bs[3], e4 = bs[4], e5 = bs[5];
+  __syncthreads();  // whoever used `stage` before is done with it
+  if (e0 >= 0 && x == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      stage[0 * 64 + k * 8 + y] = v[k];
+  }
+  if (e1 >= 0 && x == 7) {
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      stage[1 * 64 + k * 8 + y] = v[k];
+  }
+  if (e2 >= 0 && y == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      stage[2 * 64 + k * 8 + x] = v[k];
+  }
+  if (e3 >= 0 && y == 7) {
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      stage[3 * 64 + k * 8 + x] = v[k];
+  }
+  __syncthreads();
+  if (e0 >= 0)
+    ((Real *)fp[e0])[t] = stage[t];
+  if (e1 >= 0)
+    ((Real *)fp[e1])[t] = stage[64 + t];
+  if (e2 >= 0)
+    ((Real *)fp[e2])[t] = stage[128 + t];
+  if (e3 >= 0)
+    ((Real *)fp[e3])[t] = stage[192 + t];
+  if (e4 >= 0)
+    ((Real *)fp[e4])[t] = v[0];
+  if (e5 >= 0)
+    ((Real *)fp[e5])[t] = v[7];
+}
+
 // read of data another GPU stored into this rank's window: never through a possibly stale L1 line
 template <typename Real>
 __device__ __forceinline__ Real ld_recv(const Real *p) {

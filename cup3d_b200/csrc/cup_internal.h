@@ -194,6 +194,7 @@ struct CupCtx {
   bool no_flux_correction = false;  // st_mg on the leaves (stencil_apply(CUP_ST_MG)): k_mg has no flux faces
   void *obst = nullptr;         // cup::Obstacles (obstacle.cu)
   void *io_buf = nullptr;       // io_dump packing: 5 floats per cell (allocated on first use)
+  void *xfer = nullptr;         // staging buffers of cup_state_h2d / d2h (capi.cu)
   bool keep_tmp_udef = false;   // projection(): F_TMP already holds fish_tmpv()'s udef
   // stencil_run(st, list, n) (main.c:3631): the caller's block list on the device while a listed
   // sweep runs; d_list holds 2*nblk ints (the list, and its split into regular / interface blocks)

@@ -211,6 +211,7 @@ template <typename Real>
 __global__ void __launch_bounds__(TPB) k_up(LevelView lv, const int *__restrict__ pslot, const int *__restrict__ oct,
                                             SlotVec<Real> u, SlotVec<Real> us, const Real *__restrict__ precv,
                                             WaitDesc wait, UpComm uc, PostDesc post) {
+  __shared__ Real stage[256];
   const int t = threadIdx.x, x = t & 7, y = t >> 3;
   comm_wait_cta(wait);
   void *const *fp = nullptr;
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(TPB) k_up(LevelView lv, const int *__restrict_
       ub[k * 64 + t] = v[k];
     }
     if (fp)
-      push_faces<Real>(uc.bsend + (size_t)b * 6, fp, v, t, x, y);
+      push_faces_staged<Real>(uc.bsend + (size_t)b * 6, fp, v, t, x, y, stage);
   }
   comm_post_at_exit(post);
 }

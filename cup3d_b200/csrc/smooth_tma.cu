@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(TPB, UPF ? 10 : 12)
     if (COMM && i < fc.nbnd) {
       // push the new boundary planes to the neighbours' owners (plane order as load_halo expects)
       void *const *fp = ((seq0 + 1) & 1) ? fc.fptr1 : fc.fptr0;
-      push_faces<Real>(fc.bsend + (size_t)b * 6, fp, v, t, x, y);
+      push_faces_staged<Real>(fc.bsend + (size_t)b * 6, fp, v, t, x, y, ex);  // ex: the transposes are done
       if (i + G >= fc.nbnd) {
         // that was this CTA's last boundary block: retire them; whoever retires the last one of
         // the whole grid publishes the new sequence number to the peers

@@ -19,14 +19,14 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def connect(rank, world, boot):
+def connect(rank, world, boot, real_bytes=8):
     """-> Context of this rank on its device, communicator initialised.  boot = ("nccl", id) or ("host", port)"""
     import torch
     import cup3d_b200
     from cup3d_b200 import capi
     dev = rank % torch.cuda.device_count()
     torch.cuda.set_device(dev)
-    ctx = cup3d_b200.Context(dev, 8)
+    ctx = cup3d_b200.Context(dev, real_bytes)
     if boot[0] == "nccl":
         ctx.comm_init(rank, world, boot[1])
     else:
@@ -260,3 +260,72 @@ def test_multi_level_mesh_across_ranks(built, name, world, kind):
     assert relerr(full["advdiff"][:, 2:5], c.g["advdiff"][:, 0:3]) < 1e-12
     assert relerr(full["proj"][:, 1], c.g["proj_step5"][:, 0]) < 1e-7
     assert relerr(full["proj"][:, 2:5], c.g["proj_step5"][:, 1:4]) < 1e-9
+
+
+def worker_sphere(rank, world, boot, rbytes, coarse, q):
+    """a synthetic multi-level mesh (spherical-shell refinement, the bench's AMR mesh in small) split over
+    `world` ranks (world == 1: the single-rank run the others are compared with)"""
+    if coarse is not None:
+        os.environ["CUP_COARSE_BLOCKS"] = str(coarse)
+    sys.path.insert(0, ROOT)
+    import torch
+    import cup3d_b200
+    from cup3d_b200 import capi, mesh
+    gib, grb = mesh.amr_blocks(0, 2, mesh.sphere_shell((0.5, 0.5, 0.5), 0.2, 0.5), bpd=(8, 8, 8))
+    owner = capi.split_owner(len(gib), world)
+    mine = np.nonzero(owner == rank)[0]
+    ctx = connect(rank, world, boot, rbytes) if world > 1 else cup3d_b200.Context(0, rbytes)
+    ctx.mesh_upload(gib[mine], grb[mine], (8, 8, 8), 3)
+    X, Y, Z = mesh.cell_centers(gib[mine], grb[mine])
+    n = len(mine)
+    h = grb[mine][:, 0][:, None, None, None]
+    rhs = (h ** 3 * (np.cos(np.pi * X) * np.cos(2 * np.pi * Y) * np.cos(3 * np.pi * Z) +
+                     0.1 * np.sin(9 * np.pi * X) * np.sin(7 * np.pi * Y))).reshape(n, 512)
+    st = np.zeros((n, 9, 512))
+    st[:, 2] = (np.sin(2 * np.pi * X) * np.cos(2 * np.pi * Y)).reshape(n, 512)
+    st[:, 3] = (-np.cos(2 * np.pi * X) * np.sin(2 * np.pi * Y)).reshape(n, 512)
+    st[:, 4] = (0.1 * np.sin(2 * np.pi * Z)).reshape(n, 512)
+    tol = dict(ptol=1e-9, ptol_rel=1e-10) if rbytes == 8 else dict(ptol=1e-4, ptol_rel=1e-3)
+    ctx.set_params(dt=2e-4, nu=1e-3, uinf=(0.0, 0.0, 0.0), step=5, mean_constraint=2, **tol)
+    out = {}
+    out["vc"] = ctx.mg_vcycle(np.ascontiguousarray(rhs))
+    out["vc2"] = ctx.mg_vcycle(np.ascontiguousarray(rhs))
+    out["op"] = ctx.pois_op(np.ascontiguousarray(rhs))
+    st = np.ascontiguousarray(st)
+    its = []
+    ctx.state_h2d(st)
+    for _ in range(3):
+        ctx.advdiff()
+        its.append(ctx.projection().iterations)
+    r = np.zeros_like(st)
+    ctx.state_d2h(r)
+    out["vel"] = r[:, 2:5]
+    out["its"] = np.array(its)
+    q.put((rank, mine, out))
+    if world > 1:
+        disconnect(ctx, boot)
+    else:
+        ctx.close()
+
+
+@pytest.mark.parametrize("rbytes,world,coarse", [(8, 3, None), (8, 4, 0), (4, 4, None)])
+def test_sphere_mesh_ranks_agree_with_one_rank(built, rbytes, world, coarse):
+    """the multi-rank run (default coarse-level threshold and all-levels-distributed) reproduces the
+    single-rank run on a 3-level, ~4000-block mesh: V-cycle (eager and replayed), operator, three full time
+    steps and their Krylov iteration counts -- fp64 to rounding, fp32 to single-precision rounding"""
+    one = run_ranks(worker_sphere, 1, (("host", 0), rbytes, coarse))
+    got = run_ranks(worker_sphere, world, (make_boot("host"), rbytes, coarse))
+    ref = one[0][2]
+    ntot = len(one[0][1])
+    full = {}
+    for rank, mine, out in got:
+        for k, v in out.items():
+            if k == "its":
+                assert np.array_equal(v, ref["its"]) or rbytes == 4, (v, ref["its"])
+                continue
+            full.setdefault(k, np.zeros((ntot,) + v.shape[1:]))[mine] = v
+    t_vc, t_op, t_vel = (1e-11, 1e-12, 1e-8) if rbytes == 8 else (2e-4, 2e-5, 2e-3)
+    assert relerr(full["vc"], ref["vc"]) < t_vc
+    assert relerr(full["vc2"], ref["vc"]) < t_vc
+    assert relerr(full["op"], ref["op"]) < t_op
+    assert relerr(full["vel"], ref["vel"]) < t_vel
