@@ -117,8 +117,9 @@ def test_fp32_against_float_reference(built, name):
         ctx.close()
         print("fp32 vs Real=float reference, %s: %s" % (name, {k: "%.2e" % v for k, v in e.items()}))
         # float epsilon 6e-8; a V-cycle amplifies rounding by the conditioning of ~100 smoothing sweeps
-        assert e["op"] < 5e-6 and e["advdiff"] < 5e-6
-        assert e["vcycle"] < 5e-5
-        assert e["proj_v"] < 1e-4 and e["proj_p"] < 5e-3  # both solves stop at the same relative residual 1e-4
+        # measured on the B200 (r02): vcycle 1.0-1.2e-6, op <= 1.8e-7, advdiff 1.2e-7, proj_p 1.4-1.9e-6, proj_v 2.6-5.2e-7
+        assert e["op"] < 1e-6 and e["advdiff"] < 1e-6
+        assert e["vcycle"] < 1e-5
+        assert e["proj_v"] < 1e-5 and e["proj_p"] < 5e-5  # both solves stop at the same relative residual 1e-4
     finally:
         shutil.rmtree(d, ignore_errors=True)
