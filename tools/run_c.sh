@@ -6,6 +6,7 @@ mkdir -p gpurun_out /tmp/rep
 tail -c 1500 gpurun_out/bench_c.json
 B="python bench.py --no-parity --no-sweeps --no-amr --no-cpu"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/r02_launches.csv $B --steps 2 --warmup 1 > /dev/null 2>&1
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 2600 --csv --log-file gpurun_out/r02_launches_amr.csv python bench.py --config amr --steps 1 --warmup 1 > /dev/null 2>&1
 cap() {  # name kernel-regex skip command...
   local name=$1 re=$2 skip=$3; shift 3
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:$re -s $skip -c 1 -o /tmp/rep/$name -f "$@" > /dev/null 2>&1
