@@ -960,6 +960,12 @@ bool comm_fused_desc(CupCtx *c, Level &v, FusedComm *out) {
   out->nbnd = (int)v.bnd.size();
   out->err = c->h_err;
   out->code = 1 + v.xid * 4 + K_FACE;
+  {
+    // how boundary planes leave the SM: 2 = TMA bulk stores from a shared staging area (default),
+    // 1 = coalesced 64-element stores of the CTA, 0 = each thread's own words (CUP_PUSH, diagnostics)
+    static int mode = getenv("CUP_PUSH") ? atoi(getenv("CUP_PUSH")) : 2;
+    out->push_mode = mode;
+  }
   return true;
 }
 

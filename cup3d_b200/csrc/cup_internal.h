@@ -130,6 +130,9 @@ struct Level {
   // the fast (TMA) kernels, the others the generic ghost fill
   std::vector<int> reg, irr, par_reg, par_irr;
   int *d_reg = nullptr, *d_irr = nullptr, *d_par_reg = nullptr, *d_par_irr = nullptr;
+  // leaf context: the regular blocks once more, grouped by level (one h per launch of the fast operator kernel)
+  std::vector<std::vector<int>> reg_by_level;
+  std::vector<int *> d_reg_by_level;
 };
 
 // pure-host result of the topology build (mesh.cpp); also what the CPU tests inspect

@@ -816,6 +816,8 @@ void free_mesh(CupCtx *c) {
     cudaFree(v.d_bijk);
     cudaFree(v.d_hkeys);
     cudaFree(v.d_hvals);
+    for (int *p : v.d_reg_by_level)
+      cudaFree(p);
     cudaFree(v.d_blk_sslot);
     cudaFree(v.d_blk_skind);
     cudaFree(v.d_blk_rslot);
@@ -928,6 +930,12 @@ int build_mesh(CupCtx *c, const CupBlk *gblk, long long G, const int *owner, con
     }
     CUP_TRY(upload(&v.d_reg, v.reg));
     CUP_TRY(upload(&v.d_irr, v.irr));
+    v.reg_by_level.assign((size_t)c->top + 1, std::vector<int>());
+    for (int k : v.reg)
+      v.reg_by_level[(size_t)c->blk[(size_t)v.act[(size_t)k]].level].push_back(k);
+    v.d_reg_by_level.assign((size_t)c->top + 1, nullptr);
+    for (int L = 0; L <= c->top; L++)
+      CUP_TRY(upload(&v.d_reg_by_level[(size_t)L], v.reg_by_level[(size_t)L]));
     CUP_TRY(upload(&v.d_blk_sslot, v.blk_sslot));
     CUP_TRY(upload(&v.d_blk_skind, v.blk_skind));
     CUP_TRY(upload(&v.d_blk_rslot, v.blk_rslot));

@@ -205,13 +205,14 @@ struct UpComm {
   const int *bsend = nullptr;                        // [nact][6] face-send entry or -1 (null: no face push)
   void *const *fptr0 = nullptr, *const *fptr1 = nullptr;
   const unsigned long long *face_seq = nullptr;      // parity of the exchange being posted
+  int push_mode = 2;                                 // as FusedComm::push_mode
 };
 
 template <typename Real>
 __global__ void __launch_bounds__(TPB) k_up(LevelView lv, const int *__restrict__ pslot, const int *__restrict__ oct,
                                             SlotVec<Real> u, SlotVec<Real> us, const Real *__restrict__ precv,
                                             WaitDesc wait, UpComm uc, PostDesc post) {
-  __shared__ Real stage[256];
+  __shared__ __align__(128) Real stage[384];
   const int t = threadIdx.x, x = t & 7, y = t >> 3;
   comm_wait_cta(wait);
   void *const *fp = nullptr;
@@ -240,9 +241,17 @@ __global__ void __launch_bounds__(TPB) k_up(LevelView lv, const int *__restrict_
       v[k] = ub[k * 64 + t] + d[k >> 1];
       ub[k * 64 + t] = v[k];
     }
-    if (fp)
-      push_faces_staged<Real>(uc.bsend + (size_t)b * 6, fp, v, t, x, y, stage);
+    if (fp) {
+      if (uc.push_mode == 2)
+        push_faces_tma<Real>(uc.bsend + (size_t)b * 6, fp, v, t, x, y, stage);
+      else if (uc.push_mode == 1)
+        push_faces_staged<Real>(uc.bsend + (size_t)b * 6, fp, v, t, x, y, stage);
+      else
+        push_faces<Real>(uc.bsend + (size_t)b * 6, fp, v, t, x, y);
+    }
   }
+  if (fp && uc.push_mode == 2 && t == 0)
+    push_tma_drain();  // every bulk store of this CTA has completed before it reports itself retired
   comm_post_at_exit(post);
 }
 
@@ -752,6 +761,7 @@ bottom_done:
         uc.fptr0 = fc.fptr0;
         uc.fptr1 = fc.fptr1;
         uc.face_seq = fc.seq;
+        uc.push_mode = fc.push_mode;
         upost = comm_post_desc(c, v, COMM_FACE);
       }
       if (!v.act.empty()) {
@@ -835,7 +845,25 @@ int pois_op_t(CupCtx *c, const Real *d_in, Real *d_out) {
   // stencil_run(&st_lhs / &st_mg, list, n): only the listed blocks (cup_stencil_run)
   const int *sub = c->run_nsub >= 0 ? c->run_sub : nullptr;
   const int nsub = c->run_nsub >= 0 ? c->run_nsub : (int)v.act.size();
-  if (!c->leaf_uniform)  // k_lhs + fc_fill on all leaves, per-block h
+  if (!c->leaf_uniform && !sub && smooth_use_tma() && amr_split() && !v.d_reg_by_level.empty()) {
+    // k_lhs + fc_fill on all leaves: blocks whose six neighbours are same-level leaves or walls go through the
+    // TMA-staged operator, level by level (one h per launch); interface blocks through the generic ghost fill
+    // with its flux correction
+    for (size_t L = 0; L < v.reg_by_level.size(); L++) {
+      const std::vector<int> &lst = v.reg_by_level[L];
+      if (lst.empty())
+        continue;
+      const Real hl = (Real)c->blk[(size_t)v.act[(size_t)lst[0]]].h;
+      CUP_TRY(apply_tma_launch<Real>(c, view(v), v.d_reg_by_level[L], (int)lst.size(), u, o, us, hl, shift,
+                                     hl * hl * hl, false));
+      c->launches++;
+    }
+    if (!v.irr.empty())
+      CUP_TRY(apply_amr_launch<Real>(c, view(v), v.d_irr, (int)v.irr.size(), u, o, us, h, v.d_hblk, shift,
+                                     c->no_flux_correction ? 0 : 2));
+    else
+      c->launches--;
+  } else if (!c->leaf_uniform)  // all leaves (or a caller's list) through the generic kernel, per-block h
     CUP_TRY(apply_amr_launch<Real>(c, view(v), sub, nsub, u, o, us, h, v.d_hblk, shift,
                                    c->no_flux_correction ? 0 : 2));
   else if (smooth_use_tma())

@@ -270,6 +270,8 @@ __global__ void __launch_bounds__(TPB, UPF ? 10 : 12)
       for (int k = 0; k < 8; k++)
         v[k] = invh * ((v[k] - q0) - h * g[k]);
     }
+    if (COMM && fc.push_mode == 2 && t == 0)  // ex doubles as the staging area of the bulk-store push:
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // its last reads are done before fdm_solve rewrites it
     __syncthreads();  // stage fully consumed
     if (t == 0 && more)
       issue(nslot, nnb, nui);
@@ -283,10 +285,18 @@ __global__ void __launch_bounds__(TPB, UPF ? 10 : 12)
     if (COMM && i < fc.nbnd) {
       // push the new boundary planes to the neighbours' owners (plane order as load_halo expects)
       void *const *fp = ((seq0 + 1) & 1) ? fc.fptr1 : fc.fptr0;
-      push_faces_staged<Real>(fc.bsend + (size_t)b * 6, fp, v, t, x, y, ex);  // ex: the transposes are done
+      // ex is free: the transposes are done
+      if (fc.push_mode == 2)
+        push_faces_tma<Real>(fc.bsend + (size_t)b * 6, fp, v, t, x, y, ex);
+      else if (fc.push_mode == 1)
+        push_faces_staged<Real>(fc.bsend + (size_t)b * 6, fp, v, t, x, y, ex);
+      else
+        push_faces<Real>(fc.bsend + (size_t)b * 6, fp, v, t, x, y);
       if (i + G >= fc.nbnd) {
         // that was this CTA's last boundary block: retire them; whoever retires the last one of
         // the whole grid publishes the new sequence number to the peers
+        if (fc.push_mode == 2 && t == 0)
+          push_tma_drain();  // the bulk stores of this CTA's boundary blocks have completed
         __threadfence_system();
         __syncthreads();
         if (t == 0) {

@@ -2,6 +2,8 @@
 # 1-GPU evidence run: the complete bench line, the ncu launch list and full captures summarised ON the box
 # (gpurun brings back at most 64 MiB: only the JSON summaries and one report travel)
 mkdir -p gpurun_out /tmp/rep
+(timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_amr.py tests/test_gpu_poisson.py tests/test_gpu_fp32.py -q 2>&1 | tail -12) > gpurun_out/tc.log 2>&1
+tail -4 gpurun_out/tc.log
 (time python bench.py) > gpurun_out/bench_c.json 2> gpurun_out/bench_c.err
 tail -c 1500 gpurun_out/bench_c.json
 B="python bench.py --no-parity --no-sweeps --no-amr --no-cpu"
