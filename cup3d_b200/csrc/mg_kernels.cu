@@ -205,7 +205,7 @@ struct UpComm {
   const int *bsend = nullptr;                        // [nact][6] face-send entry or -1 (null: no face push)
   void *const *fptr0 = nullptr, *const *fptr1 = nullptr;
   const unsigned long long *face_seq = nullptr;      // parity of the exchange being posted
-  int push_mode = 2;                                 // as FusedComm::push_mode
+  int push_mode = 1;                                 // as FusedComm::push_mode
 };
 
 template <typename Real>

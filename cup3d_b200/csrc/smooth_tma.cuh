@@ -25,7 +25,7 @@ struct FusedComm {
   int nbnd;
   int *err;                            // host-visible error word (comm_dev.cuh)
   int code;
-  int push_mode;                       // 0: plain stores, 1: staged coalesced stores, 2: TMA bulk stores (default)
+  int push_mode;                       // 0: plain stores, 1: staged coalesced stores (default), 2: TMA bulk stores
 };
 
 // Fused prolongation (mg_up/mg_up2, main.c:4787-4807): the first post-smoothing sweep of a level
