@@ -194,6 +194,7 @@ struct CupCtx {
   const void *adv_rk = nullptr;  // cup::AdvRk of the stage being swept (advdiff_t -> stencil_t), else null
   void *graph_cache = nullptr;  // captured V-cycles keyed by (in, out) (mg_kernels.cu)
   void *tma_cache = nullptr;    // tensor-map cache (smooth_tma.cu)
+  long long tma_extra_rows = 0; // > 0: blocks behind the `extra` pointer of the next face maps (leaf-context ghost scratch)
   bool no_flux_correction = false;  // st_mg on the leaves (stencil_apply(CUP_ST_MG)): k_mg has no flux faces
   void *obst = nullptr;         // cup::Obstacles (obstacle.cu)
   void *io_buf = nullptr;       // io_dump packing: 5 floats per cell (allocated on first use)

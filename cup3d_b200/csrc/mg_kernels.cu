@@ -7,6 +7,7 @@
 // All kernels are HBM-bandwidth bound by design (no dense contraction on this
 // path, tensor cores unused).  Algorithmic traffic per cell: smooth 3 Reals
 // (read u, f; write u'), down 2.25, tau 4 per coarse cell, up 2.25.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <map>
@@ -852,15 +853,23 @@ int pois_op_t(CupCtx *c, const Real *d_in, Real *d_out) {
     // k_lhs + fc_fill on all leaves: blocks whose six neighbours are same-level leaves or walls go through the
     // TMA-staged operator, level by level (one h per launch); interface blocks through the generic ghost fill
     // with its flux correction
+    // the ghost scratch behind u.extra holds max(leaf ghosts, nslot - nblk + 1) blocks (capi.cu:alloc_state):
+    // the face maps must cover all of it (a ghost slot beyond the map's extent would read as zeros)
+    c->tma_extra_rows = std::max<long long>(c->leafv.nghost, c->nslot - c->nblk + 1);
     for (size_t L = 0; L < v.reg_by_level.size(); L++) {
       const std::vector<int> &lst = v.reg_by_level[L];
       if (lst.empty())
         continue;
       const Real hl = (Real)c->blk[(size_t)v.act[(size_t)lst[0]]].h;
-      CUP_TRY(apply_tma_launch<Real>(c, view(v), v.d_reg_by_level[L], (int)lst.size(), u, o, us, hl, shift,
-                                     hl * hl * hl, false));
+      const int rc = apply_tma_launch<Real>(c, view(v), v.d_reg_by_level[L], (int)lst.size(), u, o, us, hl, shift,
+                                            hl * hl * hl, false);
+      if (rc != CUP_OK) {
+        c->tma_extra_rows = 0;
+        return rc;
+      }
       c->launches++;
     }
+    c->tma_extra_rows = 0;
     if (!v.irr.empty())
       CUP_TRY(apply_amr_launch<Real>(c, view(v), v.d_irr, (int)v.irr.size(), u, o, us, h, v.d_hblk, shift,
                                      c->no_flux_correction ? 0 : 2));

@@ -409,7 +409,9 @@ int tma_slab_maps(CupCtx *c, const void *leaf, CUtensorMap out[2]) {
 }
 
 int tma_face_maps(CupCtx *c, const void *leaf, const void *extra, CUtensorMap out[4]) {
-  const long long nleaf = c->nblk, nx = c->nslot - c->nblk + 1;
+  // the extra part normally holds the multigrid parents and ghosts (nslot - nblk + 1 blocks); the leaf
+  // context's ghost scratch of a flat vector can be larger (c->tma_extra_rows, set by its caller)
+  const long long nleaf = c->nblk, nx = c->tma_extra_rows > 0 ? c->tma_extra_rows : c->nslot - c->nblk + 1;
   // a part that holds no blocks of this vector still needs a valid (unused) descriptor
   const void *lb = leaf ? leaf : extra;
   const void *eb = extra ? extra : leaf;
