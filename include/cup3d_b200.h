@@ -138,7 +138,11 @@ int cup_stencil_run(CupCtx *ctx, CupStencilId id, const long long *list, long lo
 /* flat-vector operators, host buffers (H2D + compute + D2H, synchronous) */
 int cup_pois_op(CupCtx *ctx, const double *h_in, double *h_out);
 int cup_mg_vcycle(CupCtx *ctx, const double *h_in, double *h_out);
-/* same on device-resident vectors of Real (asynchronous on the ctx stream) */
+/* same on device-resident vectors of Real (asynchronous on the ctx stream).  The V-cycle is captured
+ * into a CUDA graph per (d_in, d_out) pair and replayed; a graph only stores the two addresses and the
+ * mesh's tables, so it stays valid if the caller frees and re-allocates a vector at the same address, and
+ * every graph is dropped when the mesh changes (cup_mesh_upload / cup_mesh_adapt).  At most 128 pairs are
+ * kept. */
 int cup_pois_op_dev(CupCtx *ctx, const void *d_in, void *d_out);
 int cup_mg_vcycle_dev(CupCtx *ctx, const void *d_in, void *d_out);
 /* sum_i a_i b_i / h_i^3 (pois_dot, main.c:4854); synchronous */
