@@ -484,7 +484,7 @@ def run_ours(args, rank, world, local_rank):
         try:
             torch.cuda.empty_cache()
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--config", "amr", "--steps", "3",
-                                "--warmup", "1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=420)
+                                "--warmup", "2"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
             got = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
             line["amr_step"] = json.loads(got[-1]) if got else {"error": r.stderr[-300:]}
         except Exception as ex:
