@@ -575,6 +575,7 @@ def run_amr(args, rank, world, local_rank):
     l0 = ctx.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     its, vcs = 0, 0
+    its_list = []  # a step that runs into the solver's 1000-iteration cap (fp32 residual floor) shows up here
     marks = []  # (before advdiff, between, after projection) of every step: the two halves of the step
     e0.record(stream)
     for _ in range(args.steps):
@@ -587,6 +588,7 @@ def run_amr(args, rank, world, local_rank):
         marks.append(m)
         its += info.iterations
         vcs += info.vcycles
+        its_list.append(int(info.iterations))
     e1.record(stream)
     barrier()
     ms = maxr(e0.elapsed_time(e1))
@@ -633,6 +635,7 @@ def run_amr(args, rank, world, local_rank):
                    "l2_policy": "inputs larger than L2 (%.2f GB per field per rank)" % (n * 512 * rbytes / 1e9),
                    "parallelism": "%d rank(s); coarse-fine interfaces across ranks through ghost blocks" % world},
         "krylov_iterations_per_step": its / args.steps, "vcycles_per_step": vcs / args.steps,
+        "krylov_iterations": its_list,
         "phases_ms": {k: round(v, 3) for k, v in phase_ms.items()},
         "roofline": {"bound": "hbm", "kernel": "whole step, algorithmic traffic of its two dominant parts",
                      "vcycle_bytes": vc_bytes, "advdiff_bytes": adv_bytes,
