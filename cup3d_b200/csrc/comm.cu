@@ -2,9 +2,10 @@
 //
 // Replaces the reference's MPI layer on the hot path:
 //   tree_sync      (Allgatherv of all blocks, main.c:2928)   -> comm_gather_blocks
-//   halo_sync      (whole 8^3 blocks by Alltoallv, :3101)    -> halo_exchange: device-side
-//                                                               packing of 8x8 FACES + grouped
-//                                                               ncclSend/ncclRecv per peer
+//   halo_sync      (whole 8^3 blocks by Alltoallv, :3101)    -> halo_exchange: 8x8 FACES stored into
+//                                                               the neighbours' receive windows
+//                                                               (ghost BLOCKS only where a level has
+//                                                               coarse-fine interfaces across ranks)
 //   mg_down/mg_up  (Alltoallv of 128 / 64 Reals, :4754,:4791)-> restrict_exchange / prolong_exchange
 //   MPI_Allreduce  (:4295, :4820, :4860, ...)                -> ncclAllReduce on device scalars
 // Everything is stream-ordered on the context's stream; the host never waits.
@@ -190,12 +191,16 @@ static int allgather_bytes(CupCtx *c, const void *send, void *recv, size_t bytes
   }
   char *d;
   CUP_CUDA(cudaMalloc((void **)&d, bytes * (size_t)(R + 1)));
-  CUP_CUDA(cudaMemcpyAsync(d + bytes * R, send, bytes, cudaMemcpyHostToDevice, c->stream));
-  CUP_NCCL(g_nccl.AllGather(d + bytes * R, d, bytes, ncclChar, cm->nccl, c->stream));
-  CUP_CUDA(cudaMemcpyAsync(recv, d, bytes * (size_t)R, cudaMemcpyDeviceToHost, c->stream));
-  CUP_CUDA(cudaStreamSynchronize(c->stream));
+  auto run = [&]() -> int {
+    CUP_CUDA(cudaMemcpyAsync(d + bytes * R, send, bytes, cudaMemcpyHostToDevice, c->stream));
+    CUP_NCCL(g_nccl.AllGather(d + bytes * R, d, bytes, ncclChar, cm->nccl, c->stream));
+    CUP_CUDA(cudaMemcpyAsync(recv, d, bytes * (size_t)R, cudaMemcpyDeviceToHost, c->stream));
+    CUP_CUDA(cudaStreamSynchronize(c->stream));
+    return CUP_OK;
+  };
+  const int rc = run();
   cudaFree(d);
-  return CUP_OK;
+  return rc;
 }
 
 int comm_check_error(CupCtx *c) {
@@ -320,14 +325,17 @@ int comm_allreduce(CupCtx *c, int first, int n) { return allreduce_impl(c, first
 // ===========================================================================
 // Exchanges.  Two transports behind one post/wait interface:
 //
-//  * one-sided (default): the producer's pack kernel stores straight into the
-//    consumer's receive window over NVLink (CUDA-IPC mapped peer memory), a
-//    1-CTA signal kernel bumps the level's sequence number and writes it into
-//    the peers' flag words, and the consumer runs a 1-CTA wait kernel before
-//    its boundary blocks.  No NCCL kernel has to find room on SMs that the
-//    persistent sweep kernels occupy, so the exchange really overlaps the
-//    interior sweep.  Face areas are double buffered by sequence parity.
-//    Everything is replayable from a CUDA graph: epochs live in device memory.
+//  * one-sided (default): the producer kernel stores straight into the
+//    consumer's receive window over NVLink (CUDA-IPC mapped peer memory); its
+//    LAST CTA to retire bumps the (context, kind) sequence number and writes it
+//    into the peers' flag words (comm_dev.cuh: comm_post_at_exit), and the
+//    consumer kernel waits for those flags itself before its first read of
+//    received data (comm_wait_cta) -- no signal or wait kernels in between
+//    (k_signal / k_wait below remain for posts and waits that have no kernel
+//    to ride on).  No NCCL kernel has to find room on SMs that the persistent
+//    sweep kernels occupy, so the exchange really overlaps the interior sweep.
+//    Areas are double buffered by sequence parity.  Everything is replayable
+//    from a CUDA graph: epochs live in device memory.
 //  * NCCL (CUP_P2P=0 or IPC unavailable): pack to a staging buffer, grouped
 //    ncclSend/ncclRecv per peer.
 // ===========================================================================
