@@ -31,3 +31,18 @@ def test_rank_other_than_zero_of_the_reference_arm_does_nothing(built):
                         "--cpu-level", "2", "--steps", "1", "--warmup", "0"], stdout=subprocess.PIPE,
                        stderr=subprocess.PIPE, text=True, timeout=120, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_cited_evidence_files_exist():
+    """every profiles/ file that DESIGN.md, README.md or profiles/README.md cites by name is committed"""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    have = {os.path.basename(p) for p in glob.glob(os.path.join(root, "profiles", "*"))}
+    missing = []
+    for doc in ("DESIGN.md", "README.md", os.path.join("profiles", "README.md")):
+        text = open(os.path.join(root, doc)).read()
+        for name in set(re.findall(r"`(?:profiles/)?(r0\d_[A-Za-z0-9_.\-]+\.(?:json|jsonl|csv|txt|tsv))`", text)):
+            if name not in have:
+                missing.append((doc, name))
+    assert not missing, missing
